@@ -1,0 +1,146 @@
+"""ctypes binding of libespic_b200.so (C ABI in include/espic_b200.h).
+
+There is exactly one compute path: the sm_100a kernels in this shared library.  If the
+library is missing or no Blackwell GPU is present every operator raises; nothing falls back
+to CPU arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libespic_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+c_void_p, c_int, c_float, c_double = C.c_void_p, C.c_int, C.c_float, C.c_double
+P = c_void_p  # every array argument is passed as a raw device (or host) address
+
+# name -> (restype, argtypes); mirrors include/espic_b200.h one to one
+SIGNATURES = {
+    "espic_abi_version": (c_int, []),
+    "espic_create": (c_int, [C.POINTER(c_void_p), c_int]),
+    "espic_destroy": (None, [c_void_p]),
+    "espic_set_stream": (c_int, [c_void_p, c_void_p]),
+    "espic_last_error": (C.c_char_p, [c_void_p]),
+    "espic_status": (c_int, [c_void_p, C.POINTER(c_int)]),
+    "espic_device_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
+    "espic_launch_count": (C.c_longlong, [c_void_p]),
+    "espic_timing_enable": (c_int, [c_void_p, c_int]),
+    "espic_timing_read": (c_int, [c_void_p, C.POINTER(c_double), C.POINTER(c_int), C.POINTER(c_double)]),
+    "espic_move_particles": (c_int, [c_void_p, P, P, P, c_float, c_float, c_float, c_int, P, P, P, P,
+                                     c_float, c_int, c_int, c_int, c_int, c_int]),
+    "espic_move_particles_dev": (c_int, [c_void_p, P, P, P, c_float, c_float, c_float, P, P, P, P, P,
+                                         c_float, c_int, c_int, c_int, c_int, c_int]),
+    "espic_shift_velocities": (c_int, [c_void_p, P, c_int, c_int, c_double]),
+    "espic_poisson_solve": (c_int, [c_void_p, P, P, P, c_float, P, c_float, c_float, c_int, c_int, c_int]),
+    "espic_prepare_charge": (c_int, [c_void_p, P, P, P, c_int, c_int, c_int, c_int]),
+    "espic_inject_particles": (c_int, [c_void_p, c_int, P, c_int, c_float, c_float, P, P, c_float, c_int,
+                                       P, P, c_int, P, P, P, P]),
+    "espic_seed": (c_int, [c_void_p, C.c_ulong]),
+    "espic_draw_velocities": (c_int, [c_void_p, c_int, c_float, c_float, P]),
+    "espic_genrand": (c_int, [c_void_p, c_int, P]),
+    "espic_field_filter": (c_int, [c_void_p, c_int, P, P, c_float, c_int, P, P]),
+    "espic_hole_position": (c_int, [c_void_p, c_int, P, P, c_double, c_float, c_int, P, P, P]),
+    "espic_phase_space_histogram": (c_int, [c_void_p, P, P, c_int, P, c_int, c_float, c_float, c_float,
+                                            c_float, c_int, c_int, P]),
+    # reference-named host-pointer drop-ins
+    "move_particles_c": (None, [P, P, P, c_float, c_float, c_float, c_int, P, P, P, P, c_float, c_int,
+                                c_int, c_int, c_int, c_int]),
+    "poisson_solve_c": (None, [P, P, P, c_float, P, c_float, c_float, c_int, c_int, c_int]),
+    "draw_velocities_c": (None, [c_int, c_float, c_float, P]),
+    "sgenrand": (None, [C.c_ulong]),
+    "genrand": (c_float, []),
+    "electric_field_filter_c": (None, [c_int, P, P, c_float, c_int, P, P]),
+    "histogram2d_uniform_grid_c": (None, [P, P, c_float, c_float, c_float, c_float, c_int, c_int, c_int, P]),
+    "inject_particles_c": (None, [c_int, P, c_int, c_float, c_float, P, P, c_float, c_int, P, P, c_int,
+                                  P, P, P, P]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libespic_b200.so failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library with argument types declared.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C espic_hole_tracking_b200/csrc`). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library out of sync
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+class EspicError(RuntimeError):
+    pass
+
+
+class Context:
+    """Owns one espic_ctx (device scratch + the stream kernels are enqueued on)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        handle = c_void_p()
+        rc = self._lib.espic_create(C.byref(handle), int(device))
+        if rc != 0:
+            raise EspicError(
+                f"espic_create(device={device}) failed with code {rc}: a Blackwell (sm_100) GPU is "
+                "required; this package has no CPU path")
+        self.handle = handle
+        self.device = int(device)
+
+    def check(self, rc: int, what: str = "") -> None:
+        if rc != 0:
+            msg = self._lib.espic_last_error(self.handle).decode(errors="replace")
+            raise EspicError(f"{what} failed (code {rc}): {msg}")
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self.check(self._lib.espic_set_stream(self.handle, c_void_p(cuda_stream)), "espic_set_stream")
+
+    def status(self) -> int:
+        st = c_int(0)
+        self.check(self._lib.espic_status(self.handle, C.byref(st)), "espic_status")
+        return st.value
+
+    def launch_count(self) -> int:
+        return int(self._lib.espic_launch_count(self.handle))
+
+    def device_info(self):
+        a, b, c = c_int(), c_int(), c_int()
+        self.check(self._lib.espic_device_info(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sm_count": a.value, "mover_grid": b.value, "mover_block": c.value}
+
+    def timing_enable(self, on: bool = True) -> None:
+        self.check(self._lib.espic_timing_enable(self.handle, int(on)), "espic_timing_enable")
+
+    def timing_read(self):
+        mean, n, tot = c_double(), c_int(), c_double()
+        self.check(self._lib.espic_timing_read(self.handle, C.byref(mean), C.byref(n), C.byref(tot)))
+        return {"mean_ms": mean.value, "launches": n.value, "total_ms": tot.value}
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self._lib.espic_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

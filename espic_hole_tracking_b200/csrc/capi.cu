@@ -1,0 +1,542 @@
+// C ABI of libespic_b200.so (see include/espic_b200.h): context management, the espic_*
+// device-pointer operators, and the reference-named host-pointer drop-ins.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "espic_internal.cuh"
+
+namespace espic {
+
+int fail(espic_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int check_cuda(espic_ctx* ctx, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return fail(ctx, ESPIC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// Grow-only device scratch; new memory is zero-filled on the context's stream.
+int ensure(espic_ctx* ctx, Scratch& s, size_t bytes, const char* what) {
+    if (bytes <= s.bytes) return 0;
+    if (s.ptr) {
+        // the old buffer may still be in use by work queued on the stream
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "cudaStreamSynchronize");
+        cudaFree(s.ptr);
+        s.ptr = nullptr;
+        s.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, ESPIC_E_NOMEM, "cudaMalloc(%zu bytes) for %s: %s", want, what, cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(p, 0, want, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return check_cuda(ctx, e, "cudaMemsetAsync");
+    }
+    s.ptr = p;
+    s.bytes = want;
+    return 0;
+}
+
+int ensure_acc(espic_ctx* ctx, int n_points) {
+    if (n_points <= ctx->acc_len) return 0;
+    if (ctx->acc) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return check_cuda(ctx, e, "cudaStreamSynchronize");
+        cudaFree(ctx->acc);
+        ctx->acc = nullptr;
+        ctx->acc_len = 0;
+    }
+    const int len = n_points + 64;
+    cudaError_t e = cudaMalloc((void**)&ctx->acc, (size_t)len * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, ESPIC_E_NOMEM, "cudaMalloc for density accumulators: %s", cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(ctx->acc, 0, (size_t)len * sizeof(unsigned long long), ctx->stream);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "cudaMemsetAsync");
+    ctx->acc_len = len;
+    return 0;
+}
+
+static void free_scratch(Scratch& s) {
+    if (s.ptr) cudaFree(s.ptr);
+    s.ptr = nullptr;
+    s.bytes = 0;
+}
+
+}  // namespace espic
+
+using namespace espic;
+
+// carve a sub-buffer out of the staging allocation
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <class T>
+    T* take(size_t n) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += ((n * sizeof(T) + 255) / 256) * 256;
+        return p;
+    }
+};
+static size_t padded(size_t bytes) { return ((bytes + 255) / 256) * 256; }
+
+extern "C" {
+
+int espic_abi_version(void) { return ESPIC_ABI_VERSION; }
+
+int espic_create(espic_ctx** out, int device) {
+    if (!out) return ESPIC_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return ESPIC_E_NODEVICE;
+    }
+    if (device < 0 || device >= count) return ESPIC_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return ESPIC_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ESPIC_E_CUDA;
+    if (prop.major < 10) {
+        fprintf(stderr, "espic_b200: device %d is sm_%d%d; this library contains sm_100a code only\n", device,
+                prop.major, prop.minor);
+        return ESPIC_E_NODEVICE;
+    }
+    espic_ctx* ctx = new espic_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaMalloc((void**)&ctx->status, 64) != cudaSuccess || cudaMemset(ctx->status, 0, 64) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->dev_int2, 64) != cudaSuccess || cudaMemset(ctx->dev_int2, 0, 64) != cudaSuccess) {
+        delete ctx;
+        return ESPIC_E_NOMEM;
+    }
+    *out = ctx;
+    return ESPIC_OK;
+}
+
+void espic_destroy(espic_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->acc) cudaFree(ctx->acc);
+    if (ctx->status) cudaFree(ctx->status);
+    if (ctx->dev_int2) cudaFree(ctx->dev_int2);
+    free_scratch(ctx->staging);
+    free_scratch(ctx->chunk_counts);
+    free_scratch(ctx->dv_table);
+    free_scratch(ctx->solve_ws);
+    free_scratch(ctx->inject_ws);
+    free_scratch(ctx->rng_ws);
+    free_scratch(ctx->host_stage);
+    if (ctx->ev) {
+        for (int i = 0; i < ctx->ev_cap; ++i) cudaEventDestroy(ctx->ev[i]);
+        free(ctx->ev);
+    }
+    delete ctx;
+}
+
+int espic_set_stream(espic_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return ESPIC_E_ARG;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return ESPIC_OK;
+}
+
+const char* espic_last_error(espic_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int espic_status(espic_ctx* ctx, int* status_out) {
+    if (!ctx || !status_out) return ESPIC_E_ARG;
+    int st = 0;
+    ESPIC_CUDA(ctx, cudaMemcpyAsync(&st, ctx->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ESPIC_CUDA(ctx, cudaMemsetAsync(ctx->status, 0, sizeof(int), ctx->stream));
+    ESPIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *status_out = st;
+    return ESPIC_OK;
+}
+
+int espic_device_info(espic_ctx* ctx, int* sm_count, int* mover_grid, int* mover_block) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (mover_grid) *mover_grid = ctx->mover_grid;
+    if (mover_block) *mover_block = ctx->mover_block;
+    return ESPIC_OK;
+}
+
+long long espic_launch_count(espic_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int espic_timing_enable(espic_ctx* ctx, int on) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (on && !ctx->ev) {
+        ctx->ev_cap = 8192;
+        ctx->ev = (cudaEvent_t*)calloc((size_t)ctx->ev_cap, sizeof(cudaEvent_t));
+        if (!ctx->ev) return fail(ctx, ESPIC_E_NOMEM, "event array");
+        for (int i = 0; i < ctx->ev_cap; ++i) ESPIC_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    }
+    ctx->timing_on = on ? 1 : 0;
+    ctx->ev_used = 0;
+    return ESPIC_OK;
+}
+
+int espic_timing_read(espic_ctx* ctx, double* mean_ms, int* launches, double* total_ms) {
+    if (!ctx) return ESPIC_E_ARG;
+    ESPIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0.;
+    const int n = ctx->ev_used / 2;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        ESPIC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+        tot += ms;
+    }
+    if (mean_ms) *mean_ms = n ? tot / n : 0.;
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = tot;
+    ctx->ev_used = 0;
+    return ESPIC_OK;
+}
+
+// ---- (A) device-pointer operators -------------------------------------------------------------
+
+int espic_move_particles(espic_ctx* ctx, const float* grid, const float* object_mask, const float* potential,
+                         float dt, float charge_to_mass, float background_density, int largest_index,
+                         float* particles, float* density, int* empty_slots, int* current_empty_slot,
+                         float a_b, int update_position, int periodic_particles, int largest_allowed_slot,
+                         int n_points, int particle_storage_length) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !object_mask || !potential || !particles || !density || !empty_slots || !current_empty_slot)
+        return fail(ctx, ESPIC_E_ARG, "espic_move_particles: null pointer argument");
+    return launch_move(ctx, grid, object_mask, potential, dt, charge_to_mass, background_density, largest_index,
+                       nullptr, particles, density, empty_slots, current_empty_slot, a_b, update_position,
+                       periodic_particles, largest_allowed_slot, n_points, particle_storage_length);
+}
+
+int espic_move_particles_dev(espic_ctx* ctx, const float* grid, const float* object_mask, const float* potential,
+                             float dt, float charge_to_mass, float background_density,
+                             const int* largest_index_dev, float* particles, float* density, int* empty_slots,
+                             int* current_empty_slot, float a_b, int update_position, int periodic_particles,
+                             int largest_allowed_slot, int n_points, int particle_storage_length) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !object_mask || !potential || !particles || !density || !empty_slots || !current_empty_slot ||
+        !largest_index_dev)
+        return fail(ctx, ESPIC_E_ARG, "espic_move_particles_dev: null pointer argument");
+    return launch_move(ctx, grid, object_mask, potential, dt, charge_to_mass, background_density, -1,
+                       largest_index_dev, particles, density, empty_slots, current_empty_slot, a_b,
+                       update_position, periodic_particles, largest_allowed_slot, n_points,
+                       particle_storage_length);
+}
+
+int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storage_length, int largest_index,
+                           double v_b) {
+    if (!ctx || !particles) return ESPIC_E_ARG;
+    return launch_shift_velocities(ctx, particles, particle_storage_length, largest_index, v_b);
+}
+
+int espic_poisson_solve(espic_ctx* ctx, const float* grid, const float* object_mask, const float* charge,
+                        float debye_length, float* potential, float object_potential, float object_transparency,
+                        int boltzmann_electrons, int periodic_potential, int n_points) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !object_mask || !charge || !potential)
+        return fail(ctx, ESPIC_E_ARG, "espic_poisson_solve: null pointer argument");
+    return launch_poisson(ctx, grid, object_mask, charge, debye_length, potential, object_potential,
+                          object_transparency, boltzmann_electrons, periodic_potential, n_points);
+}
+
+int espic_prepare_charge(espic_ctx* ctx, float* ion_density, float* electron_density, float* charge, int n_points,
+                         int periodic, int fix_ions, int fix_electrons) {
+    if (!ctx || !ion_density || !electron_density || !charge) return ESPIC_E_ARG;
+    return launch_prepare_charge(ctx, ion_density, electron_density, charge, n_points, periodic, fix_ions,
+                                 fix_electrons);
+}
+
+int espic_inject_particles(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt,
+                           float background_density, const float* velocities, const float* uniform01, float a_b,
+                           int k, int* particles_hist, float* particles, int particle_storage_length,
+                           int* empty_slots, int* current_empty_slot, int* largest_index, float* density) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (n_inject > 0 && (!grid || !velocities || !uniform01 || !particles_hist || !particles || !empty_slots ||
+                         !current_empty_slot || !largest_index || !density))
+        return fail(ctx, ESPIC_E_ARG, "espic_inject_particles: null pointer argument");
+    return launch_inject(ctx, n_inject, grid, n_points, dt, background_density, velocities, uniform01, a_b, k,
+                         particles_hist, particles, particle_storage_length, empty_slots, current_empty_slot,
+                         largest_index, density);
+}
+
+int espic_seed(espic_ctx* ctx, unsigned long seed) { return ctx ? rng_seed(ctx, seed) : ESPIC_E_ARG; }
+
+int espic_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out) {
+    if (!ctx || (n > 0 && !v_out)) return ESPIC_E_ARG;
+    return rng_draw_velocities(ctx, n, v_th, v_d, v_out);
+}
+
+int espic_genrand(espic_ctx* ctx, int n, float* out) {
+    if (!ctx || (n > 0 && !out)) return ESPIC_E_ARG;
+    return rng_uniforms(ctx, n, out);
+}
+
+int espic_field_filter(espic_ctx* ctx, int n_points, const float* grid, const float* data, float L, int n_fine,
+                       const float* fine_mesh, float* res) {
+    if (!ctx || !grid || !data || !fine_mesh || !res) return ESPIC_E_ARG;
+    return launch_field_filter(ctx, n_points, grid, data, L, n_fine, fine_mesh, res);
+}
+
+int espic_hole_position(espic_ctx* ctx, int n_points, const float* grid, const float* potential, double dz,
+                        float L, int n_fine, const float* fine_mesh, float* scratch_res, float* position_out) {
+    if (!ctx || !grid || !potential || !fine_mesh || !scratch_res || !position_out) return ESPIC_E_ARG;
+    return launch_hole_position(ctx, n_points, grid, potential, dz, L, n_fine, fine_mesh, scratch_res,
+                                position_out);
+}
+
+int espic_phase_space_histogram(espic_ctx* ctx, const float* xs, const float* ys, int n_data, const int* tags,
+                                int tag_value, float x_min, float step_x, float y_min, float step_y,
+                                int n_bins_x, int n_bins_y, int* hist) {
+    if (!ctx || !xs || !ys || !hist) return ESPIC_E_ARG;
+    return launch_histogram(ctx, xs, ys, n_data, tags, tag_value, x_min, step_x, y_min, step_y, n_bins_x,
+                            n_bins_y, hist);
+}
+
+// ---- (B) reference-named host-pointer drop-ins -------------------------------------------------
+// One process-wide context on the current device, created on first use.  These functions
+// return void like the reference's; any failure is fatal and loud (no CPU fallback exists).
+
+static espic_ctx* g_default = nullptr;
+static std::mutex g_mutex;
+
+static espic_ctx* default_ctx() {
+    if (!g_default) {
+        int dev = 0;
+        if (const char* s = getenv("ESPIC_DEVICE")) dev = atoi(s);
+        int rc = espic_create(&g_default, dev);
+        if (rc) {
+            fprintf(stderr, "espic_b200: cannot create a context on CUDA device %d (code %d); "
+                            "this library has no CPU path\n", dev, rc);
+            abort();
+        }
+    }
+    return g_default;
+}
+
+static void die(espic_ctx* ctx, const char* where, int rc) {
+    fprintf(stderr, "espic_b200: %s failed (code %d): %s\n", where, rc, espic_last_error(ctx));
+    abort();
+}
+
+static void report_status(espic_ctx* ctx) {
+    int st = 0;
+    if (espic_status(ctx, &st)) return;
+    // same wording as the reference's printf()s, once per call instead of once per particle
+    if (st & ESPIC_ST_BAD_LEFT_INDEX) printf("bad left_index\n");
+    if (st & ESPIC_ST_STACK_OVERFLOW) printf("bad current_empty_slot\n");
+    if (st & ESPIC_ST_STACK_EMPTY) printf("no empty slots\n");
+    if (st & ESPIC_ST_BAD_INJECT_INDEX) printf("bad left_index:\n");
+    if (st & ESPIC_ST_BAD_OBJECT_MASK) printf("bad object_mask\n");
+    if (st & ESPIC_ST_SAMPLER_STALL) printf("Warning: method draw_velocities_c doesn't converge\n");
+}
+
+#define H2D(dst, src, n, T) \
+    if ((rc = check_cuda(ctx, cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, ctx->stream), "H2D"))) die(ctx, __func__, rc)
+#define D2H(dst, src, n, T) \
+    if ((rc = check_cuda(ctx, cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream), "D2H"))) die(ctx, __func__, rc)
+
+void move_particles_c(float* grid, float* object_mask, float* potential, float dt, float charge_to_mass,
+                      float background_density, int largest_index, float* particles, float* density,
+                      int* empty_slots, int* current_empty_slot, float a_b, int update_position,
+                      int periodic_particles, int largest_allowed_slot, int n_points,
+                      int particle_storage_length) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    const size_t S = (size_t)particle_storage_length, n = (size_t)n_points;
+    const size_t n_stack = (size_t)largest_allowed_slot + 1;
+    const size_t need = 4 * padded(n * 4) + padded(2 * S * 4) + padded(n_stack * 4) + 256;
+    if ((rc = ensure(ctx, ctx->host_stage, need, "host staging"))) die(ctx, __func__, rc);
+    Carver cv{(char*)ctx->host_stage.ptr};
+    float* d_grid = cv.take<float>(n);
+    float* d_mask = cv.take<float>(n);
+    float* d_phi = cv.take<float>(n);
+    float* d_den = cv.take<float>(n);
+    float* d_part = cv.take<float>(2 * S);
+    int* d_stack = cv.take<int>(n_stack);
+    int* d_top = ctx->dev_int2;
+    const size_t used = (size_t)(largest_index + 1);
+    H2D(d_grid, grid, n, float);
+    H2D(d_mask, object_mask, n, float);
+    H2D(d_phi, potential, n, float);
+    if (used) {
+        H2D(d_part, particles, used, float);
+        H2D(d_part + S, particles + S, used, float);
+    }
+    H2D(d_stack, empty_slots, n_stack, int);
+    H2D(d_top, current_empty_slot, 1, int);
+    rc = espic_move_particles(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, largest_index,
+                              d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles,
+                              largest_allowed_slot, n_points, particle_storage_length);
+    if (rc) die(ctx, __func__, rc);
+    if (used) {
+        D2H(particles, d_part, used, float);
+        D2H(particles + S, d_part + S, used, float);
+    }
+    D2H(density, d_den, n, float);
+    D2H(empty_slots, d_stack, n_stack, int);
+    D2H(current_empty_slot, d_top, 1, int);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    report_status(ctx);
+}
+
+void poisson_solve_c(float* grid, float* object_mask, float* charge, float debye_length, float* potential,
+                     float object_potential, float object_transparency, int boltzmann_electrons,
+                     int periodic_potential, int n_points) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    const size_t n = (size_t)n_points;
+    if ((rc = ensure(ctx, ctx->host_stage, 4 * padded(n * 4) + 256, "host staging"))) die(ctx, __func__, rc);
+    Carver cv{(char*)ctx->host_stage.ptr};
+    float* d_grid = cv.take<float>(n);
+    float* d_mask = cv.take<float>(n);
+    float* d_rho = cv.take<float>(n);
+    float* d_phi = cv.take<float>(n);
+    H2D(d_grid, grid, n, float);
+    H2D(d_mask, object_mask, n, float);
+    H2D(d_rho, charge, n, float);
+    H2D(d_phi, potential, n, float);
+    rc = espic_poisson_solve(ctx, d_grid, d_mask, d_rho, debye_length, d_phi, object_potential,
+                             object_transparency, boltzmann_electrons, periodic_potential, n_points);
+    if (rc) die(ctx, __func__, rc);
+    D2H(potential, d_phi, n, float);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    report_status(ctx);
+}
+
+void sgenrand(unsigned long seed) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_seed(default_ctx(), seed);
+}
+
+void draw_velocities_c(int n, float v_th, float v_d, float* v_array) {
+    if (n <= 0) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    if ((rc = ensure(ctx, ctx->host_stage, padded((size_t)n * 4) + 256, "host staging"))) die(ctx, __func__, rc);
+    float* d_v = (float*)ctx->host_stage.ptr;
+    if ((rc = espic_draw_velocities(ctx, n, v_th, v_d, d_v))) die(ctx, __func__, rc);
+    D2H(v_array, d_v, n, float);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    report_status(ctx);
+}
+
+float genrand(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    float out = 0.f;
+    float* d = (float*)(ctx->dev_int2 + 8);
+    if ((rc = espic_genrand(ctx, 1, d))) die(ctx, __func__, rc);
+    D2H(&out, d, 1, float);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    return out;
+}
+
+void electric_field_filter_c(int n_points, float* grid, float* data_array, float L, int n_fine_mesh,
+                             float* fine_mesh, float* Res) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    const size_t n = (size_t)n_points, m = (size_t)n_fine_mesh;
+    if ((rc = ensure(ctx, ctx->host_stage, 2 * padded(n * 4) + 2 * padded(m * 4) + 256, "host staging")))
+        die(ctx, __func__, rc);
+    Carver cv{(char*)ctx->host_stage.ptr};
+    float* d_grid = cv.take<float>(n);
+    float* d_data = cv.take<float>(n);
+    float* d_fine = cv.take<float>(m);
+    float* d_res = cv.take<float>(m);
+    H2D(d_grid, grid, n, float);
+    H2D(d_data, data_array, n, float);
+    H2D(d_fine, fine_mesh, m, float);
+    if ((rc = espic_field_filter(ctx, n_points, d_grid, d_data, L, n_fine_mesh, d_fine, d_res))) die(ctx, __func__, rc);
+    D2H(Res, d_res, m, float);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+}
+
+void histogram2d_uniform_grid_c(float* X, float* Y, float x_min, float step_x, float y_min, float step_y,
+                                int n_bins_x, int n_bins_y, int n_data, int* hist) {
+    if (n_data <= 0) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    const size_t n = (size_t)n_data, bins = (size_t)n_bins_x * n_bins_y;
+    if ((rc = ensure(ctx, ctx->host_stage, 2 * padded(n * 4) + padded(bins * 4) + 256, "host staging")))
+        die(ctx, __func__, rc);
+    Carver cv{(char*)ctx->host_stage.ptr};
+    float* d_x = cv.take<float>(n);
+    float* d_y = cv.take<float>(n);
+    int* d_h = cv.take<int>(bins);
+    H2D(d_x, X, n, float);
+    H2D(d_y, Y, n, float);
+    H2D(d_h, hist, bins, int);
+    rc = espic_phase_space_histogram(ctx, d_x, d_y, n_data, nullptr, 0, x_min, step_x, y_min, step_y, n_bins_x,
+                                     n_bins_y, d_h);
+    if (rc) die(ctx, __func__, rc);
+    D2H(hist, d_h, bins, int);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+}
+
+void inject_particles_c(int n_inject, float* grid, int n_points, float dt, float background_density,
+                        float* velocities, float* uniform01, float a_b, int k, int* particles_hist,
+                        float* particles, int particle_storage_length, int* empty_slots,
+                        int* current_empty_slot, int* largest_index, float* density) {
+    if (n_inject <= 0) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    int rc;
+    const size_t S = (size_t)particle_storage_length, n = (size_t)n_points, m = (size_t)n_inject;
+    const size_t need = 2 * padded(n * 4) + 2 * padded(m * 4) + padded(2 * S * 4) + 2 * padded(S * 4) + 256;
+    if ((rc = ensure(ctx, ctx->host_stage, need, "host staging"))) die(ctx, __func__, rc);
+    Carver cv{(char*)ctx->host_stage.ptr};
+    float* d_grid = cv.take<float>(n);
+    float* d_den = cv.take<float>(n);
+    float* d_vel = cv.take<float>(m);
+    float* d_uni = cv.take<float>(m);
+    float* d_part = cv.take<float>(2 * S);
+    int* d_stack = cv.take<int>(S);
+    int* d_hist = cv.take<int>(S);
+    int* d_top = ctx->dev_int2;
+    int* d_last = ctx->dev_int2 + 1;
+    H2D(d_grid, grid, n, float);
+    H2D(d_den, density, n, float);
+    H2D(d_vel, velocities, m, float);
+    H2D(d_uni, uniform01, m, float);
+    H2D(d_part, particles, 2 * S, float);
+    H2D(d_stack, empty_slots, S, int);
+    H2D(d_hist, particles_hist, S, int);
+    H2D(d_top, current_empty_slot, 1, int);
+    H2D(d_last, largest_index, 1, int);
+    rc = espic_inject_particles(ctx, n_inject, d_grid, n_points, dt, background_density, d_vel, d_uni, a_b, k,
+                                d_hist, d_part, particle_storage_length, d_stack, d_top, d_last, d_den);
+    if (rc) die(ctx, __func__, rc);
+    D2H(density, d_den, n, float);
+    D2H(particles, d_part, 2 * S, float);
+    D2H(empty_slots, d_stack, S, int);
+    D2H(particles_hist, d_hist, S, int);
+    D2H(current_empty_slot, d_top, 1, int);
+    D2H(largest_index, d_last, 1, int);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    report_status(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// K3: wall injection.  Replaces the body of inject_particles (ref infMagSim_cython.py:230-285)
+// and provides the device-side source of its two random inputs: the flux-weighted drifting
+// Maxwellian rejection sampler draw_velocities_c (ref infMagSim_c.c:560-666) and the uniform
+// partial-step fractions the driver's host sampler supplies (ref infMagSim_script.py:321).
+//
+// The reference pops one slot per injected particle from the LIFO stack, in order.  Here
+// particle l takes stack entry top-l directly, which is the same assignment as long as no
+// particle has a "bad left_index" (ref :272-274: such a particle keeps its slot on the
+// stack and the next one overwrites it).  That case needs |partial_dt*v| larger than the
+// whole domain and is unreachable with physical inputs, but it is still honoured: a first
+// kernel counts bad particles and, if there are any, the commit kernel replays the
+// reference's sequential loop on one thread instead of the parallel path.
+//
+// Random numbers: the reference's generator is a process-global, strictly sequential MT19937
+// whose consumption per particle depends on the rejection loop; its stream cannot be split
+// across threads.  The device sampler therefore uses the counter-based Philox4x32-10
+// generator (one independent counter per output element) with the same float conversion
+// (ref :101) and the same acceptance test in double (ref :614, :654).  Parity of the
+// injection body itself is exact when both sides are fed the same velocities and fractions
+// (tests/test_inject_gpu.py); parity of the sampler is statistical.
+#include "espic_internal.cuh"
+
+namespace espic {
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) -------------------------------------------------
+struct Philox {
+    uint32_t key[2];
+    __device__ __forceinline__ static void round(uint32_t c[4], const uint32_t k[2]) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    }
+    __device__ __forceinline__ void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t out[4]) const {
+        uint32_t c[4] = {c0, c1, c2, c3};
+        uint32_t k[2] = {key[0], key[1]};
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round(c, k);
+            k[0] += 0x9E3779B9u;
+            k[1] += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+};
+
+// ref infMagSim_c.c:101: (float)y / (unsigned long)0xffffffff -- the divisor becomes the
+// float 2^32, and the quotient may round up to exactly 1.0f.
+__device__ __forceinline__ float u32_to_unit_float(uint32_t y) { return (float)y / 4294967296.0f; }
+
+__global__ void k_uniforms(int n, float* __restrict__ out, unsigned long long seed, unsigned long long call) {
+    Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; 4 * i < n; i += gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        ph((uint32_t)i, 0u, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x554e4946u, r);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (4 * i + c < n) out[4 * i + c] = u32_to_unit_float(r[c]);
+    }
+}
+
+// One thread per velocity; same constants, window and acceptance test as the reference.
+__global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restrict__ out,
+                                  unsigned long long seed, unsigned long long call, int* status) {
+    const float half_window = 5.f;
+    const float beta = (float)((double)v_d / (sqrt(2.) * (double)v_th));
+    const double b = (double)beta;
+    const double gauss = 1. / sqrt(3.14159265358979323846) * exp(-pow(b, 2.));
+    const float ratio = (float)((gauss - b * (1. - erf(b))) / (gauss + b * (1. + erf(b))));
+    const double vd = (double)v_d, vt = (double)v_th;
+    const double disc = sqrt(pow(vd, 2.) + 4. * pow(vt, 2.));
+    const double two_vt2 = 2. * pow(vt, 2.);
+    Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        uint32_t block = 0;
+        ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
+        const float side = u32_to_unit_float(r[0]) - 1.f / (1.f + ratio);
+        float mode, lo, hi;
+        if (side >= 0.f) {
+            mode = (float)((-vd + disc) / 2.);
+            hi = mode + half_window * v_th;
+            lo = (float)fmax((double)(mode - half_window * v_th), 0.);
+        } else {
+            mode = (float)((-vd - disc) / 2.);
+            hi = (float)fmin((double)(mode + half_window * v_th), 0.);
+            lo = mode - half_window * v_th;
+        }
+        const double mode_term = pow((double)(mode + v_d), 2.);
+        const double abs_mode = fabs((double)mode);
+        int next = 2;  // first trial uses r[2], r[3] of block 0; later blocks give two trials each
+        float v = 0.f;
+        for (int tries = 1;; ++tries) {
+            if (next >= 4) {
+                ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
+                next = 0;
+            }
+            const float u_v = u32_to_unit_float(r[next]);
+            const float u_a = u32_to_unit_float(r[next + 1]);
+            next += 2;
+            v = __fadd_rn(__fmul_rn(u_v, hi - lo), lo);  // ref :611-612 / :651-652
+            const double bound = log(fabs((double)v) / abs_mode) +
+                                 (mode_term - pow((double)(v + v_d), 2.)) / two_vt2;  // ref :614 / :654
+            if (log((double)u_a) <= bound) break;
+            // ref :589-607: after 1000 rejections the reference prints a warning and keeps
+            // looping; we raise a status bit, and give up after 1e6 so a NaN parameter cannot
+            // hang the GPU
+            if (tries == 1000) atomicOr(status, ESPIC_ST_SAMPLER_STALL);
+            if (tries >= 1000000) break;
+        }
+        out[i] = v;
+    }
+}
+
+// ---- injection body --------------------------------------------------------------------------
+struct InjectArgs {
+    const float* grid;
+    const float* vel;
+    const float* uni;
+    float* px;
+    float* pv;
+    int* hist;
+    int* empty_slots;
+    int* top;
+    int* largest;
+    unsigned long long* acc;
+    float* density;
+    int* status;
+    int* ws;  // [0] bad count
+    int n_inject, n_points, k;
+    float dt, a_b;
+    double inv_scale;
+};
+
+struct Injected {
+    float x, v;
+    int cell;
+    bool bad;
+};
+
+// ref infMagSim_cython.py:246, 262-271 -- float arithmetic throughout
+__device__ __forceinline__ Injected place_injected(const Geom& g, float vel, float u, float dt, float a_b) {
+    Injected r;
+    const float edge = 2.e-6f;  // ref :238
+    const float part_dt = __fmul_rn(dt, u);
+    r.v = __fsub_rn(vel, __fmul_rn(a_b, part_dt));
+    const float wall = (vel < 0.f) ? __fsub_rn(g.z_hi, edge) : __fadd_rn(g.z_lo, edge);
+    r.x = __fadd_rn(wall, __fmul_rn(part_dt, r.v));
+    r.cell = (int)__fdiv_rn(__fsub_rn(r.x, g.z_lo), g.dz);
+    r.bad = (r.cell < 0) || (r.cell > g.last_cell);
+    return r;
+}
+
+__global__ void k_inject_classify(const InjectArgs a) {
+    const Geom g = make_geom(a.grid, a.n_points);
+    int bad = 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x)
+        bad += place_injected(g, a.vel[l], a.uni[l], a.dt, a.a_b).bad ? 1 : 0;
+    bad = __syncthreads_count(bad);
+    if (threadIdx.x == 0 && bad) atomicAdd(a.ws, bad);
+}
+
+__device__ __forceinline__ void deposit_injected(const Geom& g, const Injected& p, unsigned long long* acc) {
+    const unsigned w0 = left_share_fixed(g, p.x);
+    atomicAdd(acc + p.cell, (unsigned long long)w0);
+    atomicAdd(acc + p.cell + 1, (unsigned long long)(kWeightOne - w0));
+}
+
+__global__ void k_inject_commit(const InjectArgs a) {
+    const Geom g = make_geom(a.grid, a.n_points);
+    const int top0 = *a.top;
+    const int n_bad = a.ws[0];
+    if (n_bad == 0) {
+        int my_max = -1;
+        for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x) {
+            const int sp = top0 - l;
+            if (sp < 0) {  // ref :255-256 "no empty slots" (the reference then reads empty_slots[-1])
+                atomicOr(a.status, ESPIC_ST_STACK_EMPTY);
+                continue;
+            }
+            const int slot = a.empty_slots[sp];
+            const Injected p = place_injected(g, a.vel[l], a.uni[l], a.dt, a.a_b);
+            a.hist[slot] = a.k;
+            a.pv[slot] = p.v;
+            a.px[slot] = p.x;
+            my_max = max(my_max, slot);
+            deposit_injected(g, p, a.acc);
+            a.empty_slots[sp] = -1;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
+        if ((threadIdx.x & 31) == 0 && my_max >= 0) atomicMax(a.largest, my_max);
+    } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // replay of the reference's sequential loop (only when a bad left_index occurred)
+        int top = top0, last = *a.largest;
+        for (int l = 0; l < a.n_inject; ++l) {
+            if (top < 0) {
+                atomicOr(a.status, ESPIC_ST_STACK_EMPTY);
+                break;
+            }
+            const int slot = a.empty_slots[top];
+            const Injected p = place_injected(g, a.vel[l], a.uni[l], a.dt, a.a_b);
+            a.hist[slot] = a.k;
+            a.pv[slot] = p.v;
+            a.px[slot] = p.x;
+            last = max(last, slot);
+            if (p.bad) {
+                atomicOr(a.status, ESPIC_ST_BAD_INJECT_INDEX);
+            } else {
+                deposit_injected(g, p, a.acc);
+                a.empty_slots[top] = -1;
+                top -= 1;
+            }
+        }
+        *a.largest = last;
+        a.ws[1] = top;  // final stack top for k_inject_finish
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_inject_finish(const InjectArgs a) {
+    for (int j = threadIdx.x; j < a.n_points; j += blockDim.x) {
+        const unsigned long long v = a.acc[j];
+        if (v) {
+            a.density[j] = __fadd_rn(a.density[j], (float)((double)v * a.inv_scale));
+            a.acc[j] = 0ull;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int top0 = *a.top;
+        if (a.ws[0] == 0) {
+            const int n_ok = min(a.n_inject, top0 + 1);
+            *a.top = top0 - (n_ok > 0 ? n_ok : 0);
+        } else {
+            *a.top = a.ws[1];
+        }
+        a.ws[0] = 0;
+        a.ws[1] = 0;
+    }
+}
+
+int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
+                  const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
+                  int storage, int* empty_slots, int* top, int* largest, float* density) {
+    if (n_inject <= 0) return 0;
+    if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
+    int rc = ensure_acc(ctx, n_points);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->inject_ws, 64, "inject workspace");
+    if (rc) return rc;
+    InjectArgs a{};
+    a.grid = grid;
+    a.vel = vel;
+    a.uni = uni;
+    a.px = particles;
+    a.pv = particles + storage;
+    a.hist = hist;
+    a.empty_slots = empty_slots;
+    a.top = top;
+    a.largest = largest;
+    a.acc = ctx->acc;
+    a.density = density;
+    a.status = ctx->status;
+    a.ws = (int*)ctx->inject_ws.ptr;
+    a.n_inject = n_inject;
+    a.n_points = n_points;
+    a.k = k;
+    a.dt = dt;
+    a.a_b = a_b;
+    a.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
+    int grid_dim = (n_inject + 255) / 256;
+    if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
+    k_inject_classify<<<grid_dim, 256, 0, ctx->stream>>>(a);
+    k_inject_commit<<<grid_dim, 256, 0, ctx->stream>>>(a);
+    k_inject_finish<<<1, 1024, 0, ctx->stream>>>(a);
+    ctx->launches += 3;
+    return check_cuda(ctx, cudaGetLastError(), "inject launch");
+}
+
+// ---- sampler front ends -----------------------------------------------------------------------
+int rng_seed(espic_ctx* ctx, unsigned long seed) {
+    ctx->rng_seeded = 1;
+    ctx->rng_consumed = 0;
+    // spread the (typically small) integer seed over the 64-bit Philox key
+    unsigned long long z = (unsigned long long)seed + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    ctx->rng_key = z;
+    return 0;
+}
+
+static unsigned long long rng_key(espic_ctx* ctx) {
+    if (!ctx->rng_seeded) rng_seed(ctx, 4357ul);  // the reference's default seed (ref infMagSim_c.c:78-79)
+    return ctx->rng_key;
+}
+
+int rng_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out) {
+    if (n <= 0) return 0;
+    const unsigned long long key = rng_key(ctx);
+    int grid_dim = (n + 127) / 128;
+    if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
+    k_draw_velocities<<<grid_dim, 128, 0, ctx->stream>>>(n, v_th, v_d, v_out, key, ctx->rng_consumed++, ctx->status);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_draw_velocities launch");
+}
+
+int rng_uniforms(espic_ctx* ctx, int n, float* out) {
+    if (n <= 0) return 0;
+    const unsigned long long key = rng_key(ctx);
+    int grid_dim = (n / 4 + 255) / 256 + 1;
+    if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
+    k_uniforms<<<grid_dim, 256, 0, ctx->stream>>>(n, out, key, ctx->rng_consumed++);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_uniforms launch");
+}
+
+}  // namespace espic

@@ -1,0 +1,192 @@
+/*
+ * espic_b200.h -- C ABI of libespic_b200.so, the sm_100a implementation of the per-timestep
+ * hot path of ctzhou/ESPIC_hole_tracking's 1-D infinite-B electrostatic PIC.
+ *
+ * Two families of entry points:
+ *
+ *  (A) espic_*  -- DEVICE-pointer operators on an explicit context (stream + scratch).
+ *      Particle stores, grids and the free-slot stack stay resident in HBM between calls;
+ *      the two in/out scalars of the reference (stack top, largest used index) are DEVICE
+ *      ints so a timestep needs no host synchronisation.  This is what the Python operator
+ *      layer (espic_hole_tracking_b200/operators.py) and the driver mirror call.
+ *
+ *  (B) the reference's own symbol names with HOST pointers (move_particles_c,
+ *      poisson_solve_c, ...), same parameter lists as infMagSim_c.c, for relinking the
+ *      reference's Cython extension against this library without touching the driver.
+ *      Each call stages its arrays through the device (H2D, kernels, D2H).
+ *
+ * "ref:" citations are file:line in the reference repository.
+ * All functions returning int return 0 on success or a negative ESPIC_E_* code; the message
+ * is available from espic_last_error().  No entry point falls back to CPU arithmetic.
+ */
+#ifndef ESPIC_B200_H
+#define ESPIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESPIC_ABI_VERSION 1
+
+enum {
+    ESPIC_OK = 0,
+    ESPIC_E_CUDA = -1,     /* a CUDA runtime call failed */
+    ESPIC_E_ARG = -2,      /* invalid argument */
+    ESPIC_E_NOMEM = -3,    /* scratch allocation failed */
+    ESPIC_E_NODEVICE = -4  /* no CUDA device / wrong architecture */
+};
+
+/* Bits of the device status word (espic_status): the reference only printf()s in these
+ * situations and then indexes out of bounds; we record the event and stay in bounds. */
+enum {
+    ESPIC_ST_BAD_LEFT_INDEX = 1,   /* ref infMagSim_c.c:164-165,188-189 "bad left_index" */
+    ESPIC_ST_STACK_OVERFLOW = 2,   /* ref infMagSim_c.c:215-216 "bad current_empty_slot" */
+    ESPIC_ST_STACK_EMPTY = 4,      /* ref infMagSim_cython.py:255-256 "no empty slots" */
+    ESPIC_ST_BAD_INJECT_INDEX = 8, /* ref infMagSim_cython.py:272-273 */
+    ESPIC_ST_BAD_OBJECT_MASK = 16, /* ref infMagSim_c.c:468,482,485 */
+    ESPIC_ST_SAMPLER_STALL = 32    /* ref infMagSim_c.c:589-607 (1000 rejections) */
+};
+
+typedef struct espic_ctx espic_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int espic_abi_version(void);
+int espic_create(espic_ctx **out, int device);
+void espic_destroy(espic_ctx *ctx);
+/* cudaStream_t as void*; NULL = the legacy default stream.  All work of this context is
+ * enqueued on it; nothing synchronises unless stated. */
+int espic_set_stream(espic_ctx *ctx, void *cuda_stream);
+const char *espic_last_error(espic_ctx *ctx);
+/* Reads and clears the status word (synchronises the stream). */
+int espic_status(espic_ctx *ctx, int *status_out);
+/* Multiprocessor count and the persistent grid the mover uses (for bench bookkeeping). */
+int espic_device_info(espic_ctx *ctx, int *sm_count, int *mover_grid, int *mover_block);
+/* Kernels launched on this context since creation (bench's gpu_launches). */
+long long espic_launch_count(espic_ctx *ctx);
+/* Per-launch CUDA-event timing of the mover kernel: enable, run, then read the mean launch
+ * duration in ms and the launch count (synchronises). */
+int espic_timing_enable(espic_ctx *ctx, int on);
+int espic_timing_read(espic_ctx *ctx, double *mean_ms, int *launches, double *total_ms);
+
+/* ---- (A) device-pointer operators -------------------------------------------------------- */
+
+/* Replaces move_particles_c (ref infMagSim_c.c:121-125), same parameter order and meaning.
+ * particles = float[2][particle_storage_length] (row 0 positions, row 1 velocities);
+ * density (n_points floats) is OVERWRITTEN; removed slots are pushed on empty_slots in
+ * ascending slot order exactly as the reference's sequential loop does; current_empty_slot
+ * is a DEVICE int (stack top), updated in place. */
+int espic_move_particles(espic_ctx *ctx, const float *grid, const float *object_mask,
+                         const float *potential, float dt, float charge_to_mass,
+                         float background_density, int largest_index, float *particles,
+                         float *density, int *empty_slots, int *current_empty_slot, float a_b,
+                         int update_position, int periodic_particles, int largest_allowed_slot,
+                         int n_points, int particle_storage_length);
+
+/* Same, but largest_index is read from a DEVICE int at launch time (the injector updates it
+ * on the device); max_slots bounds the launch (use particle_storage_length). */
+int espic_move_particles_dev(espic_ctx *ctx, const float *grid, const float *object_mask,
+                             const float *potential, float dt, float charge_to_mass,
+                             float background_density, const int *largest_index_dev,
+                             float *particles, float *density, int *empty_slots,
+                             int *current_empty_slot, float a_b, int update_position,
+                             int periodic_particles, int largest_allowed_slot, int n_points,
+                             int particle_storage_length);
+
+/* v[i] -= v_b for i <= largest_index: the tail of initialize_mover
+ * (ref infMagSim_cython.py:174-176; the subtraction runs in double there). */
+int espic_shift_velocities(espic_ctx *ctx, float *particles, int particle_storage_length,
+                           int largest_index, double v_b);
+
+/* Replaces poisson_solve_c (ref infMagSim_c.c:356-358), same parameters.  Single-CTA
+ * kernel; rows are built exactly as the reference builds them (Robin ends, object rows,
+ * transparency blend, Boltzmann term, the periodic Sherman-Morrison variant including its
+ * two quirks) and the Thomas recurrences run as fp64 block scans. */
+int espic_poisson_solve(espic_ctx *ctx, const float *grid, const float *object_mask,
+                        const float *charge, float debye_length, float *potential,
+                        float object_potential, float object_transparency,
+                        int boltzmann_electrons, int periodic_potential, int n_points);
+
+/* Density end-node fix + charge density of the driver loop
+ * (ref infMagSim_script.py:763-779,807): periodic -> fold the end nodes, else double them
+ * (each species only if its fix flag is set); charge = ion - electron.  In place. */
+int espic_prepare_charge(espic_ctx *ctx, float *ion_density, float *electron_density,
+                         float *charge, int n_points, int periodic, int fix_ions,
+                         int fix_electrons);
+
+/* Replaces the body of inject_particles (ref infMagSim_cython.py:230-285) with both random
+ * inputs supplied as device arrays: velocities[n_inject] (signed; the sign picks the wall)
+ * and uniform01[n_inject] (partial-step fractions).  particles_hist = int[storage] tags.
+ * current_empty_slot and largest_index are DEVICE ints, updated in place. */
+int espic_inject_particles(espic_ctx *ctx, int n_inject, const float *grid, int n_points,
+                           float dt, float background_density, const float *velocities,
+                           const float *uniform01, float a_b, int k, int *particles_hist,
+                           float *particles, int particle_storage_length, int *empty_slots,
+                           int *current_empty_slot, int *largest_index, float *density);
+
+/* Device replacements of sgenrand / draw_velocities_c / genrand (ref infMagSim_c.c:54-65,
+ * 560-666, 67-103): the same flux-weighted drifting-Maxwellian rejection sampler (window,
+ * side choice and acceptance test as in the reference, float conversion of ref :101) driven
+ * by the counter-based Philox4x32-10 generator instead of the reference's sequential,
+ * process-global MT19937, whose data-dependent consumption cannot be split across threads.
+ * Same distribution, different stream: parity of the sampler is statistical (SURVEY.md s.7
+ * hard part 7).  The key and call counter live in the context, so successive calls continue
+ * the stream.  v_out / out are device arrays. */
+int espic_seed(espic_ctx *ctx, unsigned long seed);
+int espic_draw_velocities(espic_ctx *ctx, int n, float v_th, float v_d, float *v_out);
+int espic_genrand(espic_ctx *ctx, int n, float *out);
+
+/* ---- "next" rows: per-step diagnostics ---------------------------------------------------- */
+/* Replaces electric_field_filter_c (ref infMagSim_c.c:668-683). Device arrays. */
+int espic_field_filter(espic_ctx *ctx, int n_points, const float *grid, const float *data,
+                       float L, int n_fine, const float *fine_mesh, float *res);
+/* Hole position of the driver (ref infMagSim_script.py:746-753): np.gradient(potential, dz)
+ * (float32 central differences, one-sided at the ends), the filter above and
+ * fine_mesh[argmax]; scratch_res (n_fine floats) receives the filter response and
+ * position_out (one device float) the position.  dz is the driver's Python float. */
+int espic_hole_position(espic_ctx *ctx, int n_points, const float *grid,
+                        const float *potential, double dz, float L, int n_fine,
+                        const float *fine_mesh, float *scratch_res, float *position_out);
+/* Replaces histogram2d_uniform_grid_c (ref infMagSim_c.c:543-558) directly on device arrays
+ * xs[n_data], ys[n_data] (e.g. the two rows of a particle store: parked slots sit at 2*z_max,
+ * outside any histogram range, which is what the driver's "occupied" mask removes,
+ * ref infMagSim_script.py:866-867).  If tags != NULL only entries with tags[i] == tag_value
+ * are counted (ref :880-881).  Counts are ADDED to hist[n_bins_x*n_bins_y]. */
+int espic_phase_space_histogram(espic_ctx *ctx, const float *xs, const float *ys, int n_data,
+                                const int *tags, int tag_value, float x_min, float step_x,
+                                float y_min, float step_y, int n_bins_x, int n_bins_y,
+                                int *hist);
+
+/* ---- (B) reference-named host-pointer drop-ins ------------------------------------------ */
+void move_particles_c(float *grid, float *object_mask, float *potential, float dt,
+                      float charge_to_mass, float background_density, int largest_index,
+                      float *particles, float *density, int *empty_slots,
+                      int *current_empty_slot, float a_b, int update_position,
+                      int periodic_particles, int largest_allowed_slot, int n_points,
+                      int particle_storage_length); /* ref infMagSim_c.c:121-125 */
+void poisson_solve_c(float *grid, float *object_mask, float *charge, float debye_length,
+                     float *potential, float object_potential, float object_transparency,
+                     int boltzmann_electrons, int periodic_potential,
+                     int n_points); /* ref infMagSim_c.c:356-358 */
+void draw_velocities_c(int n, float v_th, float v_d, float *v_array); /* ref :560 */
+void sgenrand(unsigned long seed);                                    /* ref :54-56 */
+float genrand(void);                                                  /* ref :67-69 */
+void electric_field_filter_c(int n_points, float *grid, float *data_array, float L,
+                             int n_fine_mesh, float *fine_mesh, float *Res); /* ref :668 */
+void histogram2d_uniform_grid_c(float *X, float *Y, float x_min, float step_x, float y_min,
+                                float step_y, int n_bins_x, int n_bins_y, int n_data,
+                                int *hist); /* ref :543-544 */
+/* New symbol (the reference's injection body is Cython, infMagSim_cython.py:230-285):
+ * host-pointer form of espic_inject_particles. */
+void inject_particles_c(int n_inject, float *grid, int n_points, float dt,
+                        float background_density, float *velocities, float *uniform01,
+                        float a_b, int k, int *particles_hist, float *particles,
+                        int particle_storage_length, int *empty_slots,
+                        int *current_empty_slot, int *largest_index, float *density);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESPIC_B200_H */

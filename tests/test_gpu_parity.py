@@ -1,0 +1,395 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via the operator layer) against
+the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): particle state (x, v), particle-to-cell indexing, removal
+order and free-slot stack are BIT-EXACT; density and potential agree within 1e-6 relative.
+The reference's own float32 serial accumulation is itself off from the exact sum of its
+weights by up to a few 1e-6 at thousands of particles per cell, so density
+is checked twice: against the float64-exact sum of the reference's weights (tolerance 1e-6
+of the peak density, typically 1e-7) and against the reference's float32 result (tolerance =
+1e-6 plus the reference's own measured deviation from the exact sum).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import workloads as wl
+from tests.helpers import assert_bits_equal, deposit_f64, to_dev
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6  # north-star tolerance for densities and fields
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import espic_hole_tracking_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def cpu(ref_or_port):
+    return ref_or_port
+
+
+@pytest.fixture(scope="module")
+def ref_or_port():
+    from oracle import cpu as ocpu
+    if ocpu.have("reference"):
+        return ocpu.load("reference")
+    if not ocpu.have("port"):
+        ocpu.build()
+    return ocpu.load("port")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def check_density(d_gpu, d_ref, grid, x_final, bg, periodic):
+    exact, n_alive = deposit_f64(grid, x_final, bg, periodic)
+    peak = exact.max()
+    err_gpu = np.abs(d_gpu.astype(np.float64) - exact).max() / peak
+    err_ref = np.abs(d_ref.astype(np.float64) - exact).max() / peak
+    assert err_gpu <= REL, (err_gpu, err_ref)
+    assert np.abs(d_gpu.astype(np.float64) - d_ref).max() / peak <= REL + err_ref
+    return err_gpu, err_ref
+
+
+@pytest.mark.parametrize("n_cells", [500, 512, 4096])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_mover_multi_step(ops, cpu, n_cells, periodic):
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid, amplitude=2.0)
+    dt = wl.timestep()
+    n = 60_000
+    _, sp = wl.make_plasma(n, n_cells, seed=n_cells + int(periodic), holes=0.02)
+    sp.particles[0, :6] = np.array([-3.0, 3.0, -3.0000005, 2.9999995, 3.5, -7.0], np.float32)
+    bg = wl.background_density(n, 1, n_cells)
+    c = sp.copy()
+    g = to_dev(sp, torch)
+    g_grid, g_mask, g_phi = dev(grid), dev(mask), dev(phi)
+    g_den = torch.full((len(grid),), 7.0, device="cuda")
+    top_g, last_g = list(sp.current_empty_slot), list(sp.largest_index)
+    for step in range(10):
+        a_b = 0.37 * (step % 3)
+        d_ref = np.full_like(grid, -7.0)
+        cpu.move_particles(grid, mask, phi, dt, sp.charge_to_mass, bg, c.largest_index, c.particles, d_ref,
+                           c.empty_slots, c.current_empty_slot, a_b=a_b, update_position=True,
+                           periodic_particles=periodic)
+        ops.move_particles(g_grid, g_mask, g_phi, dt, sp.charge_to_mass, bg, last_g, g["particles"], g_den,
+                           g["empty_slots"], top_g, a_b, update_position=True, periodic_particles=periodic,
+                           use_pure_c_version=True)
+        assert top_g == c.current_empty_slot
+        assert_bits_equal(g["particles"].cpu().numpy(), c.particles, f"particles step {step}")
+        top = top_g[0]
+        assert_bits_equal(g["empty_slots"].cpu().numpy()[:top + 1], c.empty_slots[:top + 1], "stack")
+        check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, periodic)
+    assert ops.default_context().status() == 0
+    if not periodic:
+        assert top_g[0] > sp.current_empty_slot[0]
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_mover_scalar_path_and_device_scalars(ops, cpu, periodic):
+    """Storage length not a multiple of 4 (no float4 path) + DeviceInt stack top / largest index."""
+    n_cells = 512
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid)
+    rng = np.random.default_rng(11)
+    n, storage = 10_001, 12_347
+    sp = wl.make_species(n, storage, rng, math.sqrt(1836.0), -1836.0, holes=0.01)
+    c = sp.copy()
+    g = to_dev(sp, torch)
+    top = ops.DeviceInt(sp.current_empty_slot[0])
+    last = ops.DeviceInt(sp.largest_index[0])
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    for _ in range(3):
+        cpu.move_particles(grid, mask, phi, 1e-3, -1836.0, 5.0, c.largest_index, c.particles, d_ref, c.empty_slots,
+                           c.current_empty_slot, a_b=0.1, periodic_particles=periodic)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), 1e-3, -1836.0, 5.0, last, g["particles"], g_den,
+                           g["empty_slots"], top, 0.1, periodic_particles=periodic)
+    assert top[0] == c.current_empty_slot[0]
+    assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+    assert_bits_equal(g["empty_slots"].cpu().numpy()[:top[0] + 1], c.empty_slots[:top[0] + 1], "stack")
+    check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], 5.0, periodic)
+
+
+def test_mover_object_and_no_position_update(ops, cpu):
+    n_cells = 512
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    mask[250:262] = 1.0
+    mask[249], mask[262] = 0.4, 0.7
+    phi = wl.smooth_potential(grid)
+    ions, _ = wl.make_plasma(40_000, n_cells, seed=5)
+    c = ions.copy()
+    g = to_dev(ions, torch)
+    top_g, last_g = list(ions.current_empty_slot), list(ions.largest_index)
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    for upd in (False, True):
+        cpu.move_particles(grid, mask, phi, 1e-2, 1.0, 3.0, c.largest_index, c.particles, d_ref, c.empty_slots,
+                           c.current_empty_slot, a_b=0.0, update_position=upd)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), 1e-2, 1.0, 3.0, last_g, g["particles"], g_den,
+                           g["empty_slots"], top_g, 0.0, update_position=upd)
+        assert top_g == c.current_empty_slot
+        assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+        assert_bits_equal(g["empty_slots"].cpu().numpy()[:top_g[0] + 1], c.empty_slots[:top_g[0] + 1], "stack")
+        np.testing.assert_allclose(g_den.cpu().numpy(), d_ref, rtol=0, atol=3e-6 * d_ref.max())
+    assert top_g[0] > ions.current_empty_slot[0]
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_mover_large_grid_path(ops, cpu, periodic):
+    """65537 grid points: the tables do not fit in shared memory (C4 of BASELINE.json)."""
+    n_cells = 65536
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid, amplitude=1.0)
+    n = 300_000
+    _, sp = wl.make_plasma(n, n_cells, seed=3, holes=0.01)
+    bg = wl.background_density(n, 1, n_cells)
+    c = sp.copy()
+    g = to_dev(sp, torch)
+    top_g, last_g = list(sp.current_empty_slot), list(sp.largest_index)
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    for _ in range(3):
+        cpu.move_particles(grid, mask, phi, wl.timestep(), sp.charge_to_mass, bg, c.largest_index, c.particles,
+                           d_ref, c.empty_slots, c.current_empty_slot, a_b=0.0, periodic_particles=periodic)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), wl.timestep(), sp.charge_to_mass, bg, last_g,
+                           g["particles"], g_den, g["empty_slots"], top_g, 0.0, periodic_particles=periodic)
+    assert top_g == c.current_empty_slot
+    assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+    assert_bits_equal(g["empty_slots"].cpu().numpy()[:top_g[0] + 1], c.empty_slots[:top_g[0] + 1], "stack")
+    check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, periodic)
+
+
+def test_accumulate_density_and_initialize_mover(ops, cpu):
+    n_cells = 512
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid)
+    ions, _ = wl.make_plasma(30_000, n_cells, seed=8)
+    bg = wl.background_density(30_000, 1, n_cells)
+    c = ions.copy()
+    g = to_dev(ions, torch)
+    top_g, last_g = list(ions.current_empty_slot), list(ions.largest_index)
+    d_ref = np.zeros_like(grid)
+    g_den = torch.zeros(len(grid), device="cuda")
+    cpu.accumulate_density(grid, mask, bg, c.largest_index, c.particles, d_ref, c.empty_slots, c.current_empty_slot)
+    ops.accumulate_density(dev(grid), dev(mask), bg, last_g, g["particles"], g_den, g["empty_slots"], top_g,
+                           use_pure_c_version=True)
+    check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :30_000], bg, False)
+    assert abs(float(g_den.sum().item()) * bg - 30_000) < 0.05  # charge conservation
+    cpu.initialize_mover(grid, mask, phi, wl.timestep(), 1.0, c.largest_index, c.particles, c.empty_slots,
+                         c.current_empty_slot, v_b=0.123456789, a_b=0.01)
+    ops.initialize_mover(dev(grid), dev(mask), dev(phi), wl.timestep(), 1.0, last_g, g["particles"],
+                         g["empty_slots"], top_g, v_b=0.123456789, a_b=0.01, use_pure_c_version=True)
+    assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles after initialize_mover")
+
+
+@pytest.mark.parametrize("n_points", [9, 513, 4097, 65537])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_poisson(ops, cpu, n_points, periodic):
+    grid = wl.make_grid(n_points - 1)
+    rng = np.random.default_rng(n_points)
+    charge = (0.05 * rng.standard_normal(n_points)).astype(np.float32)
+    mask = np.zeros_like(grid)
+    p_ref = np.zeros_like(grid)
+    cpu.poisson_solve(grid, mask, charge, wl.DEBYE_LENGTH, p_ref, periodic_potential=periodic)
+    p_gpu = torch.zeros(n_points, device="cuda")
+    ops.poisson_solve(dev(grid), dev(mask), dev(charge), wl.DEBYE_LENGTH, p_gpu, periodic_potential=periodic,
+                      use_pure_c_version=True)
+    scale = np.abs(p_ref).max()
+    assert scale > 0
+    err = np.abs(p_gpu.cpu().numpy().astype(np.float64) - p_ref).max() / scale
+    assert err <= REL, err
+
+
+def test_poisson_object_and_boltzmann(ops, cpu):
+    n_points = 513
+    grid = wl.make_grid(n_points - 1)
+    rng = np.random.default_rng(3)
+    charge = (1.0 + 0.05 * rng.standard_normal(n_points)).astype(np.float32)
+    mask = np.zeros_like(grid)
+    mask[200:240] = 1.0
+    mask[199], mask[240] = 0.3, 0.6
+    mask[300] = 0.5
+    for transparency in (0.0, 0.35, 1.0):
+        for boltz in (False, True):
+            p_ref = (0.1 * np.sin(grid)).astype(np.float32)
+            p_gpu = dev(p_ref)
+            cpu.poisson_solve(grid, mask, charge, 0.25, p_ref, object_potential=-3.0,
+                              object_transparency=transparency, boltzmann_electrons=boltz)
+            ops.poisson_solve(dev(grid), dev(mask), dev(charge), 0.25, p_gpu, object_potential=-3.0,
+                              object_transparency=transparency, boltzmann_electrons=boltz)
+            err = np.abs(p_gpu.cpu().numpy().astype(np.float64) - p_ref).max() / np.abs(p_ref).max()
+            assert err <= REL, (transparency, boltz, err)
+
+
+def test_prepare_charge(ops):
+    rng = np.random.default_rng(0)
+    for periodic in (False, True):
+        ni = rng.random(513).astype(np.float32)
+        ne = rng.random(513).astype(np.float32)
+        gi, ge, gc = dev(ni), dev(ne), torch.zeros(513, device="cuda")
+        ops.prepare_charge(gi, ge, gc, periodic_particles=periodic)
+        for d in (ni, ne):  # infMagSim_script.py:764-769
+            if periodic:
+                d[0] += d[-1]
+                d[-1] = d[0]
+            else:
+                d[0] *= 2.0
+                d[-1] *= 2.0
+        assert_bits_equal(gi.cpu().numpy(), ni)
+        assert_bits_equal(ge.cpu().numpy(), ne)
+        assert_bits_equal(gc.cpu().numpy(), ni - ne)
+
+
+def test_injection_given_inputs(ops, cpu):
+    """Injection body with both random inputs supplied: slot assignment, tags, x, v bit-exact."""
+    from oracle import cpu as ocpu
+    port = ocpu.load("port") if ocpu.have("port") else None
+    if port is None:
+        ocpu.build()
+        port = ocpu.load("port")
+    for n_cells in (500, 4096):
+        grid = wl.make_grid(n_cells)
+        ions, _ = wl.make_plasma(20_000, n_cells, seed=9)
+        c = ions.copy()
+        g = to_dev(ions, torch)
+        d0 = np.random.default_rng(1).random(len(grid)).astype(np.float32)
+        d_ref, g_den = d0.copy(), dev(d0)
+        cpu.seedgenrand_c(384)
+        n_inj = 3_000
+        vel = cpu.draw_velocities(n_inj, 1.0, 0.3)
+        uni = np.random.default_rng(2).random(n_inj).astype(np.float32)
+        bg = 40.0
+        port.inject_given(n_inj, grid, 0.01, bg, vel, uni, 0.2, 17, c.tags, c.particles, c.empty_slots,
+                          c.current_empty_slot, c.largest_index, d_ref)
+        top_g, last_g = list(ions.current_empty_slot), list(ions.largest_index)
+        ops.inject_particles_given(n_inj, dev(grid), 0.01, bg, dev(vel), dev(uni), 0.2, 17, g["tags"],
+                                   g["particles"], g["empty_slots"], top_g, last_g, g_den)
+        assert top_g == c.current_empty_slot and last_g == c.largest_index
+        assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+        assert_bits_equal(g["empty_slots"].cpu().numpy(), c.empty_slots, "stack")
+        assert_bits_equal(g["tags"].cpu().numpy(), c.tags, "tags")
+        np.testing.assert_allclose(g_den.cpu().numpy(), d_ref, rtol=0, atol=2e-6 * d_ref.max())
+    assert ops.default_context().status() == 0
+
+
+def test_injection_bad_index_replays_reference_order(ops):
+    """A particle whose partial step carries it past the far wall keeps its slot on the stack
+    (infMagSim_cython.py:272-274); the kernel falls back to the sequential replay."""
+    from oracle import cpu as ocpu
+    if not ocpu.have("port"):
+        ocpu.build()
+    port = ocpu.load("port")
+    grid = wl.make_grid(64)
+    ions, _ = wl.make_plasma(100, 64, seed=1)
+    c = ions.copy()
+    g = to_dev(ions, torch)
+    vel = np.array([1.0, 900.0, 2.0, -3.0, 800.0], np.float32)  # 900*0.01*0.9 > 6: out of the domain
+    uni = np.array([0.5, 0.9, 0.1, 0.7, 0.95], np.float32)
+    d_ref = np.zeros_like(grid)
+    g_den = torch.zeros(len(grid), device="cuda")
+    port.inject_given(5, grid, 0.01, 1.0, vel, uni, 0.0, 3, c.tags, c.particles, c.empty_slots,
+                      c.current_empty_slot, c.largest_index, d_ref)
+    top_g, last_g = list(ions.current_empty_slot), list(ions.largest_index)
+    ops.inject_particles_given(5, dev(grid), 0.01, 1.0, dev(vel), dev(uni), 0.0, 3, g["tags"], g["particles"],
+                               g["empty_slots"], top_g, last_g, g_den)
+    assert top_g == c.current_empty_slot == [ions.current_empty_slot[0] - 3]
+    assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+    assert_bits_equal(g["empty_slots"].cpu().numpy(), c.empty_slots, "stack")
+    from espic_hole_tracking_b200._lib import lib  # noqa: F401
+    assert ops.default_context().status() & 8  # ESPIC_ST_BAD_INJECT_INDEX
+
+
+@pytest.mark.parametrize("v_th,v_d", [(42.85, 0.0), (1.0, 0.8), (42.85, -30.0)])
+def test_device_sampler_statistics(ops, cpu, v_th, v_d):
+    """Same distribution as draw_velocities_c (different stream): moments and a two-sample KS
+    distance against the oracle's MT19937-driven sampler."""
+    n = 400_000
+    ops.seedgenrand_c(384)
+    v_gpu = ops.draw_velocities(n, v_th, v_d).cpu().numpy()
+    v_gpu2 = ops.draw_velocities(n, v_th, v_d).cpu().numpy()
+    assert not np.array_equal(v_gpu, v_gpu2)  # the stream advances between calls
+    ops.seedgenrand_c(384)
+    assert np.array_equal(ops.draw_velocities(n, v_th, v_d).cpu().numpy(), v_gpu)  # reseeding replays it
+    cpu.seedgenrand_c(384)
+    v_cpu = cpu.draw_velocities(n, v_th, v_d)
+    assert abs((v_gpu > 0).mean() - (v_cpu > 0).mean()) < 4e-3
+    for sign in (1, -1):
+        a, b = np.sort(v_gpu[sign * v_gpu > 0]), np.sort(v_cpu[sign * v_cpu > 0])
+        assert abs(a.mean() - b.mean()) < 0.01 * v_th
+        assert abs(a.std() - b.std()) < 0.01 * v_th
+        both = np.concatenate([a, b])
+        ks = np.abs(np.searchsorted(a, both, side="right") / len(a)
+                    - np.searchsorted(b, both, side="right") / len(b)).max()
+        assert ks < 1.95 * math.sqrt((len(a) + len(b)) / (len(a) * len(b)))  # alpha ~ 1e-3
+    u = ops.operators.device_uniforms(1_000_000).cpu().numpy()
+    assert 0.0 <= u.min() and u.max() <= 1.0 and abs(u.mean() - 0.5) < 1e-3 and abs(u.var() - 1 / 12) < 1e-3
+
+
+def test_hole_tracking_filter_and_histogram(ops, cpu):
+    n_cells = 512
+    grid = wl.make_grid(n_cells)
+    dz = 6.0 / n_cells
+    rng = np.random.default_rng(4)
+    z = grid.astype(np.float64)
+    phi = (0.3 * np.exp(-((z - 0.7) / 0.5) ** 2) + 0.002 * rng.standard_normal(len(grid))).astype(np.float32)
+    fine = np.linspace(-3, 3, 1001).astype(np.float32)
+    sig = np.gradient(phi, dz).astype(np.float32)
+    r_ref = cpu.electric_field_filter(grid, sig, 0.5, fine)
+    r_gpu = ops.electric_field_filter(dev(grid), dev(sig), 0.5, dev(fine)).cpu().numpy()
+    np.testing.assert_allclose(r_gpu, r_ref, rtol=0, atol=2e-5 * np.abs(r_ref).max())
+    pos = ops.hole_position_tracking(dev(phi), dz, 0.5, dev(grid), dev(fine), 6.0 / 1000).cpu().numpy()[0]
+    assert pos == fine[np.argmax(r_ref)]
+    x = rng.uniform(-3.2, 3.2, 200_000).astype(np.float32)
+    v = (4 * rng.standard_normal(200_000)).astype(np.float32)
+    tags = (rng.random(200_000) < 0.3).astype(np.int32)
+    h_ref = cpu.histogram2d_uniform_grid(x, v, -3.0, 3.0, -8.0, 8.0, 100, 100)[0]
+    h_gpu, xc, yc = ops.histogram2d_uniform_grid(dev(x), dev(v), -3.0, 3.0, -8.0, 8.0, 100, 100)
+    np.testing.assert_array_equal(h_gpu.cpu().numpy(), h_ref)
+    h_ref0 = cpu.histogram2d_uniform_grid(x[tags == 0], v[tags == 0], -3.0, 3.0, -8.0, 8.0, 100, 100)[0]
+    h_gpu0 = ops.histogram2d_uniform_grid(dev(x), dev(v), -3.0, 3.0, -8.0, 8.0, 100, 100, tags=dev(tags))[0]
+    np.testing.assert_array_equal(h_gpu0.cpu().numpy(), h_ref0)
+
+
+def test_host_pointer_dropins(ops, cpu):
+    """The reference-named symbols with HOST arrays (what a relinked Cython extension calls)."""
+    import ctypes as C
+    from espic_hole_tracking_b200._lib import lib
+    L = lib()
+    n_cells = 512
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid)
+    _, sp = wl.make_plasma(20_000, n_cells, seed=21, holes=0.01)
+    c, h = sp.copy(), sp.copy()
+    d_ref, d_h = np.zeros_like(grid), np.zeros_like(grid)
+    cpu.move_particles(grid, mask, phi, 1e-3, -1836.0, 7.0, c.largest_index, c.particles, d_ref, c.empty_slots,
+                       c.current_empty_slot, a_b=0.0)
+    top = C.c_int(h.current_empty_slot[0])
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    L.move_particles_c(p(grid), p(mask), p(phi), 1e-3, -1836.0, 7.0, h.largest_index[0], p(h.particles), p(d_h),
+                       p(h.empty_slots), C.cast(C.byref(top), C.c_void_p), 0.0, 1, 0, len(h.empty_slots) - 1,
+                       len(grid), h.particles.shape[1])
+    assert top.value == c.current_empty_slot[0]
+    assert_bits_equal(h.particles, c.particles, "particles")
+    assert_bits_equal(h.empty_slots[:top.value + 1], c.empty_slots[:top.value + 1], "stack")
+    np.testing.assert_allclose(d_h, d_ref, rtol=0, atol=2e-6 * d_ref.max())
+    charge = (d_ref - d_ref.mean()).astype(np.float32)
+    p_ref, p_h = np.zeros_like(grid), np.zeros_like(grid)
+    cpu.poisson_solve(grid, mask, charge, 0.125, p_ref)
+    L.poisson_solve_c(p(grid), p(mask), p(charge), 0.125, p(p_h), -4.0, 1.0, 0, 0, len(grid))
+    assert np.abs(p_h - p_ref).max() <= REL * np.abs(p_ref).max()
