@@ -41,6 +41,7 @@ SIGNATURES = {
     "espic_seed": (c_int, [c_void_p, C.c_ulong]),
     "espic_draw_velocities": (c_int, [c_void_p, c_int, c_float, c_float, P]),
     "espic_genrand": (c_int, [c_void_p, c_int, P]),
+    "espic_selftest_quotient": (c_int, [c_void_p, P, c_int, C.POINTER(C.c_ulonglong)]),
     "espic_field_filter": (c_int, [c_void_p, c_int, P, P, c_float, c_int, P, P]),
     "espic_hole_position": (c_int, [c_void_p, c_int, P, P, c_double, c_float, c_int, P, P, P]),
     "espic_phase_space_histogram": (c_int, [c_void_p, P, P, c_int, P, c_int, c_float, c_float, c_float,

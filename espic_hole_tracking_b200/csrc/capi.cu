@@ -240,6 +240,11 @@ int espic_move_particles_dev(espic_ctx* ctx, const float* grid, const float* obj
                        particle_storage_length);
 }
 
+int espic_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out) {
+    if (!ctx || !grid || !counts_out || n_points < 2) return ESPIC_E_ARG;
+    return launch_selftest_quotient(ctx, grid, n_points, counts_out);
+}
+
 int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storage_length, int largest_index,
                            double v_b) {
     if (!ctx || !particles) return ESPIC_E_ARG;

@@ -23,74 +23,88 @@ struct Geom {
     float parked;    // inactive-slot marker 2*z_max
     float live_thr;  // smallest float >= 0.99*parked: (double)x < 0.99*parked  <=>  x < live_thr
     float lo_edge, hi_edge;  // z_lo + 1e-6f, z_hi - 1e-6f
-    float inv_dz;    // only used for deposit weights (tolerance-checked, not bit-checked)
+    float rcp_dz;    // RN(1/dz), for the correctly rounded quotient below
+    float half_span, near_span;  // span/2 and 1.49*span: one-compare test for "within a period"
+    float q_shift;   // trunc(z_lo/dz): cell index -> quotient estimate of x/dz (deposit weights)
     int last_cell;   // n_points - 2
+    bool fast_div;   // the 3-operation quotient is safe for this dz (normal exponent range)
 };
 
 __device__ __forceinline__ Geom make_geom(const float* __restrict__ grid, int n_points) {
     Geom g;
     g.z_lo = __ldg(grid);
     g.z_hi = __ldg(grid + n_points - 1);
-    g.dz = (g.z_hi - g.z_lo) / (float)(n_points - 1);
-    g.span = g.z_hi - g.z_lo;
+    g.dz = __fdiv_rn(__fsub_rn(g.z_hi, g.z_lo), (float)(n_points - 1));
+    g.span = __fsub_rn(g.z_hi, g.z_lo);
     g.parked = (float)(2. * (double)g.z_hi);
     g.live_thr = __double2float_ru(0.99 * (double)g.parked);
-    g.lo_edge = g.z_lo + 1.e-6f;
-    g.hi_edge = g.z_hi - 1.e-6f;
-    g.inv_dz = 1.0f / g.dz;
+    g.lo_edge = __fadd_rn(g.z_lo, 1.e-6f);
+    g.hi_edge = __fsub_rn(g.z_hi, 1.e-6f);
+    g.rcp_dz = __frcp_rn(g.dz);
+    g.half_span = 0.5f * g.span;
+    g.near_span = 1.49f * g.span;
+    g.q_shift = truncf(g.z_lo * g.rcp_dz);
     g.last_cell = n_points - 2;
+    // exponent window in which neither dz, 1/dz, the quotient nor the residual can leave the
+    // normal range for |x - z_lo| <= span
+    g.fast_div = (g.dz > 1e-18f) && (g.dz < 1e18f) && (g.span < 1e18f);
     return g;
 }
 
-// fmodf(x - z_lo, span) followed by the reference's re-basing (ref infMagSim_c.c:148-153).
-// The three branches in front are exact special cases of fmodf (identity inside one period,
-// Sterbenz-exact subtraction one period above); everything else takes the library routine,
-// which is exact as well.
-__device__ __forceinline__ float fold_periodic(const Geom& g, float x) {
-    float a = x - g.z_lo;
-    float off;
-    if (a >= 0.f && a < g.span) {
-        off = a;
-    } else if (a >= g.span && a < 2.f * g.span) {
-        off = a - g.span;
-    } else if (a < 0.f && a > -g.span) {
-        off = a;
-    } else {
-        off = fmodf(a, g.span);
-    }
-    return (off >= 0.f) ? off + g.z_lo : off + g.z_hi;
+static __device__ __noinline__ float fmod_slow(float a, float b) { return fmodf(a, b); }
+
+// RN(a/dz).  FAST: bit-identical to IEEE division in three operations (Markstein):
+// q0 = RN(a*y), r = a - q0*dz exactly (one FMA), q = RN(q0 + r*y), with y = RN(1/dz).
+// Correct whenever no intermediate leaves the normal range: kernels take the FAST
+// instantiation only when Geom::fast_div holds, and every call site passes |a| <= span
+// (positions are folded or bounds-checked first).  For a below the normal range the last place
+// may differ, which cannot change the truncation (0).  espic_selftest_quotient() checks this
+// exhaustively on the device against the division instruction for a given grid.
+template <bool FAST>
+__device__ __forceinline__ float quotient_dz(const Geom& g, float a) {
+    if (!FAST) return __fdiv_rn(a, g.dz);
+    const float q0 = __fmul_rn(a, g.rcp_dz);
+    const float r = fmaf(-q0, g.dz, a);
+    return fmaf(r, g.rcp_dz, q0);
 }
 
-// (int)((x - z_lo)/dz) with IEEE division and truncation (ref infMagSim_c.c:161-163).
-// Returns the reference's index; `bad` is raised when it lies outside [0, n_points-2]
-// (the reference prints and then indexes out of bounds; callers clamp).
-template <bool PERIODIC>
+// fmodf(x - z_lo, span) followed by the reference's re-basing (ref infMagSim_c.c:148-153).
+// Within one period either side the remainder is the dividend itself or one exact
+// (Sterbenz) subtraction; anything farther out (or NaN) takes the library routine, exact too.
+__device__ __forceinline__ float fold_periodic(const Geom& g, float x) {
+    const float a = __fsub_rn(x, g.z_lo);
+    float off = __fsub_rn(a, (a >= g.span) ? g.span : 0.f);
+    if (!(fabsf(a - g.half_span) < g.near_span)) off = fmod_slow(a, g.span);  // rare
+    return __fadd_rn(off, (off >= 0.f) ? g.z_lo : g.z_hi);
+}
+
+// (int)((x - z_lo)/dz) with IEEE division and truncation (ref infMagSim_c.c:161-163), clamped
+// into [0, n_points-2] (the reference prints "bad left_index" and then indexes out of bounds);
+// `bad` accumulates whether clamping changed anything.
+template <bool PERIODIC, bool FAST>
 __device__ __forceinline__ int cell_of(const Geom& g, float x, bool& bad) {
-    int c = (int)((x - g.z_lo) / g.dz);
-    if (PERIODIC && c > g.last_cell) c = 0;
-    bad = (c < 0) || (c > g.last_cell);
-    return c;
+    int c = __float2int_rz(quotient_dz<FAST>(g, __fsub_rn(x, g.z_lo)));
+    if (PERIODIC) c = (c > g.last_cell) ? 0 : c;
+    const int cc = min(max(c, 0), g.last_cell);
+    bad |= (cc != c);
+    return cc;
 }
 
 // Share of the particle given to its LEFT node (ref infMagSim_c.c:219-223): fmodf(x,dz)/dz
-// for x>0, 1+fmodf(x,dz)/dz otherwise.  The remainder is formed exactly (one fused
-// multiply-add against the truncated quotient, corrected by +-1 if the quotient estimate was
-// off); the division by dz is a multiplication by 1/dz, a 1-ulp liberty that only touches
-// the tolerance-checked density.  Returned as 24-bit fixed point in [0, 2^24].
-__device__ __forceinline__ unsigned left_share_fixed(const Geom& g, float x) {
-    float q = truncf(x * g.inv_dz);
-    float r = fmaf(-q, g.dz, x);
-    if (x > 0.f) {
-        if (r < 0.f) r = fmaf(-(q - 1.f), g.dz, x);
-        else if (r >= g.dz) r = fmaf(-(q + 1.f), g.dz, x);
-    } else {
-        if (r > 0.f) r = fmaf(-(q + 1.f), g.dz, x);
-        else if (r <= -g.dz) r = fmaf(-(q - 1.f), g.dz, x);
-    }
-    float share = r * g.inv_dz;
-    if (!(x > 0.f)) share = 1.0f + share;
-    share = fminf(fmaxf(share, 0.f), 1.f);
-    return __float2uint_rn(share * (float)kWeightOne);
+// for x>0, 1+fmodf(x,dz)/dz otherwise, as 24-bit fixed point in [0, 2^24].
+// The remainder is one FMA against a quotient estimate derived from the cell index (exact when
+// the estimate is the true truncated quotient; otherwise off by whole cells, which the
+// floor below removes), the division by dz a multiplication by RN(1/dz).  Those liberties are
+// <= 1 ulp and only touch the density, which is tolerance-checked, never the particle state.
+// Particles exactly on a node keep the reference's assignment (x>0: share 0, x<=0: share 1).
+__device__ __forceinline__ unsigned left_share_fixed(const Geom& g, float x, int cell) {
+    const float q = (float)cell + g.q_shift;
+    const float s = __fmul_rn(fmaf(-q, g.dz, x), g.rcp_dz);  // fmod(x,dz)/dz up to whole cells
+    const bool pos = x > 0.f;
+    float t = pos ? s : -s;
+    t = __fsub_rn(t, floorf(t));                             // in [0,1)
+    const float share = pos ? t : __fsub_rn(1.0f, t);
+    return __float2uint_rn(__fmul_rn(share, (float)kWeightOne));
 }
 
 // ---- context -------------------------------------------------------------------------------
@@ -156,6 +170,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage);
+int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);
 int launch_shift_velocities(espic_ctx* ctx, float* particles, int storage, int largest_index, double v_b);
 int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const float* charge,
                    float debye, float* potential, float obj_pot, float transparency, int boltzmann,

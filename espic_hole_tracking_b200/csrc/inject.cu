@@ -162,7 +162,7 @@ __global__ void k_inject_classify(const InjectArgs a) {
 }
 
 __device__ __forceinline__ void deposit_injected(const Geom& g, const Injected& p, unsigned long long* acc) {
-    const unsigned w0 = left_share_fixed(g, p.x);
+    const unsigned w0 = left_share_fixed(g, p.x, p.cell);
     atomicAdd(acc + p.cell, (unsigned long long)w0);
     atomicAdd(acc + p.cell + 1, (unsigned long long)(kWeightOne - w0));
 }

@@ -35,6 +35,7 @@
 namespace espic {
 
 constexpr int kMoveThreads = 256;
+constexpr int kMoveMinBlocks = 4;  // 64 registers per thread: four 8-warp CTAs per SM
 constexpr int kIterPerChunk = 32;                       // warp iterations (of 32 quads) per chunk
 constexpr int kQuadsPerChunk = 32 * kIterPerChunk;      // 1024 quads
 constexpr int kChunkSlots = 4 * kQuadsPerChunk;         // 4096 slots
@@ -62,84 +63,236 @@ struct MoveArgs {
 
 enum { ACT_NONE = 0, ACT_DEPOSIT = 1, ACT_REMOVE = 2 };
 
-// One slot of the reference's loop body (ref infMagSim_c.c:143-217), everything except the
-// deposit itself.  Bit-exact in x and v: each rounded operation of the reference is one
-// rounded intrinsic here.
+// ---------------------------------------------------------------------------------------------
+// Generic slot update: the reference's loop body (ref infMagSim_c.c:143-217) in full generality
+// (update_position on/off, absorbing object, any geometry, any position), everything except
+// the deposit.  Bit-exact in x and v: each rounded operation of the reference is one rounded
+// intrinsic here.  Used out of line for the tail of the store, for start-up calls
+// (accumulate_density / initialize_mover) and whenever the fast path below meets a case it
+// does not handle.
+// ---------------------------------------------------------------------------------------------
 template <bool PERIODIC>
-__device__ __forceinline__ int push_one(const Geom& g, float& x, float& v, const float* dv,
-                                        float dt, bool update_position, bool has_obj,
-                                        const float* __restrict__ grid,
-                                        const float* __restrict__ mask, int& cell, bool& bad_any) {
+__device__ __forceinline__ int push_generic(const Geom& g, float& x_io, float& v_io, const float* dv, float dt,
+                                            bool update_position, bool has_obj, const float* __restrict__ grid,
+                                            const float* __restrict__ mask, int& cell_out, bool& bad_any) {
+    float x = x_io, v = v_io;
     bool alive;
     if (PERIODIC) {
-        alive = x < g.live_thr;
-        if (alive) x = fold_periodic(g, x);
+        alive = x < g.live_thr;                       // ref :146
+        if (alive) x = fold_periodic(g, x);           // ref :148-153
     } else {
-        alive = (x > g.lo_edge) && (x < g.hi_edge);
+        alive = (x > g.lo_edge) && (x < g.hi_edge);   // ref :156
     }
     const bool alive_at_entry = alive;
-    cell = 0;
+    int cell = 0;
     if (alive_at_entry) {
-        bool bad;
-        cell = cell_of<PERIODIC>(g, x, bad);
-        bad_any |= bad;
-        cell = min(max(cell, 0), g.last_cell);
-        v = __fadd_rn(v, dv[cell]);
+        bool bad = false;
+        cell = cell_of<PERIODIC, false>(g, x, bad);   // ref :161-165
+        v = __fadd_rn(v, dv[cell]);                   // ref :166-168 via the per-cell kick table
         if (update_position) {
-            x = __fadd_rn(x, __fmul_rn(v, dt));
+            x = __fadd_rn(x, __fmul_rn(v, dt));       // ref :170
             if (PERIODIC) {
-                alive = x < g.live_thr;
-                if (alive) x = fold_periodic(g, x);
+                alive = x < g.live_thr;               // ref :172
+                if (alive) x = fold_periodic(g, x);   // ref :174-179
             } else {
-                alive = (x > g.lo_edge) && (x < g.hi_edge);
+                alive = (x > g.lo_edge) && (x < g.hi_edge);  // ref :182
             }
-            if (alive) {
-                cell = cell_of<PERIODIC>(g, x, bad);
-                bad_any |= bad;
-                cell = min(max(cell, 0), g.last_cell);
-            }
+            if (alive) cell = cell_of<PERIODIC, false>(g, x, bad);  // ref :185-189
         }
+        bad_any |= bad;
     }
     bool swallowed = false;
     if (has_obj && alive) {  // ref :200-210, evaluated in double there
-        float m0 = __ldg(mask + cell);
+        const float m0 = __ldg(mask + cell);
         if (m0 > 0.f) {
-            float m1 = __ldg(mask + cell + 1);
-            double covered = (m1 > 0.f) ? 1. - (double)m0 : (double)m0;
+            const float m1 = __ldg(mask + cell + 1);
+            const double covered = (m1 > 0.f) ? 1. - (double)m0 : (double)m0;
             swallowed = (double)x > (double)__ldg(grid + cell) + covered * (double)g.dz;
         }
     }
-    if (alive_at_entry || x < g.live_thr) {  // ref :211
-        if (!alive || swallowed) {
-            x = g.parked;
-            return ACT_REMOVE;
-        }
-        return ACT_DEPOSIT;
-    }
-    return ACT_NONE;
+    cell_out = cell;
+    int act = ACT_NONE;
+    if (alive_at_entry || x < g.live_thr) act = (!alive || swallowed) ? ACT_REMOVE : ACT_DEPOSIT;  // ref :211-212
+    x_io = (act == ACT_REMOVE) ? g.parked : x;
+    v_io = v;
+    return act;
+}
+
+// lo += w with the carry into hi taken from the value the atomic returns; the carry update is
+// a predicated shared-memory reduction (no branch).
+__device__ __forceinline__ void smem_add_carry(unsigned* lo, unsigned* hi, unsigned w) {
+    const unsigned old = atomicAdd(lo, w);
+    const unsigned carry = (old > ~w) ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(hi)),
+        "r"(carry)
+        : "memory");
 }
 
 template <bool SMEM>
 __device__ __forceinline__ void deposit_one(const Geom& g, float x, int cell, unsigned* s_lo,
                                             unsigned* s_hi, unsigned long long* acc) {
-    const unsigned w0 = left_share_fixed(g, x);
+    const unsigned w0 = left_share_fixed(g, x, cell);
     const unsigned w1 = kWeightOne - w0;
     if (SMEM) {
-        unsigned old0 = atomicAdd(s_lo + cell, w0);
-        unsigned old1 = atomicAdd(s_lo + cell + 1, w1);
-        if (old0 + w0 < old0) atomicAdd(s_hi + cell, 1u);
-        if (old1 + w1 < old1) atomicAdd(s_hi + cell + 1, 1u);
+        smem_add_carry(s_lo + cell, s_hi + cell, w0);
+        smem_add_carry(s_lo + cell + 1, s_hi + cell + 1, w1);
     } else {
         atomicAdd(acc + cell, (unsigned long long)w0);
         atomicAdd(acc + cell + 1, (unsigned long long)w1);
     }
 }
 
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
-
+// One quad (4 consecutive slots, possibly extending past n_slots) through the generic update:
+// scalar loads, push, deposit, scalar stores.  Returns the 4-bit mask of removed components.
 template <bool PERIODIC, bool SMEM>
-__global__ void __launch_bounds__(kMoveThreads) k_move(const MoveArgs a) {
+__device__ __noinline__ unsigned quad_generic(const MoveArgs& a, int q, int n_slots, const float* dv,
+                                              bool has_obj, unsigned* s_lo, unsigned* s_hi) {
+    const Geom g = make_geom(a.grid, a.n_points);
+    const bool upd = a.update_position != 0;
+    unsigned rem = 0;
+    bool bad_any = false;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        const int s = 4 * q + c;
+        if (s >= n_slots) break;
+        float x = a.px[s], v = a.pv[s];
+        int cell;
+        const int act = push_generic<PERIODIC>(g, x, v, dv, a.dt, upd, has_obj, a.grid, a.mask, cell, bad_any);
+        a.px[s] = x;
+        a.pv[s] = v;
+        if (act == ACT_DEPOSIT) deposit_one<SMEM>(g, x, cell, s_lo, s_hi, a.acc);
+        rem |= (act == ACT_REMOVE) ? (1u << c) : 0u;
+    }
+    if (bad_any) atomicOr(a.status, ESPIC_ST_BAD_LEFT_INDEX);
+    return rem;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast slot update: the production case (position update on, no absorbing object, dz in the
+// normal exponent range), straight-line code.  Everything it does not cover raises `rare`
+// instead of being handled: the caller then discards the quad's results and sends the quad
+// through quad_generic.  Rare cases: a position outside one period of the domain (periodic),
+// a folded position landing exactly on z_max, a cell index outside the grid, a NaN, and -- in
+// periodic mode only, where it does not occur in practice -- a removal.
+// On return x,v hold the updated slot (unchanged for dead slots), `cell` the deposit cell,
+// and the result says whether the slot deposits; `removed` (non-periodic) whether it was parked.
+// ---------------------------------------------------------------------------------------------
+template <bool PERIODIC>
+__device__ __forceinline__ bool push_fast(const Geom& g, float& x_io, float& v_io, const float* dv, float dt,
+                                          int& cell_out, bool& removed, bool& rare) {
+    const float x_in = x_io, v_in = v_io;
+    const unsigned last = (unsigned)g.last_cell;
+    if (PERIODIC) {
+        const bool alive0 = x_in < g.live_thr;                              // ref :146
+        // ref :148-153 for a position already inside the domain: fmodf is the identity
+        const float a0 = __fsub_rn(x_in, g.z_lo);
+        const float x0 = __fadd_rn(a0, g.z_lo);
+        bool odd = !(a0 >= 0.f) || !(a0 < g.span);
+        const int c0r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x0, g.z_lo)));  // ref :161
+        const int c0 = (int)min((unsigned)c0r, last);
+        odd |= (c0 != c0r);
+        const float v1 = __fadd_rn(v_in, dv[c0]);                           // ref :166-168
+        const float x1 = __fadd_rn(x0, __fmul_rn(v1, dt));                  // ref :170
+        const bool alive1 = x1 < g.live_thr;                                // ref :172
+        // ref :174-179 within one period either side of the domain
+        const float a1 = __fsub_rn(x1, g.z_lo);
+        const float off = __fsub_rn(a1, (a1 >= g.span) ? g.span : 0.f);
+        odd |= !(fabsf(a1 - g.half_span) < g.near_span);
+        const float x2 = __fadd_rn(off, (off >= 0.f) ? g.z_lo : g.z_hi);
+        const int c1r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x2, g.z_lo)));  // ref :185
+        const int c1 = (int)min((unsigned)c1r, last);
+        odd |= (c1 != c1r) || !alive1;
+        rare |= odd && alive0;
+        cell_out = c1;
+        removed = false;
+        x_io = alive0 ? x2 : x_in;
+        v_io = alive0 ? v1 : v_in;
+        return alive0;
+    } else {
+        const bool alive0 = (x_in > g.lo_edge) && (x_in < g.hi_edge);        // ref :156
+        const int c0r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x_in, g.z_lo)));  // ref :161
+        const int c0 = (int)min((unsigned)c0r, last);
+        const float v1 = __fadd_rn(v_in, dv[c0]);                           // ref :166-168
+        const float x1 = __fadd_rn(x_in, __fmul_rn(v1, dt));                // ref :170
+        const bool alive1 = (x1 > g.lo_edge) && (x1 < g.hi_edge);           // ref :182
+        const int c1r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x1, g.z_lo)));    // ref :185
+        const int c1 = (int)min((unsigned)c1r, last);
+        rare |= alive0 && ((c0 != c0r) || (alive1 && (c1 != c1r)) || !(x1 == x1));
+        cell_out = c1;
+        // ref :211-217: alive slots that left the domain, and out-of-bounds slots that do not
+        // carry the parked marker, are parked and pushed on the stack
+        removed = alive0 ? !alive1 : (x_in < g.live_thr);
+        x_io = removed ? g.parked : (alive0 ? x1 : x_in);
+        v_io = alive0 ? v1 : v_in;
+        return alive0 && alive1;
+    }
+}
+
+struct Quad {
+    float x[4], v[4];
+};
+
+__device__ __forceinline__ void load_quad(const MoveArgs& a, int q, Quad& p) {
+    const float4 xx = __ldcs(reinterpret_cast<const float4*>(a.px) + q);
+    const float4 vv = __ldcs(reinterpret_cast<const float4*>(a.pv) + q);
+    p.x[0] = xx.x; p.x[1] = xx.y; p.x[2] = xx.z; p.x[3] = xx.w;
+    p.v[0] = vv.x; p.v[1] = vv.y; p.v[2] = vv.z; p.v[3] = vv.w;
+}
+
+__device__ __forceinline__ void store_quad(const MoveArgs& a, int q, const Quad& p) {
+    __stcs(reinterpret_cast<float4*>(a.px) + q, make_float4(p.x[0], p.x[1], p.x[2], p.x[3]));
+    __stcs(reinterpret_cast<float4*>(a.pv) + q, make_float4(p.v[0], p.v[1], p.v[2], p.v[3]));
+}
+
+// Fast path for one complete quad held in registers: push the four slots; if the warp met no
+// rare case, deposit and store; otherwise redo this quad generically from memory.
+template <bool PERIODIC, bool SMEM>
+__device__ __forceinline__ unsigned quad_fast(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
+                                              const float* dv, unsigned* s_lo, unsigned* s_hi) {
+    int cell[4];
+    unsigned dep = 0, rem = 0;
+    bool rare = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        bool removed;
+        const bool d = push_fast<PERIODIC>(g, p.x[c], p.v[c], dv, a.dt, cell[c], removed, rare);
+        dep |= d ? (1u << c) : 0u;
+        rem |= removed ? (1u << c) : 0u;
+    }
+    if (__any_sync(0xffffffffu, rare)) {  // uniform, practically never taken
+        return quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, false, s_lo, s_hi);
+    }
+    store_quad(a, q, p);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (dep & (1u << c)) deposit_one<SMEM>(g, p.x[c], cell[c], s_lo, s_hi, a.acc);
+    return rem;
+}
+
+// Ordered compaction of the removed slot ids of one warp iteration (ascending slot order):
+// lanes hold consecutive quads, so a lane's ids follow all ids of lower lanes.
+__device__ __forceinline__ void stage_removed(unsigned rem, int q, int lane, int* stage, int& removed) {
+    if (__ballot_sync(0xffffffffu, rem != 0u)) {  // uniform
+        const unsigned b0 = __ballot_sync(0xffffffffu, rem & 1u);
+        const unsigned b1 = __ballot_sync(0xffffffffu, rem & 2u);
+        const unsigned b2 = __ballot_sync(0xffffffffu, rem & 4u);
+        const unsigned b3 = __ballot_sync(0xffffffffu, rem & 8u);
+        const unsigned lt = (1u << lane) - 1u;
+        int pos = removed + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (rem & (1u << c)) stage[pos++] = 4 * q + c;
+        removed += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+    }
+}
+
+// FAST: interior chunks run the register fast path on float4 quads; everything else (the last
+// chunk of the store, unaligned stores, start-up calls with update_position=0, an absorbing
+// object, exotic dz) goes quad by quad through quad_generic.
+template <bool PERIODIC, bool SMEM>
+__global__ void __launch_bounds__(kMoveThreads, kMoveMinBlocks) k_move(const MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_points = a.n_points;
     const int n_pad = (n_points + 3) & ~3;
@@ -156,8 +309,8 @@ __global__ void __launch_bounds__(kMoveThreads) k_move(const MoveArgs a) {
         for (int j = tid; j < n_points; j += blockDim.x) {
             if (j < n_points - 1) {
                 // ref :166-168, hoisted from the particle loop to once per cell
-                float e_cell = __fdiv_rn(-__fsub_rn(__ldg(a.phi + j + 1), __ldg(a.phi + j)), g.dz);
-                float kick = __fsub_rn(__fmul_rn(a.qm, e_cell), a.a_b);
+                const float e_cell = __fdiv_rn(-__fsub_rn(__ldg(a.phi + j + 1), __ldg(a.phi + j)), g.dz);
+                const float kick = __fsub_rn(__fmul_rn(a.qm, e_cell), a.a_b);
                 s_dv[j] = __fmul_rn(kick, a.dt);
             }
             s_lo[j] = 0u;
@@ -173,100 +326,44 @@ __global__ void __launch_bounds__(kMoveThreads) k_move(const MoveArgs a) {
 
     const int lane = tid & 31;
     const int warps_per_cta = blockDim.x >> 5;
-    const int gw = (tid >> 5) * gridDim.x + blockIdx.x;  // interleave warps of all CTAs
+    const int gw = (tid >> 5) * gridDim.x + blockIdx.x;  // interleave the warps of all CTAs
     const int total_warps = warps_per_cta * gridDim.x;
     const int n_slots = (a.largest_index_dev ? *a.largest_index_dev : a.largest_index) + 1;
     const int n_quads = (n_slots + 3) >> 2;
+    const int n_full_quads = n_slots >> 2;
     const int n_chunks = (n_quads + kQuadsPerChunk - 1) / kQuadsPerChunk;
-    const bool upd = a.update_position != 0;
-    const float dt = a.dt;
-    bool bad_any = false;
-
-    float4* x4 = reinterpret_cast<float4*>(a.px);
-    float4* v4 = reinterpret_cast<float4*>(a.pv);
+    const bool fast = a.vec_ok && a.update_position != 0 && !has_obj && g.fast_div;  // uniform
 
     for (int chunk = gw; chunk < n_chunks; chunk += total_warps) {
         int removed = 0;
         int* stage = a.staging + (size_t)chunk * kChunkSlots;
         const int qbase = chunk * kQuadsPerChunk;
+        if (fast && qbase + kQuadsPerChunk <= n_full_quads) {
 #pragma unroll 1
-        for (int it = 0; it < kIterPerChunk; it += 2) {
-            const int q[2] = {qbase + it * 32 + lane, qbase + (it + 1) * 32 + lane};
-            if (qbase + it * 32 >= n_quads) break;  // warp-uniform
-            float X[2][4], V[2][4];
-            // issue all loads of both quads before touching either (memory-level parallelism)
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (q[u] < n_quads) {
-                    if (a.vec_ok) {
-                        float4 xx = ld_stream(x4 + q[u]);
-                        float4 vv = ld_stream(v4 + q[u]);
-                        X[u][0] = xx.x; X[u][1] = xx.y; X[u][2] = xx.z; X[u][3] = xx.w;
-                        V[u][0] = vv.x; V[u][1] = vv.y; V[u][2] = vv.z; V[u][3] = vv.w;
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            int s = 4 * q[u] + c;
-                            X[u][c] = (s < n_slots) ? a.px[s] : g.parked;
-                            V[u][c] = (s < n_slots) ? a.pv[s] : 0.f;
-                        }
-                    }
+            for (int it = 0; it < kIterPerChunk; it += 2) {
+                const int q0 = qbase + it * 32 + lane, q1 = q0 + 32;
+                Quad p0, p1;
+                load_quad(a, q0, p0);  // both quads' loads are issued before either is used
+                load_quad(a, q1, p1);
+                const unsigned r0 = quad_fast<PERIODIC, SMEM>(a, g, p0, q0, n_slots, dv, s_lo, s_hi);
+                const unsigned r1 = quad_fast<PERIODIC, SMEM>(a, g, p1, q1, n_slots, dv, s_lo, s_hi);
+                if (!PERIODIC || __any_sync(0xffffffffu, (r0 | r1) != 0u)) {
+                    stage_removed(r0, q0, lane, stage, removed);
+                    stage_removed(r1, q1, lane, stage, removed);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                unsigned rem_mask = 0;
-                if (q[u] < n_quads) {
-                    int cell[4];
-                    int act[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const bool in_range = (4 * q[u] + c) < n_slots;
-                        act[c] = ACT_NONE;
-                        cell[c] = 0;
-                        if (in_range)
-                            act[c] = push_one<PERIODIC>(g, X[u][c], V[u][c], dv, dt, upd, has_obj,
-                                                        a.grid, a.mask, cell[c], bad_any);
-                    }
-                    if (a.vec_ok) {
-                        st_stream(x4 + q[u], make_float4(X[u][0], X[u][1], X[u][2], X[u][3]));
-                        st_stream(v4 + q[u], make_float4(V[u][0], V[u][1], V[u][2], V[u][3]));
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            int s = 4 * q[u] + c;
-                            if (s < n_slots) {
-                                a.px[s] = X[u][c];
-                                a.pv[s] = V[u][c];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (act[c] == ACT_DEPOSIT)
-                            deposit_one<SMEM>(g, X[u][c], cell[c], s_lo, s_hi, a.acc);
-                        rem_mask |= (act[c] == ACT_REMOVE) ? (1u << c) : 0u;
-                    }
-                }
-                // ordered compaction of removed slot ids (ascending slot order)
-                if (__ballot_sync(0xffffffffu, rem_mask != 0u)) {
-                    const unsigned b0 = __ballot_sync(0xffffffffu, rem_mask & 1u);
-                    const unsigned b1 = __ballot_sync(0xffffffffu, rem_mask & 2u);
-                    const unsigned b2 = __ballot_sync(0xffffffffu, rem_mask & 4u);
-                    const unsigned b3 = __ballot_sync(0xffffffffu, rem_mask & 8u);
-                    const unsigned lt = (1u << lane) - 1u;
-                    int pos = removed + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) +
-                              __popc(b3 & lt);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (rem_mask & (1u << c)) stage[pos++] = 4 * q[u] + c;
-                    removed += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-                }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < kIterPerChunk; ++it) {
+                if (qbase + it * 32 >= n_quads) break;  // uniform
+                const int q = qbase + it * 32 + lane;
+                unsigned r = 0;
+                if (q < n_quads) r = quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, has_obj, s_lo, s_hi);
+                stage_removed(r, q, lane, stage, removed);
             }
         }
         if (lane == 0) a.counts[chunk] = removed;
     }
-    if (bad_any) atomicOr(a.status, ESPIC_ST_BAD_LEFT_INDEX);
 
     if (SMEM) {
         __syncthreads();
@@ -513,6 +610,37 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                                                             largest_allowed_slot);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "mover epilogue launch");
+}
+
+// Every float a in [0, span]: fast quotient vs the division instruction.
+__global__ void k_selftest_quotient(const float* __restrict__ grid, int n_points, unsigned long long* counts) {
+    const Geom g = make_geom(grid, n_points);
+    const unsigned hi = __float_as_uint(g.span);
+    unsigned long long bad_cell = 0, bad_bits = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= hi; i += stride) {
+        const float a = __uint_as_float((unsigned)i);
+        const float qf = quotient_dz<true>(g, a);
+        const float qr = __fdiv_rn(a, g.dz);
+        if (__float2int_rz(qf) != __float2int_rz(qr)) ++bad_cell;
+        if (a >= 1e-30f && __float_as_uint(qf) != __float_as_uint(qr)) ++bad_bits;
+    }
+    if (!g.fast_div) bad_cell = bad_bits = 0;  // the kernels use the division instruction for such grids
+    if (bad_cell) atomicAdd(counts, bad_cell);
+    if (bad_bits) atomicAdd(counts + 1, bad_bits);
+}
+
+int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out) {
+    int rc = ensure(ctx, ctx->inject_ws, 64, "selftest workspace");
+    if (rc) return rc;
+    unsigned long long* d = (unsigned long long*)((char*)ctx->inject_ws.ptr + 32);
+    ESPIC_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    k_selftest_quotient<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(grid, n_points, d);
+    ctx->launches++;
+    ESPIC_CUDA(ctx, cudaGetLastError());
+    ESPIC_CUDA(ctx, cudaMemcpyAsync(counts_out, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    ESPIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 int launch_shift_velocities(espic_ctx* ctx, float* particles, int storage, int largest_index, double v_b) {

@@ -1,0 +1,340 @@
+"""Device-resident mirror of the reference's simulation driver loop (infMagSim_script.py).
+
+Keeps the reference driver's structure -- config keys of ``input.txt`` (:22-79), the particle
+stores / free-slot stacks / one-element scalars (:395-416, 485-489, 505-530, 614-618), the
+start-up sequence accumulate_density -> initialize_mover (:696-716) and the per-step order of
+the loop (:756-1023): density all-reduce, end-node fix, charge density, field solve, hole
+tracking, ion push, electron push, wall injection -- and calls the operator layer for every one
+of them.  All state lives in HBM; a step enqueues kernels and never synchronises with the host.
+
+Particles are sharded over ranks exactly as the reference shards them over MPI ranks: each
+rank owns private particle stores and a full copy of the grids, deposits with
+background_density = n*P*dz/(z_max-z_min) (:402, :510) and the only per-step exchange is the
+sum all-reduce of the density grids (:763, :773), here ONE collective over the concatenated
+[2, n_points] ion+electron buffer.
+
+Out of scope: the moving-box controller and its filtfilt (:917-928; the
+reference default is moving_box_simulation=False, so the box velocity stays v_b_0 and a_b=0),
+the absorbing-object geometry helper (:192-246; object_mask stays zero as in every config),
+counter-streaming beams, Boltzmann/quasineutral/prescribed-potential modes, plotting and .npz
+output.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import operators as ops
+from ._lib import Context
+
+
+@dataclass
+class SimConfig:
+    # ---- input.txt keys (infMagSim_script.py:22-79); names as in the file ----
+    n_steps: int = 100
+    n_particles: int = 100_000          # per rank, per species
+    n_cells: int = 512
+    step_size: float = 0.3
+    v_d_i: float = 0.0
+    v_b_0: float = 0.0
+    dimple_velocity: float = 0.0
+    dimple_height: float = 0.95
+    dimple_velocity_width: float = 0.3
+    dimple_spatial_width: float = 4.0
+    mass_ratio: float = 1836.0
+    sigma: float = 1.0                   # "Te/Ti"
+    hole_tracking_end_step: int = 0
+    w_ion_perturbation: float = 0.0
+    amplitude_perturbation: float = 0.0
+    background_acceleration: float = 0.0
+    hole_pushing_start_step: int = 0
+    hole_pushing_end_step: int = 0
+    density_growth_start_step: int = 0   # "background_density_growth_start_step"
+    density_growth_rate: float = 0.0
+    # ---- module-level flags the reference hard-codes (:133-189, 256-273, 396-406, 720-744) ----
+    periodic_particles: bool = False
+    time_steps_immobile_ions: int = 30000
+    time_steps_immobile_electrons: int = 0
+    create_electron_dimple: bool = True
+    debye_length: float = 0.125
+    z_min: float = -3.0
+    z_max: float = 3.0
+    extra_storage_factor: float = 1.25   # the reference uses 10 (:401); 1.25 is ample
+    n_tracking_mesh_points: int = 1001
+    initial_transient_steps: int = 80
+    track_hole: bool = True
+    phase_space_histograms: bool = False
+    seed: int = 384
+
+    _KEYS = {"n_steps": int, "n_particles": int, "step_size": float, "v_d_i": float,
+             "dimple_velocity": float, "dimple_height": float, "dimple_velocity_width": float,
+             "dimple_spatial_width": float, "mass_ratio": float, "Te/Ti": float, "v_b_0": float,
+             "n_cells": int, "hole_tracking_end_step": int, "w_ion_perturbation": float,
+             "amplitude_perturbation": float, "background_acceleration": float,
+             "hole_pushing_start_step": int, "hole_pushing_end_step": int,
+             "background_density_growth_start_step": int, "density_growth_rate": float}
+
+    @classmethod
+    def from_input_file(cls, path: str, **overrides) -> "SimConfig":
+        """Whitespace-separated ``key value`` lines, the reference's format (:33-79)."""
+        rename = {"Te/Ti": "sigma", "background_density_growth_start_step": "density_growth_start_step"}
+        kw = {}
+        with open(path) as fh:
+            for line in fh:
+                parts = line.split()
+                if len(parts) >= 2 and parts[0] in cls._KEYS:
+                    kw[rename.get(parts[0], parts[0])] = cls._KEYS[parts[0]](parts[1])
+        kw.update(overrides)
+        return cls(**kw)
+
+
+def expected_particle_injection(n_infinity, v_th, v_d, dt):
+    """Wall flux of a drifting Maxwellian through both ends (infMagSim_script.py:414-416)."""
+    beta = v_d / (math.sqrt(2.) * v_th)
+    return (2 * n_infinity * v_th / math.sqrt(2. * math.pi) * math.exp(-beta ** 2) * dt
+            + n_infinity * v_d * math.erf(beta) * dt)
+
+
+class DeviceUniformSampler:
+    """Partial-step fractions drawn on the device (same role as uniform_2d_sampler.get(n)[:,0])."""
+    shared_seed = False
+
+    def __init__(self, ctx: Context, device):
+        self.ctx, self.device = ctx, device
+
+    def get_device(self, n):
+        return ops.device_uniforms(n, device=self.device, ctx=self.ctx)
+
+
+class SpeciesStore:
+    """One species: float32 [2,S] store, int32 [1,S] tags, int32 [S] LIFO stack, device scalars."""
+
+    def __init__(self, n_active: int, storage: int, charge_to_mass: float, v_th: float, parked: float, device):
+        self.n0 = n_active
+        self.storage = storage
+        self.charge_to_mass = charge_to_mass
+        self.v_th = v_th
+        self.particles = torch.empty((2, storage), dtype=torch.float32, device=device)
+        self.particles[0, n_active:] = parked            # :484-485
+        self.particles[1, n_active:] = 0.0
+        self.tags = torch.zeros((1, storage), dtype=torch.int32, device=device)
+        # free slots listed in reverse so the lowest is popped first (:486-489)
+        self.empty_slots = torch.full((storage,), -1, dtype=torch.int32, device=device)
+        n_free = storage - n_active
+        if n_free > 0:
+            self.empty_slots[:n_free] = torch.arange(storage - 1, n_active - 1, -1, dtype=torch.int32, device=device)
+        self.current_empty_slot = ops.DeviceInt(n_free - 1, device=device)
+        self.largest_index = ops.DeviceInt(n_active - 1, device=device)
+
+
+class Simulation:
+    def __init__(self, cfg: SimConfig, rank: int = 0, world_size: int = 1, device=None, process_group=None,
+                 injection_sampler=None):
+        self.cfg = cfg
+        self.rank, self.world = rank, world_size
+        self.pg = process_group
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.ctx = ops.default_context(self.device)
+        c = cfg
+        n_points = c.n_cells + 1
+        grid64, dz = np.linspace(c.z_min, c.z_max, num=n_points, endpoint=True, retstep=True)  # :263
+        self.dz = float(dz)
+        self.n_points = n_points
+        self.grid = torch.from_numpy(grid64.astype(np.float32)).to(self.device)
+        fine = np.linspace(c.z_min, c.z_max, num=c.n_tracking_mesh_points, endpoint=True)
+        self.fine_mesh = torch.from_numpy(fine.astype(np.float32)).to(self.device)
+        self.seed = c.seed + rank ** 3                                    # :277
+        ops.seedgenrand_c(self.seed, ctx=self.ctx)                         # :278
+        self.host_rng = np.random.RandomState(self.seed % (2 ** 32))       # np.random.seed(seed), :313
+        self.v_th_i = 1.0
+        self.v_th_e = math.sqrt(c.mass_ratio)                              # :509
+        self.dt = c.step_size * c.debye_length / self.v_th_e               # :660
+        self.background_density = c.n_particles * world_size * self.dz / (c.z_max - c.z_min)  # :402,510
+        self.parked = 2 * c.z_max                                          # :406
+        storage = int(math.ceil(c.extra_storage_factor * c.n_particles / 4.0)) * 4
+        self.ions = SpeciesStore(c.n_particles, storage, 1.0, self.v_th_i / math.sqrt(c.sigma), self.parked,
+                                 self.device)
+        self.electrons = SpeciesStore(c.n_particles, storage, -c.mass_ratio, self.v_th_e, self.parked,
+                                      self.device)
+        z = lambda: torch.zeros(n_points, dtype=torch.float32, device=self.device)
+        self.object_mask = z()
+        self.potential = z()
+        self.densities = torch.zeros((2, n_points), dtype=torch.float32, device=self.device)
+        self.ion_density, self.electron_density = self.densities[0], self.densities[1]
+        self.charge_density = z()
+        self.background_potential = torch.from_numpy(
+            np.linspace(c.background_acceleration, 0., num=n_points, endpoint=True).astype(np.float32)).to(self.device)
+        self.set_background_acceleration = 0 < c.hole_pushing_start_step < c.n_steps  # :149-152
+        self.hole_relative_positions = torch.zeros(max(c.n_steps, 1), dtype=torch.float32, device=self.device)
+        self.sampler = injection_sampler or DeviceUniformSampler(self.ctx, self.device)
+        self.k = 0
+        self.t = 0.0
+        self.v_b = c.v_b_0     # box velocity (moving box disabled: constant), :730-736
+        self.a_b = 0.0
+        self.hist = {}
+
+    # ---- particle initialisation ----------------------------------------------------------
+    def load_particles(self, ions_xv: np.ndarray, electrons_xv: np.ndarray) -> None:
+        """Identical initial particle arrays on both sides of a parity test: float32 [2, n]."""
+        for store, xv in ((self.ions, ions_xv), (self.electrons, electrons_xv)):
+            n = xv.shape[1]
+            assert n == store.n0
+            store.particles[:, :n] = torch.from_numpy(np.ascontiguousarray(xv, dtype=np.float32)).to(self.device)
+
+    def init_synthetic(self, perturb: float = 0.01) -> None:
+        """Uniform positions with a small sinusoidal displacement, Maxwellian velocities, and the
+        reference's phase-space "dimple" carved out of the electrons by rejection
+        (infMagSim_script.py:518-520, 602-613).  Generated on the device (torch RNG)."""
+        c = self.cfg
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(self.seed)
+        L = c.z_max - c.z_min
+        for store, dimple in ((self.ions, False), (self.electrons, c.create_electron_dimple and not c.periodic_particles)):
+            n = store.n0
+            x = torch.rand(n, generator=gen, device=self.device, dtype=torch.float64) * L + c.z_min
+            x = x + perturb * torch.sin(2 * math.pi * x / L)
+            v = torch.randn(n, generator=gen, device=self.device, dtype=torch.float32) * store.v_th
+            if dimple:
+                sig = self.v_th_e * c.dimple_velocity_width
+                lam = c.dimple_spatial_width * c.debye_length
+                todo = torch.arange(n, device=self.device)
+                while todo.numel() > 0:   # re-draw the velocity of rejected samples (:536-613)
+                    vv, xx = v[todo].double(), x[todo]
+                    dim = c.dimple_height * torch.exp(-(vv - c.dimple_velocity) ** 2 / (2 * sig ** 2)) \
+                        / (1. + 0.0002 * torch.exp(torch.abs(xx) / lam))
+                    rej = torch.rand(todo.numel(), generator=gen, device=self.device, dtype=torch.float64) < dim
+                    todo = todo[rej]
+                    if todo.numel():
+                        v[todo] = torch.randn(todo.numel(), generator=gen, device=self.device,
+                                              dtype=torch.float32) * store.v_th
+            store.particles[0, :n] = x.float()
+            store.particles[1, :n] = v
+
+    # ---- start-up (infMagSim_script.py:696-716) --------------------------------------------
+    def initialize(self) -> None:
+        c = self.cfg
+        for store, den in ((self.ions, self.ion_density), (self.electrons, self.electron_density)):
+            ops.accumulate_density(self.grid, self.object_mask, self.background_density, store.largest_index,
+                                   store.particles, den, store.empty_slots, store.current_empty_slot,
+                                   periodic_particles=c.periodic_particles, use_pure_c_version=True, ctx=self.ctx)
+        for store in (self.ions, self.electrons):
+            ops.initialize_mover(self.grid, self.object_mask, self.potential, self.dt, store.charge_to_mass,
+                                 store.largest_index, store.particles, store.empty_slots,
+                                 store.current_empty_slot, v_b=self.v_b, a_b=0.0,
+                                 periodic_particles=c.periodic_particles, use_pure_c_version=True, ctx=self.ctx)
+
+    # ---- one timestep (infMagSim_script.py:756-1023) ---------------------------------------
+    def reduce_densities(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.densities, op=dist.ReduceOp.SUM, group=self.pg)   # :763, :773 in one call
+
+    def injection_counts(self, k: int):
+        """Expected wall flux with stochastic rounding (:965-975, 1005-1009)."""
+        c = self.cfg
+        L = c.z_max - c.z_min
+        growth = math.exp(max(0, k - c.density_growth_start_step) * c.density_growth_rate * c.step_size)
+        w_ion = c.w_ion_perturbation * self.v_th_e / c.debye_length * math.sqrt(1. / c.mass_ratio)   # :663
+        e_i = expected_particle_injection(c.n_particles / L, self.v_th_i / math.sqrt(c.sigma), self.v_b - c.v_d_i,
+                                          self.dt)
+        e_i *= (1 - c.amplitude_perturbation * math.sin(max(0, k - c.hole_tracking_end_step) * self.dt * w_ion))
+        e_i *= growth
+        n_i = int(e_i)
+        if (e_i - n_i) > self.host_rng.rand():
+            n_i += 1
+        e_e = expected_particle_injection(c.n_particles / L, self.v_th_e, self.v_b, self.dt) * growth
+        n_e = int(e_e)
+        if (e_e - n_e) > self.host_rng.rand():
+            n_e += 1
+        return n_i, n_e
+
+    def step(self) -> None:
+        c, k = self.cfg, self.k
+        periodic = c.periodic_particles
+        self.reduce_densities()
+        ops.prepare_charge(self.ion_density, self.electron_density, self.charge_density, periodic_particles=periodic,
+                           fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True, ctx=self.ctx)
+        ops.poisson_solve(self.grid, self.object_mask, self.charge_density, c.debye_length, self.potential,
+                          object_potential=-3., object_transparency=1., boltzmann_electrons=False,
+                          periodic_potential=periodic, use_pure_c_version=True, ctx=self.ctx)   # :831-836
+        if self.set_background_acceleration and c.hole_pushing_start_step <= k < c.hole_pushing_end_step:
+            potential_ions = self.potential + self.background_potential                          # :852-855
+        else:
+            potential_ions = self.potential
+        if c.phase_space_histograms:
+            self.phase_space()
+        if c.track_hole and k > c.initial_transient_steps and k < self.hole_relative_positions.shape[0]:  # :896-897
+            ops.hole_position_tracking(self.potential, self.dz, c.debye_length * 4., self.grid, self.fine_mesh,
+                                       out=self.hole_relative_positions[k:k + 1], ctx=self.ctx)
+        s = self.ions
+        ions_mobile = k <= c.time_steps_immobile_ions                                            # :929-939
+        ops.move_particles(self.grid, self.object_mask, potential_ions, self.dt if ions_mobile else 0.,
+                           s.charge_to_mass, self.background_density, s.largest_index, s.particles,
+                           self.ion_density, s.empty_slots, s.current_empty_slot, self.a_b,
+                           periodic_particles=periodic, use_pure_c_version=True, ctx=self.ctx)
+        if not ions_mobile:
+            self.ion_density.fill_(1.0)                                                          # :934
+        s = self.electrons
+        ops.move_particles(self.grid, self.object_mask, self.potential,
+                           0. if k < c.time_steps_immobile_electrons else self.dt, s.charge_to_mass,
+                           self.background_density, s.largest_index, s.particles, self.electron_density,
+                           s.empty_slots, s.current_empty_slot, self.a_b, periodic_particles=periodic,
+                           use_pure_c_version=True, ctx=self.ctx)                                # :940-950
+        if not periodic:
+            n_i, n_e = self.injection_counts(k)
+            if n_i > 0 and ions_mobile:                                                          # :986-1000
+                s = self.ions
+                ops.inject_particles(n_i, self.grid, self.dt, self.v_th_i / math.sqrt(c.sigma),
+                                     self.background_density, self.sampler, self.v_b - c.v_d_i, self.a_b, k,
+                                     s.tags, s.particles, s.empty_slots, s.current_empty_slot, s.largest_index,
+                                     self.ion_density, ctx=self.ctx)
+            if n_e > 0:                                                                          # :1015-1019
+                s = self.electrons
+                ops.inject_particles(n_e, self.grid, self.dt, self.v_th_e, self.background_density, self.sampler,
+                                     self.v_b, self.a_b, k, s.tags, s.particles, s.empty_slots,
+                                     s.current_empty_slot, s.largest_index, self.electron_density, ctx=self.ctx)
+        self.t += self.dt
+        self.k += 1
+
+    def phase_space(self) -> None:
+        """The three per-step 100x100 histograms (:865-895); results stay on the device."""
+        c = self.cfg
+        i, e = self.ions, self.electrons
+        vi, ve = 20. * self.v_th_i, 4. * self.v_th_e
+        self.hist["ions"] = ops.histogram2d_uniform_grid(i.particles[0], i.particles[1], c.z_min, c.z_max, -vi, vi,
+                                                         100, 100, ctx=self.ctx)[0]
+        self.hist["electrons"] = ops.histogram2d_uniform_grid(e.particles[0], e.particles[1], c.z_min, c.z_max,
+                                                              -ve, ve, 100, 100, ctx=self.ctx)[0]
+        self.hist["electrons_inject0"] = ops.histogram2d_uniform_grid(
+            e.particles[0], e.particles[1], c.z_min, c.z_max, -ve, ve, 100, 100, tags=e.tags, tag_value=0,
+            ctx=self.ctx)[0]
+        if self.world > 1:
+            import torch.distributed as dist
+            for h in self.hist.values():
+                dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.pg)                          # :876,894,895
+
+    def run(self, n_steps: int) -> None:
+        for _ in range(n_steps):
+            self.step()
+
+    # ---- diagnostics ------------------------------------------------------------------------
+    def energies(self):
+        """Kinetic and field energy (the reference computes none; SURVEY.md s.8d defines them):
+        KE = 1/2 sum m v^2 / background_density per species (m_i = 1, m_e = 1/mass_ratio),
+        FE = 1/2 lambda_D^2 sum E_cell^2 dz."""
+        c = self.cfg
+        out = {}
+        for name, s, mass in (("ions", self.ions, 1.0), ("electrons", self.electrons, 1.0 / c.mass_ratio)):
+            alive = s.particles[0] < 0.99 * self.parked
+            v = s.particles[1].double()
+            out["ke_" + name] = float(0.5 * mass * (v * v * alive).sum().item() / self.background_density)
+        e = -(self.potential[1:] - self.potential[:-1]).double() / self.dz
+        out["fe"] = float(0.5 * c.debye_length ** 2 * (e * e).sum().item() * self.dz)
+        return out
+
+    def n_active(self):
+        return {name: int((s.particles[0] < 0.99 * self.parked).sum().item())
+                for name, s in (("ions", self.ions), ("electrons", self.electrons))}

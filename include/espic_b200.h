@@ -138,6 +138,14 @@ int espic_seed(espic_ctx *ctx, unsigned long seed);
 int espic_draw_velocities(espic_ctx *ctx, int n, float v_th, float v_d, float *v_out);
 int espic_genrand(espic_ctx *ctx, int n, float *out);
 
+/* Exhaustive device-side check of the mover's 3-operation quotient RN((x-z_lo)/dz) (see
+ * quotient_dz in csrc/espic_internal.cuh) against the IEEE division instruction, over EVERY
+ * float a in [0, span] for this grid.  counts_out (host, 2 values): [0] = inputs whose
+ * truncated quotient (the cell index) differs -- must be 0; [1] = normal-range inputs whose
+ * quotient differs in any bit -- must be 0.  Synchronises. */
+int espic_selftest_quotient(espic_ctx *ctx, const float *grid, int n_points,
+                            unsigned long long *counts_out);
+
 /* ---- "next" rows: per-step diagnostics ---------------------------------------------------- */
 /* Replaces electric_field_filter_c (ref infMagSim_c.c:668-683). Device arrays. */
 int espic_field_filter(espic_ctx *ctx, int n_points, const float *grid, const float *data,

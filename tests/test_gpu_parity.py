@@ -173,6 +173,18 @@ def test_mover_large_grid_path(ops, cpu, periodic):
     check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, periodic)
 
 
+@pytest.mark.parametrize("n_cells", [500, 512, 1000, 4096, 65536])
+def test_fast_quotient_is_ieee_division_exhaustively(ops, n_cells):
+    """The mover replaces the division in (x - z_min)/dz by a 3-operation sequence; this checks
+    it against the division instruction for EVERY float in [0, z_max - z_min] on the device."""
+    import ctypes as C
+    ctx = ops.default_context()
+    grid = dev(wl.make_grid(n_cells))
+    counts = (C.c_ulonglong * 2)()
+    ctx.check(ctx._lib.espic_selftest_quotient(ctx.handle, C.c_void_p(grid.data_ptr()), len(grid), counts))
+    assert counts[0] == 0 and counts[1] == 0, list(counts)
+
+
 def test_accumulate_density_and_initialize_mover(ops, cpu):
     n_cells = 512
     grid = wl.make_grid(n_cells)
