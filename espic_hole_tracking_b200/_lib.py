@@ -36,6 +36,8 @@ SIGNATURES = {
     "espic_shift_velocities": (c_int, [c_void_p, P, c_int, c_int, c_double]),
     "espic_poisson_solve": (c_int, [c_void_p, P, P, P, c_float, P, c_float, c_float, c_int, c_int, c_int]),
     "espic_prepare_charge": (c_int, [c_void_p, P, P, P, c_int, c_int, c_int, c_int]),
+    "espic_field_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_float, P, c_float, c_float,
+                                  c_int, c_int, c_int]),
     "espic_inject_particles": (c_int, [c_void_p, c_int, P, c_int, c_float, c_float, P, P, c_float, c_int,
                                        P, P, c_int, P, P, P, P]),
     "espic_seed": (c_int, [c_void_p, C.c_ulong]),

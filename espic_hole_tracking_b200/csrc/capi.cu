@@ -268,6 +268,18 @@ int espic_prepare_charge(espic_ctx* ctx, float* ion_density, float* electron_den
                                  fix_electrons);
 }
 
+int espic_field_solve(espic_ctx* ctx, const float* grid, const float* object_mask, float* ion_density,
+                      float* electron_density, float* charge, int periodic_particles, int fix_ions,
+                      int fix_electrons, float debye_length, float* potential, float object_potential,
+                      float object_transparency, int boltzmann_electrons, int periodic_potential, int n_points) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !object_mask || !ion_density || !electron_density || !charge || !potential)
+        return fail(ctx, ESPIC_E_ARG, "espic_field_solve: null pointer argument");
+    return launch_field_solve(ctx, grid, object_mask, ion_density, electron_density, charge, periodic_particles,
+                              fix_ions, fix_electrons, debye_length, potential, object_potential,
+                              object_transparency, boltzmann_electrons, periodic_potential, n_points);
+}
+
 int espic_inject_particles(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt,
                            float background_density, const float* velocities, const float* uniform01, float a_b,
                            int k, int* particles_hist, float* particles, int particle_storage_length,

@@ -175,6 +175,10 @@ int launch_shift_velocities(espic_ctx* ctx, float* particles, int storage, int l
 int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const float* charge,
                    float debye, float* potential, float obj_pot, float transparency, int boltzmann,
                    int periodic, int n_points);
+int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, float* ion, float* ele,
+                       float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
+                       float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
+                       int n_points);
 int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge, int n, int periodic,
                           int fix_i, int fix_e);
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,

@@ -49,6 +49,7 @@ struct MoveArgs {
     float* pv;
     int* staging;
     int* counts;
+    int* total_removed;  // sum of counts[] (lets k_finish skip the scan when nothing left)
     unsigned long long* acc;
     int* status;
     const int* largest_index_dev;
@@ -362,7 +363,10 @@ __global__ void __launch_bounds__(kMoveThreads, kMoveMinBlocks) k_move(const Mov
                 stage_removed(r, q, lane, stage, removed);
             }
         }
-        if (lane == 0) a.counts[chunk] = removed;
+        if (lane == 0) {
+            a.counts[chunk] = removed;
+            if (removed) atomicAdd(a.total_removed, removed);
+        }
     }
 
     if (SMEM) {
@@ -399,73 +403,72 @@ __global__ void k_build_dv(const float* __restrict__ grid, const float* __restri
 struct FinishArgs {
     unsigned long long* acc;
     float* density;
-    int* counts;     // in: removed per chunk; out: exclusive offsets
-    int* top;        // device stack top
-    int* scatter_hdr;  // [0] = old top, [1] = total removed, [2] = n_chunks
+    int* counts;       // in: removed per chunk; out: exclusive offsets
+    int* top;          // device stack top
+    int* scatter_hdr;  // [0] = old top, [1] = total removed, [2] = n_chunks, [3] = running total (input)
     int* status;
     const int* largest_index_dev;
     int largest_index;
     int largest_allowed_slot;
     int n_points;
-    double inv_scale;  // 2^-24 / background_density
+    double inv_scale;   // 2^-24 / background_density
     int* flags_global;  // reset for the next large-grid launch
 };
 
-// One CTA: fixed-point accumulators -> float density (and re-zero them), exclusive scan of
-// the per-chunk removal counts, stack-top update.
+// One CTA: fixed-point accumulators -> float density (and re-zero them); exclusive scan of the
+// per-chunk removal counts (skipped when the mover removed nothing); stack-top update.
 __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int j = tid; j < a.n_points; j += blockDim.x) {
         const unsigned long long v = a.acc[j];
         a.density[j] = (float)((double)v * a.inv_scale);
         a.acc[j] = 0ull;
     }
-    if (tid == 0) {
-        s_carry = 0;
-        if (a.flags_global) a.flags_global[0] = 0;
-    }
-    __syncthreads();
+    const int total = a.scatter_hdr[3];
     const int n_slots = (a.largest_index_dev ? *a.largest_index_dev : a.largest_index) + 1;
     const int n_quads = (n_slots + 3) >> 2;
     const int n_chunks = (n_quads + kQuadsPerChunk - 1) / kQuadsPerChunk;
-    for (int base = 0; base < n_chunks; base += blockDim.x) {
-        const int i = base + tid;
-        const int c = (i < n_chunks) ? a.counts[i] : 0;
-        int incl = c;
+    if (total != 0) {  // uniform
+        // each thread owns a contiguous run of counts: sum, block-scan the sums, write offsets
+        const int per = (n_chunks + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int i0 = min(tid * per, n_chunks), i1 = min(i0 + per, n_chunks);
+        int sum = 0;
+        for (int i = i0; i < i1; ++i) sum += a.counts[i];
+        int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((tid & 31) >= d) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
-        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+        if (lane == 31) s_warp[w] = incl;
         __syncthreads();
-        if (tid < 32) {
-            int w = s_warp[tid];
+        if (w == 0) {
+            int x = s_warp[lane];
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, w, d);
-                if (tid >= d) w += t;
+                const int t = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += t;
             }
-            s_warp[tid] = w;  // inclusive over warps
+            s_warp[lane] = x;
         }
         __syncthreads();
-        const int warp_off = (tid >> 5) ? s_warp[(tid >> 5) - 1] : 0;
-        const int carry = s_carry;
-        if (i < n_chunks) a.counts[i] = carry + warp_off + incl - c;
-        __syncthreads();
-        if (tid == blockDim.x - 1) s_carry = carry + warp_off + incl;
-        __syncthreads();
+        int run = (w ? s_warp[w - 1] : 0) + incl - sum;
+        for (int i = i0; i < i1; ++i) {
+            const int c = a.counts[i];
+            a.counts[i] = run;
+            run += c;
+        }
     }
     if (tid == 0) {
-        const int total = s_carry;
         const int old_top = *a.top;
         a.scatter_hdr[0] = old_top;
         a.scatter_hdr[1] = total;
         a.scatter_hdr[2] = n_chunks;
+        a.scatter_hdr[3] = 0;
         *a.top = old_top + total;
         if (old_top + total > a.largest_allowed_slot) atomicOr(a.status, ESPIC_ST_STACK_OVERFLOW);
+        if (a.flags_global) a.flags_global[0] = 0;
     }
 }
 
@@ -556,6 +559,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.pv = particles + storage;
     a.staging = (int*)ctx->staging.ptr;
     a.counts = (int*)ctx->chunk_counts.ptr + 4;  // first 4 ints: scatter header
+    a.total_removed = (int*)ctx->chunk_counts.ptr + 3;
     a.acc = ctx->acc;
     a.status = ctx->status;
     a.largest_index_dev = largest_index_dev;

@@ -1,6 +1,6 @@
 // K5: grid Poisson solve as one CTA.  Replaces poisson_solve_c + tridiagonal_solve_c
-// (ref infMagSim_c.c:343-354, 356-541) and the density end-node fix / charge density of the
-// driver loop (ref infMagSim_script.py:763-779, 807).
+// (ref infMagSim_c.c:343-354, 356-541) and, fused in front of it, the density end-node fix /
+// charge density of the driver loop (ref infMagSim_script.py:763-779, 807).
 //
 // The rows are built per grid node exactly as the reference builds them (float/double mix
 // included).  The Thomas algorithm's three sequential recurrences are evaluated as block-wide
@@ -8,10 +8,13 @@
 //   D[j] = diag[j] - (sup[j-1]*sub[j-1])/D[j-1]        Moebius map  -> scan of 2x2 matrices
 //   y[j] = rhs[j]  - (y[j-1]*sub[j-1])/D[j-1]          affine map   -> scan of (A,B) pairs
 //   z[j] = y[j]    - (z[j+1]*sup[j])/D[j+1]            affine map, reversed
-// Each of the 1024 threads owns a contiguous run of rows: it composes its run, the block scans
-// the 1024 composites, and the thread then re-walks its run with the reference's own
-// expression starting from the exact incoming value, so rounding differs from the sequential
-// sweep only through that incoming value (~1e-16 relative; the potential is float).
+// Each of the 1024 threads owns a contiguous run of m = ceil(n/1024) rows: it composes its run,
+// the block scans the 1024 composites, and the thread then re-walks its run with the
+// reference's own expression starting from the exact incoming value, so rounding differs from
+// the sequential sweep only through that incoming value (~1e-16 relative; the potential is
+// float).  Row j = t*m + i of thread t is stored at [i*1024 + t]: conflict-free in shared
+// memory (grids up to 5120 points keep all five fp64 arrays in the CTA's 227 KB), coalesced in
+// the global workspace used for larger grids.
 //
 // Periodic variant: bug-compatible with the reference: the second solve
 // re-eliminates the already eliminated diagonal and v.w is taken as 0 (the reference reads
@@ -32,21 +35,30 @@ struct Aff {
 __device__ __forceinline__ Mat2 mat_identity() { return Mat2{1., 0., 0., 1.}; }
 __device__ __forceinline__ Aff aff_identity() { return Aff{1., 0.}; }
 
-// later * earlier, rescaled (the map is projective) so long products neither overflow nor vanish
+// 2^-e for the binary exponent e of |m| (m finite, non-zero), built from the exponent bits
+__device__ __forceinline__ double inv_pow2_of(double m) {
+    const int hi = __double2hiint(m);
+    const int biased = (hi >> 20) & 0x7ff;
+    int inv = 2046 - biased;          // exponent field of 2^-(biased-1023)
+    inv = min(max(inv, 1), 2046);
+    return __hiloint2double(inv << 20, 0);
+}
+
+// later * earlier, rescaled by a power of two (the map is projective) so long products neither
+// overflow nor vanish
 __device__ __forceinline__ Mat2 compose(const Mat2& l, const Mat2& e) {
     Mat2 r;
     r.a = l.a * e.a + l.b * e.c;
     r.b = l.a * e.b + l.b * e.d;
     r.c = l.c * e.a + l.d * e.c;
     r.d = l.c * e.b + l.d * e.d;
-    double m = fmax(fmax(fabs(r.a), fabs(r.b)), fmax(fabs(r.c), fabs(r.d)));
-    if (m > 0. && isfinite(m)) {
-        int ex;
-        frexp(m, &ex);
-        r.a = ldexp(r.a, -ex);
-        r.b = ldexp(r.b, -ex);
-        r.c = ldexp(r.c, -ex);
-        r.d = ldexp(r.d, -ex);
+    const double m = fmax(fmax(fabs(r.a), fabs(r.b)), fmax(fabs(r.c), fabs(r.d)));
+    if (m > 0. && m < 1.7e308) {
+        const double s = inv_pow2_of(m);
+        r.a *= s;
+        r.b *= s;
+        r.c *= s;
+        r.d *= s;
     }
     return r;
 }
@@ -65,7 +77,7 @@ __device__ __forceinline__ Aff shfl_up(const Aff& v, int d) {
 // Exclusive scan over the block in thread order; element t of the result is the composition
 // of the elements of threads 0..t-1 (earlier applied first).
 template <class T>
-__device__ T block_exclusive_scan(T mine, T identity, T* s_warp) {
+__device__ __forceinline__ T block_exclusive_scan(T mine, T identity, T* s_warp) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     T incl = mine;
 #pragma unroll
@@ -93,7 +105,7 @@ __device__ T block_exclusive_scan(T mine, T identity, T* s_warp) {
     return res;
 }
 
-__device__ double block_sum(double v, double* s_red) {
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -106,7 +118,7 @@ __device__ double block_sum(double v, double* s_red) {
         if (lane == 0) s_red[0] = x;
     }
     __syncthreads();
-    double r = s_red[0];
+    const double r = s_red[0];
     __syncthreads();
     return r;
 }
@@ -114,83 +126,184 @@ __device__ double block_sum(double v, double* s_red) {
 struct SolveArgs {
     const float* grid;
     const float* mask;
-    const float* charge;
+    const float* charge;   // input charge density (when ion == nullptr)
+    float* ion;            // fused prepare: ion / electron densities (fixed in place) -> charge_out
+    float* ele;
+    float* charge_out;
     float* potential;
-    double* ws;  // 6*n doubles: low, diag, sup, rhs, D, D2
+    double* ws;  // 5 * m * 1024 doubles when the arrays do not fit in shared memory
     int* status;
     float debye, obj_pot, transparency;
     int boltzmann, periodic, n;
+    int fix_i, fix_e;
+    int use_smem;
 };
 
-// D_out[0] = d0; D_out[j] = dg[j] - (sup[j-1]*low[j])/D_out[j-1]
-__device__ void eliminate_diagonal(const double* dg, const double* low, const double* sup, double* D_out,
-                                   int n, Mat2* s_mat) {
-    const int T = blockDim.x, t = threadIdx.x;
-    const int m = (n - 1 + T - 1) / T;
-    const int j0 = 1 + t * m, j1 = min(j0 + m, n);
+// Transposed run storage: element i of thread t's run.
+#define AT(arr, i) (arr)[(size_t)(i) * kSolveThreads + threadIdx.x]
+
+// D[0] = dg[0]; D[j] = dg[j] - (sup[j-1]*low[j])/D[j-1].  `sup_prev(i)` must give sup[j-1].
+// Runs are m rows per thread: thread t owns rows t*m .. t*m+m-1 (clipped to n).
+__device__ __forceinline__ void eliminate_diagonal(const double* dg, const double* low, const double* sup,
+                                                   double* D, int n, int m, Mat2* s_mat, double* s_edge,
+                                                   double* s_scalar) {
+    const int t = threadIdx.x;
+    const int j0 = t * m;
+    // sup[j0-1] lives in the previous thread's run: publish each run's last sup
+    s_edge[t] = (j0 + m - 1 < n) ? AT(sup, m - 1) : 0.;
+    __syncthreads();
+    const double sup_before = (t > 0) ? s_edge[t - 1] : 0.;
     Mat2 comp = mat_identity();
-    for (int j = j0; j < j1; ++j) comp = compose(Mat2{dg[j], -(sup[j - 1] * low[j]), 1., 0.}, comp);
-    Mat2 pre = block_exclusive_scan(comp, mat_identity(), s_mat);
-    const double d0 = dg[0];
+    for (int i = 0; i < m; ++i) {
+        const int j = j0 + i;
+        if (j >= n || j == 0) continue;
+        const double sp = (i == 0) ? sup_before : AT(sup, i - 1);
+        comp = compose(Mat2{AT(dg, i), -(sp * AT(low, i)), 1., 0.}, comp);
+    }
+    const Mat2 pre = block_exclusive_scan(comp, mat_identity(), s_mat);
+    // value entering this run: D[j0-1] = pre applied to D[0] = dg[0] (thread 0's first element)
+    if (t == 0) s_scalar[0] = AT(dg, 0);
+    __syncthreads();
+    const double d0 = s_scalar[0];
     double d = (pre.a * d0 + pre.b) / (pre.c * d0 + pre.d);
-    __syncthreads();  // every thread has read dg[0] before thread 0 may overwrite it (in-place use)
-    if (t == 0) D_out[0] = d0;
-    for (int j = j0; j < j1; ++j) {
-        d = dg[j] - sup[j - 1] * low[j] / d;
-        D_out[j] = d;
+    for (int i = 0; i < m; ++i) {
+        const int j = j0 + i;
+        if (j >= n) break;
+        if (j == 0) {
+            d = d0;
+        } else {
+            const double sp = (i == 0) ? sup_before : AT(sup, i - 1);
+            d = AT(dg, i) - sp * AT(low, i) / d;
+        }
+        AT(D, i) = d;
     }
     __syncthreads();
 }
 
 // in place: y[j] -= (y[j-1]*low[j])/D[j-1], j = 1..n-1
-__device__ void forward_sweep(double* y, const double* low, const double* D, int n, Aff* s_aff) {
-    const int T = blockDim.x, t = threadIdx.x;
-    const int m = (n - 1 + T - 1) / T;
-    const int j0 = 1 + t * m, j1 = min(j0 + m, n);
-    Aff comp = aff_identity();
-    for (int j = j0; j < j1; ++j) comp = compose(Aff{-(low[j] / D[j - 1]), y[j]}, comp);
-    Aff pre = block_exclusive_scan(comp, aff_identity(), s_aff);
-    double prev = pre.A * y[0] + pre.B;
+__device__ __forceinline__ void forward_sweep(double* y, const double* low, const double* D, int n, int m,
+                                              Aff* s_aff, double* s_edge, double* s_scalar) {
+    const int t = threadIdx.x;
+    const int j0 = t * m;
+    s_edge[t] = (j0 + m - 1 < n) ? AT(D, m - 1) : 1.;
     __syncthreads();
-    for (int j = j0; j < j1; ++j) {
-        prev = y[j] - prev * low[j] / D[j - 1];
-        y[j] = prev;
+    const double D_before = (t > 0) ? s_edge[t - 1] : 1.;
+    Aff comp = aff_identity();
+    for (int i = 0; i < m; ++i) {
+        const int j = j0 + i;
+        if (j >= n || j == 0) continue;
+        const double Dp = (i == 0) ? D_before : AT(D, i - 1);
+        comp = compose(Aff{-(AT(low, i) / Dp), AT(y, i)}, comp);
+    }
+    const Aff pre = block_exclusive_scan(comp, aff_identity(), s_aff);
+    if (t == 0) s_scalar[0] = AT(y, 0);
+    __syncthreads();
+    double prev = pre.A * s_scalar[0] + pre.B;
+    for (int i = 0; i < m; ++i) {
+        const int j = j0 + i;
+        if (j >= n) break;
+        if (j == 0) {
+            prev = AT(y, 0);
+        } else {
+            const double Dp = (i == 0) ? D_before : AT(D, i - 1);
+            prev = AT(y, i) - prev * AT(low, i) / Dp;
+            AT(y, i) = prev;
+        }
     }
     __syncthreads();
 }
 
-// in place: z[j] -= (z[j+1]*sup[j])/D[j+1], j = n-2..0
-__device__ void backward_sweep(double* z, const double* sup, const double* D, int n, Aff* s_aff) {
-    const int T = blockDim.x, t = threadIdx.x;
-    const int m = (n - 1 + T - 1) / T;
-    const int i0 = 1 + t * m, i1 = min(i0 + m, n);  // step i handles row j = n-1-i
-    Aff comp = aff_identity();
-    for (int i = i0; i < i1; ++i) {
-        const int j = n - 1 - i;
-        comp = compose(Aff{-(sup[j] / D[j + 1]), z[j]}, comp);
-    }
-    Aff pre = block_exclusive_scan(comp, aff_identity(), s_aff);
-    double next = pre.A * z[n - 1] + pre.B;
+// in place: z[j] -= (z[j+1]*sup[j])/D[j+1], j = n-2..0.  The scan runs in REVERSE thread
+// order: thread t is scan position 1023-t.
+__device__ __forceinline__ void backward_sweep(double* z, const double* sup, const double* D, int n, int m,
+                                               Aff* s_aff, double* s_edge, double* s_scalar) {
+    const int t = threadIdx.x;
+    const int j0 = t * m;
+    s_edge[t] = (j0 < n) ? AT(D, 0) : 1.;  // D at the first row of each run = D[j+1] for the previous run's last row
     __syncthreads();
-    for (int i = i0; i < i1; ++i) {
-        const int j = n - 1 - i;
-        next = z[j] - next * sup[j] / D[j + 1];
-        z[j] = next;
+    const double D_after = (t + 1 < kSolveThreads) ? s_edge[t + 1] : 1.;
+    Aff comp = aff_identity();
+    for (int i = m - 1; i >= 0; --i) {
+        const int j = j0 + i;
+        if (j >= n - 1) continue;  // row n-1 is the start value; rows past n do not exist
+        const double Dn = (i == m - 1) ? D_after : AT(D, i + 1);
+        comp = compose(Aff{-(AT(sup, i) / Dn), AT(z, i)}, comp);
+    }
+    // reverse-order exclusive scan: hand the composite to the mirrored thread, scan, hand back
+    // (s_edge has been consumed into registers above; its storage is reused)
+    Aff* s_rev = reinterpret_cast<Aff*>(s_edge);
+    __syncthreads();
+    s_rev[kSolveThreads - 1 - t] = comp;
+    __syncthreads();
+    const Aff mine_rev = s_rev[t];
+    __syncthreads();
+    const Aff pre_rev = block_exclusive_scan(mine_rev, aff_identity(), s_aff);
+    s_rev[kSolveThreads - 1 - t] = pre_rev;
+    __syncthreads();
+    const Aff pre = s_rev[t];
+    {
+        const int tl = (n - 1) / m, il = (n - 1) - tl * m;  // owner of row n-1
+        if (t == tl) s_scalar[0] = AT(z, il);
+    }
+    __syncthreads();
+    double next = pre.A * s_scalar[0] + pre.B;
+    for (int i = m - 1; i >= 0; --i) {
+        const int j = j0 + i;
+        if (j > n - 1) continue;
+        if (j == n - 1) {
+            next = AT(z, i);
+        } else {
+            const double Dn = (i == m - 1) ? D_after : AT(D, i + 1);
+            next = AT(z, i) - next * AT(sup, i) / Dn;
+            AT(z, i) = next;
+        }
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Mat2 s_mat[32];
     __shared__ Aff s_aff[32];
     __shared__ double s_red[32];
+    __shared__ double s_scalar[2];
+    __shared__ __align__(16) double s_edge[2 * kSolveThreads];  // run-boundary values; reused as Aff[1024]
     const int n = a.n, tid = threadIdx.x;
-    double* low = a.ws;  // low[j] = sub-diagonal element of ROW j (the reference's lower_diagonal[j-1])
-    double* dg = low + n;
-    double* sup = dg + n;
-    double* rhs = sup + n;
-    double* D = rhs + n;
-    double* D2 = D + n;
+    const int m = (n + kSolveThreads - 1) / kSolveThreads;
+    const size_t plane = (size_t)m * kSolveThreads;
+    double* base = a.use_smem ? reinterpret_cast<double*>(smem_raw) : a.ws;
+    double* low = base;  // low[j] = sub-diagonal element of ROW j (the reference's lower_diagonal[j-1])
+    double* dg = low + plane;
+    double* sup = dg + plane;
+    double* rhs = sup + plane;
+    double* D = rhs + plane;
+    double* D2 = dg;  // periodic only: the plain diagonal is dead once D exists
+
+    // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
+    const float* charge = a.charge;
+    if (a.ion) {
+        __shared__ float s_end[4];
+        if (tid == 0) {
+            float i0 = a.ion[0], i1 = a.ion[n - 1], e0 = a.ele[0], e1 = a.ele[n - 1];
+            if (a.periodic) {
+                if (a.fix_i) { i0 = __fadd_rn(i0, i1); i1 = i0; }
+                if (a.fix_e) { e0 = __fadd_rn(e0, e1); e1 = e0; }
+            } else {
+                if (a.fix_i) { i0 = __fmul_rn(i0, 2.f); i1 = __fmul_rn(i1, 2.f); }
+                if (a.fix_e) { e0 = __fmul_rn(e0, 2.f); e1 = __fmul_rn(e1, 2.f); }
+            }
+            s_end[0] = i0; s_end[1] = i1; s_end[2] = e0; s_end[3] = e1;
+            a.ion[0] = i0; a.ion[n - 1] = i1; a.ele[0] = e0; a.ele[n - 1] = e1;
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += blockDim.x) {
+            const float x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : a.ion[j];
+            const float y = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
+            a.charge_out[j] = __fsub_rn(x, y);
+        }
+        __syncthreads();
+        charge = a.charge_out;
+    }
 
     // ---- rows (ref :385-503) ------------------------------------------------------------
     const float dz = (__ldg(a.grid + n - 1) - __ldg(a.grid)) / (float)(n - 1);
@@ -204,9 +317,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     const double near_one = 1. - (double)1.e-5f;
     const double tr = (double)a.transparency, op = 1. - (double)a.transparency;
     int bad_mask = 0;
-    for (int j = tid; j < n; j += blockDim.x) {
+    for (int i = 0; i < m; ++i) {
+        const int j = tid * m + i;
+        if (j >= n) break;
         double p_low = 1., p_dg = -2., p_sup = 1.;
-        double p_rhs = (j == n - 1) ? 0. : (double)a.charge[j];
+        double p_rhs = (j == n - 1) ? 0. : (double)charge[j];
         if (a.boltzmann) {
             const double ephi = exp((double)a.potential[j]);
             p_dg -= (double)(dz * dz) * ephi / (double)lam / (double)lam;
@@ -230,11 +345,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         }
         double o_low = p_low, o_dg = p_dg, o_sup = p_sup, o_rhs = p_rhs;
         if (j >= 1 && j <= n - 2) {
-            const float m = a.mask[j], mp = a.mask[j - 1];
-            if (m > 0.f) {
-                if ((double)m < near_one) {
+            const float mk = a.mask[j], mp = a.mask[j - 1];
+            if (mk > 0.f) {
+                if ((double)mk < near_one) {
                     if (a.mask[j + 1] > 0.f) {
-                        const float zl = (float)((1. - (double)m) * (double)dz);
+                        const float zl = (float)((1. - (double)mk) * (double)dz);
                         o_low = (double)(zl / dz);
                         o_dg = -1. - (double)(zl / dz);
                         o_sup = 0.;
@@ -242,13 +357,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
                         o_rhs -= (double)a.obj_pot;
                     } else if ((double)mp < near_one) {
                         const float zl = (float)((1. - (double)mp) * (double)dz);
-                        const float zr = (float)((1. - (double)m) * (double)dz);
+                        const float zr = (float)((1. - (double)mk) * (double)dz);
                         o_low = -(1. - (double)(zl / dz));
                         o_dg = (double)(-(zl + zr) / dz);
                         o_sup = -(1. - (double)(zr / dz));
                         o_rhs = -2. * (double)a.obj_pot;
                     } else if ((double)mp > near_one) {
-                        const float zr = (float)((1. - (double)m) * (double)dz);
+                        const float zr = (float)((1. - (double)mk) * (double)dz);
                         o_low = 0.;
                         o_dg = -2. * (double)zr / (double)dz;
                         o_sup = -2. * (1. - (double)(zr / dz));
@@ -256,7 +371,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
                     } else {
                         bad_mask = 1;
                     }
-                } else if ((double)m > near_one) {
+                } else if ((double)mk > near_one) {
                     if ((double)mp < near_one) {
                         const float zl = (float)((1. - (double)mp) * (double)dz);
                         o_low = -2. * (1. - (double)(zl / dz));
@@ -280,42 +395,51 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
                 o_rhs -= (double)a.obj_pot;
             }
         }
-        low[j] = p_low * tr + o_low * op;
-        dg[j] = p_dg * tr + o_dg * op;
-        sup[j] = p_sup * tr + o_sup * op;
-        rhs[j] = p_rhs * tr + o_rhs * op;
+        AT(low, i) = p_low * tr + o_low * op;
+        AT(dg, i) = p_dg * tr + o_dg * op;
+        AT(sup, i) = p_sup * tr + o_sup * op;
+        AT(rhs, i) = p_rhs * tr + o_rhs * op;
     }
     if (bad_mask) atomicOr(a.status, ESPIC_ST_BAD_OBJECT_MASK);
     __syncthreads();
 
     // ---- Thomas (ref :343-354) -------------------------------------------------------------
-    eliminate_diagonal(dg, low, sup, D, n, s_mat);
-    forward_sweep(rhs, low, D, n, s_aff);
-    backward_sweep(rhs, sup, D, n, s_aff);
-    for (int j = tid; j < n; j += blockDim.x) rhs[j] = rhs[j] / D[j];
+    eliminate_diagonal(dg, low, sup, D, n, m, s_mat, s_edge, s_scalar);
+    forward_sweep(rhs, low, D, n, m, s_aff, s_edge, s_scalar);
+    backward_sweep(rhs, sup, D, n, m, s_aff, s_edge, s_scalar);
+    for (int i = 0; i < m; ++i)
+        if (tid * m + i < n) AT(rhs, i) = AT(rhs, i) / AT(D, i);
     __syncthreads();
 
     double mean = 0.;
     if (a.periodic) {  // ref :504-514, :518-523
-        eliminate_diagonal(D, low, sup, D2, n, s_mat);  // quirk (1): second elimination of the same diagonal
+        eliminate_diagonal(D, low, sup, D2, n, m, s_mat, s_edge, s_scalar);  // quirk (1): second elimination of the same diagonal
         // w = second "solve" of u = e_{n-1}: the forward sweep leaves u unchanged, so only the
         // backward sweep and the final division act.  low[] is free now: reuse it for w.
         double* w = low;
-        for (int j = tid; j < n; j += blockDim.x) w[j] = (j == n - 1) ? 1. : 0.;
+        for (int i = 0; i < m; ++i) {
+            const int j = tid * m + i;
+            if (j < n) AT(w, i) = (j == n - 1) ? 1. : 0.;
+        }
         __syncthreads();
-        backward_sweep(w, sup, D2, n, s_aff);
-        const double v_dot_result = -rhs[0];
+        backward_sweep(w, sup, D2, n, m, s_aff, s_edge, s_scalar);
+        if (tid == 0) s_scalar[1] = AT(rhs, 0);
+        __syncthreads();
+        const double v_dot_result = -s_scalar[1];
         const double v_dot_w = 0.;  // quirk (2)
-        __syncthreads();
         double part = 0.;
-        for (int j = tid; j < n; j += blockDim.x) {
-            const double r = rhs[j] - v_dot_result / (1. + v_dot_w) * (w[j] / D2[j]);
-            rhs[j] = r;
+        for (int i = 0; i < m; ++i) {
+            if (tid * m + i >= n) break;
+            const double r = AT(rhs, i) - v_dot_result / (1. + v_dot_w) * (AT(w, i) / AT(D2, i));
+            AT(rhs, i) = r;
             part += r;
         }
         mean = block_sum(part, s_red) / (double)n;
     }
-    for (int j = tid; j < n; j += blockDim.x) a.potential[j] = (float)(rhs[j] - mean);
+    for (int i = 0; i < m; ++i) {
+        const int j = tid * m + i;
+        if (j < n) a.potential[j] = (float)(AT(rhs, i) - mean);
+    }
 }
 
 __global__ void k_prepare_charge(float* __restrict__ ion, float* __restrict__ ele, float* __restrict__ charge,
@@ -342,28 +466,78 @@ __global__ void k_prepare_charge(float* __restrict__ ion, float* __restrict__ el
     }
 }
 
+static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
+    const int n = a.n;
+    if (n < 3) return fail(ctx, ESPIC_E_ARG, "poisson_solve needs n_points >= 3");
+    const int m = (n + kSolveThreads - 1) / kSolveThreads;
+    const size_t bytes = (size_t)5 * m * kSolveThreads * sizeof(double);
+    int max_smem = 0;
+    ESPIC_CUDA(ctx, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const size_t static_smem = 19 * 1024;  // s_edge and the small arrays of the kernel
+    a.use_smem = (bytes + static_smem <= (size_t)max_smem) ? 1 : 0;
+    size_t dyn = 0;
+    if (a.use_smem) {
+        dyn = bytes;
+        static size_t configured = 0;
+        if (dyn > configured) {
+            ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured = dyn;
+        }
+    } else {
+        int rc = ensure(ctx, ctx->solve_ws, bytes, "solve workspace");
+        if (rc) return rc;
+        a.ws = (double*)ctx->solve_ws.ptr;
+    }
+    a.status = ctx->status;
+    k_poisson<<<1, kSolveThreads, dyn, ctx->stream>>>(a);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_poisson launch");
+}
+
 int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const float* charge, float debye,
                    float* potential, float obj_pot, float transparency, int boltzmann, int periodic,
                    int n_points) {
-    if (n_points < 3) return fail(ctx, ESPIC_E_ARG, "poisson_solve needs n_points >= 3");
-    int rc = ensure(ctx, ctx->solve_ws, (size_t)6 * n_points * sizeof(double), "solve workspace");
-    if (rc) return rc;
     SolveArgs a{};
     a.grid = grid;
     a.mask = mask;
     a.charge = charge;
     a.potential = potential;
-    a.ws = (double*)ctx->solve_ws.ptr;
-    a.status = ctx->status;
     a.debye = debye;
     a.obj_pot = obj_pot;
     a.transparency = transparency;
     a.boltzmann = boltzmann;
     a.periodic = periodic;
     a.n = n_points;
-    k_poisson<<<1, kSolveThreads, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    return check_cuda(ctx, cudaGetLastError(), "k_poisson launch");
+    return launch_poisson_impl(ctx, a);
+}
+
+int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, float* ion, float* ele,
+                       float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
+                       float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
+                       int n_points) {
+    SolveArgs a{};
+    a.grid = grid;
+    a.mask = mask;
+    a.ion = ion;
+    a.ele = ele;
+    a.charge_out = charge_out;
+    a.potential = potential;
+    a.debye = debye;
+    a.obj_pot = obj_pot;
+    a.transparency = transparency;
+    a.boltzmann = boltzmann;
+    a.periodic = periodic_potential;
+    a.fix_i = fix_i;
+    a.fix_e = fix_e;
+    a.n = n_points;
+    if (periodic_particles != periodic_potential) {
+        // the reference ties the two flags together (infMagSim_script.py:146); keep the general case correct
+        int rc = launch_prepare_charge(ctx, ion, ele, charge_out, n_points, periodic_particles, fix_i, fix_e);
+        if (rc) return rc;
+        a.ion = nullptr;
+        a.charge = charge_out;
+    }
+    return launch_poisson_impl(ctx, a);
 }
 
 int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge, int n, int periodic,

@@ -223,6 +223,28 @@ def prepare_charge(ion_density, electron_density, charge_density, periodic_parti
     ctx.check(rc, "prepare_charge")
 
 
+def field_solve(grid, object_mask, ion_density, electron_density, charge_density, debye_length, potential,
+                object_potential=-4., object_transparency=1., boltzmann_electrons=False,
+                periodic_particles=False, periodic_potential=None, fix_ions=True, fix_electrons=True, ctx=None):
+    """prepare_charge + poisson_solve in one kernel launch (infMagSim_script.py:763-779, 807, 831-836)."""
+    dev = grid.device if isinstance(grid, torch.Tensor) else None
+    _check(grid, "grid", torch.float32, 1, None)
+    for name, t in (("object_mask", object_mask), ("ion_density", ion_density),
+                    ("electron_density", electron_density), ("charge_density", charge_density),
+                    ("potential", potential)):
+        _check(t, name, torch.float32, 1, dev)
+    if periodic_potential is None:
+        periodic_potential = periodic_particles
+    ctx = ctx or default_context(dev)
+    _enter(ctx, dev)
+    rc = ctx._lib.espic_field_solve(ctx.handle, _ptr(grid), _ptr(object_mask), _ptr(ion_density),
+                                    _ptr(electron_density), _ptr(charge_density), int(bool(periodic_particles)),
+                                    int(bool(fix_ions)), int(bool(fix_electrons)), debye_length, _ptr(potential),
+                                    object_potential, object_transparency, int(bool(boltzmann_electrons)),
+                                    int(bool(periodic_potential)), grid.shape[0])
+    ctx.check(rc, "field_solve")
+
+
 def seedgenrand_c(seed, ctx=None):
     """infMagSim_cython.py:227-228.  Seeds the device sampler (Philox key), see inject.cu."""
     ctx = ctx or default_context()

@@ -27,6 +27,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
+from . import distributed as dd
 from . import operators as ops
 from ._lib import Context
 
@@ -146,13 +147,13 @@ class Simulation:
         self.grid = torch.from_numpy(grid64.astype(np.float32)).to(self.device)
         fine = np.linspace(c.z_min, c.z_max, num=c.n_tracking_mesh_points, endpoint=True)
         self.fine_mesh = torch.from_numpy(fine.astype(np.float32)).to(self.device)
-        self.seed = c.seed + rank ** 3                                    # :277
+        self.seed = dd.rank_seed(c.seed, rank)                             # :277
         ops.seedgenrand_c(self.seed, ctx=self.ctx)                         # :278
         self.host_rng = np.random.RandomState(self.seed % (2 ** 32))       # np.random.seed(seed), :313
         self.v_th_i = 1.0
         self.v_th_e = math.sqrt(c.mass_ratio)                              # :509
         self.dt = c.step_size * c.debye_length / self.v_th_e               # :660
-        self.background_density = c.n_particles * world_size * self.dz / (c.z_max - c.z_min)  # :402,510
+        self.background_density = dd.background_density(c.n_particles, world_size, self.dz, c.z_min, c.z_max)
         self.parked = 2 * c.z_max                                          # :406
         storage = int(math.ceil(c.extra_storage_factor * c.n_particles / 4.0)) * 4
         self.ions = SpeciesStore(c.n_particles, storage, 1.0, self.v_th_i / math.sqrt(c.sigma), self.parked,
@@ -228,9 +229,7 @@ class Simulation:
 
     # ---- one timestep (infMagSim_script.py:756-1023) ---------------------------------------
     def reduce_densities(self) -> None:
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.densities, op=dist.ReduceOp.SUM, group=self.pg)   # :763, :773 in one call
+        dd.all_reduce_densities(self.densities, self.world, self.pg)   # :763, :773 in one call
 
     def injection_counts(self, k: int):
         """Expected wall flux with stochastic rounding (:965-975, 1005-1009)."""
@@ -255,11 +254,11 @@ class Simulation:
         c, k = self.cfg, self.k
         periodic = c.periodic_particles
         self.reduce_densities()
-        ops.prepare_charge(self.ion_density, self.electron_density, self.charge_density, periodic_particles=periodic,
-                           fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True, ctx=self.ctx)
-        ops.poisson_solve(self.grid, self.object_mask, self.charge_density, c.debye_length, self.potential,
-                          object_potential=-3., object_transparency=1., boltzmann_electrons=False,
-                          periodic_potential=periodic, use_pure_c_version=True, ctx=self.ctx)   # :831-836
+        ops.field_solve(self.grid, self.object_mask, self.ion_density, self.electron_density, self.charge_density,
+                        c.debye_length, self.potential, object_potential=-3., object_transparency=1.,
+                        boltzmann_electrons=False, periodic_particles=periodic, periodic_potential=periodic,
+                        fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True,
+                        ctx=self.ctx)                                                          # :763-779, 807, 831-836
         if self.set_background_acceleration and c.hole_pushing_start_step <= k < c.hole_pushing_end_step:
             potential_ions = self.potential + self.background_potential                          # :852-855
         else:
@@ -311,10 +310,7 @@ class Simulation:
         self.hist["electrons_inject0"] = ops.histogram2d_uniform_grid(
             e.particles[0], e.particles[1], c.z_min, c.z_max, -ve, ve, 100, 100, tags=e.tags, tag_value=0,
             ctx=self.ctx)[0]
-        if self.world > 1:
-            import torch.distributed as dist
-            for h in self.hist.values():
-                dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.pg)                          # :876,894,895
+        dd.all_reduce_histograms(self.hist.values(), self.world, self.pg)                        # :876,894,895
 
     def run(self, n_steps: int) -> None:
         for _ in range(n_steps):

@@ -116,6 +116,14 @@ int espic_prepare_charge(espic_ctx *ctx, float *ion_density, float *electron_den
                          float *charge, int n_points, int periodic, int fix_ions,
                          int fix_electrons);
 
+/* espic_prepare_charge + espic_poisson_solve as ONE kernel launch: the field part of a driver
+ * timestep (ref infMagSim_script.py:763-779, 807, 831-836). */
+int espic_field_solve(espic_ctx *ctx, const float *grid, const float *object_mask,
+                      float *ion_density, float *electron_density, float *charge,
+                      int periodic_particles, int fix_ions, int fix_electrons, float debye_length,
+                      float *potential, float object_potential, float object_transparency,
+                      int boltzmann_electrons, int periodic_potential, int n_points);
+
 /* Replaces the body of inject_particles (ref infMagSim_cython.py:230-285) with both random
  * inputs supplied as device arrays: velocities[n_inject] (signed; the sign picks the wall)
  * and uniform01[n_inject] (partial-step fractions).  particles_hist = int[storage] tags.
