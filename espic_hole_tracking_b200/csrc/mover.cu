@@ -36,9 +36,8 @@ namespace espic {
 
 constexpr int kMoveThreads = 256;
 constexpr int kMoveMinBlocks = 4;  // 64 registers per thread: four 8-warp CTAs per SM
-constexpr int kIterPerChunk = 32;                       // warp iterations (of 32 quads) per chunk
-constexpr int kQuadsPerChunk = 32 * kIterPerChunk;      // 1024 quads
-constexpr int kChunkSlots = 4 * kQuadsPerChunk;         // 4096 slots
+constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
+constexpr int kUnitSlots = 4 * kUnitQuads;    // 256 slots
 constexpr int kSmemBytesPerPoint = 12;
 
 struct MoveArgs {
@@ -289,6 +288,21 @@ __device__ __forceinline__ void stage_removed(unsigned rem, int q, int lane, int
     }
 }
 
+// Work split: the complete units [0, n_units) are dealt to the W warps of the grid as contiguous,
+// ascending ranges whose lengths differ by at most one unit (static and balanced to 256
+// slots); the leftover slots behind the last complete unit form one more range owned by the
+// last warp.  Range c stages its removed slot ids at staging + first_slot(c).
+struct Split {
+    int n_units, base, extra;
+    __host__ __device__ Split(int n_slots, int n_warps) {
+        n_units = (n_slots >> 2) / kUnitQuads;
+        base = n_units / n_warps;
+        extra = n_units % n_warps;
+    }
+    __host__ __device__ int first_unit(int w) const { return w * base + (w < extra ? w : extra); }
+    __host__ __device__ int unit_count(int w) const { return base + (w < extra ? 1 : 0); }
+};
+
 // FAST: interior chunks run the register fast path on float4 quads; everything else (the last
 // chunk of the store, unaligned stores, start-up calls with update_position=0, an absorbing
 // object, exotic dz) goes quad by quad through quad_generic.
@@ -331,18 +345,17 @@ __global__ void __launch_bounds__(kMoveThreads, kMoveMinBlocks) k_move(const Mov
     const int total_warps = warps_per_cta * gridDim.x;
     const int n_slots = (a.largest_index_dev ? *a.largest_index_dev : a.largest_index) + 1;
     const int n_quads = (n_slots + 3) >> 2;
-    const int n_full_quads = n_slots >> 2;
-    const int n_chunks = (n_quads + kQuadsPerChunk - 1) / kQuadsPerChunk;
+    const Split split(n_slots, total_warps);
     const bool fast = a.vec_ok && a.update_position != 0 && !has_obj && g.fast_div;  // uniform
 
-    for (int chunk = gw; chunk < n_chunks; chunk += total_warps) {
+    {
         int removed = 0;
-        int* stage = a.staging + (size_t)chunk * kChunkSlots;
-        const int qbase = chunk * kQuadsPerChunk;
-        if (fast && qbase + kQuadsPerChunk <= n_full_quads) {
+        const int u0 = split.first_unit(gw), u1 = u0 + split.unit_count(gw);
+        int* stage = a.staging + (size_t)u0 * kUnitSlots;
+        if (fast) {
 #pragma unroll 1
-            for (int it = 0; it < kIterPerChunk; it += 2) {
-                const int q0 = qbase + it * 32 + lane, q1 = q0 + 32;
+            for (int u = u0; u < u1; ++u) {
+                const int q0 = u * kUnitQuads + lane, q1 = q0 + 32;
                 Quad p0, p1;
                 load_quad(a, q0, p0);  // both quads' loads are issued before either is used
                 load_quad(a, q1, p1);
@@ -355,16 +368,29 @@ __global__ void __launch_bounds__(kMoveThreads, kMoveMinBlocks) k_move(const Mov
             }
         } else {
 #pragma unroll 1
-            for (int it = 0; it < kIterPerChunk; ++it) {
-                if (qbase + it * 32 >= n_quads) break;  // uniform
-                const int q = qbase + it * 32 + lane;
-                unsigned r = 0;
-                if (q < n_quads) r = quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, has_obj, s_lo, s_hi);
+            for (int q = u0 * kUnitQuads + lane; q < u1 * kUnitQuads; q += 32) {
+                const unsigned r = quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, has_obj, s_lo, s_hi);
                 stage_removed(r, q, lane, stage, removed);
             }
         }
         if (lane == 0) {
-            a.counts[chunk] = removed;
+            a.counts[gw] = removed;
+            if (removed) atomicAdd(a.total_removed, removed);
+        }
+    }
+    if (gw == total_warps - 1) {
+        // the slots behind the last complete unit (fewer than 256 + 3): generic, bounds-checked
+        int removed = 0;
+        int* stage = a.staging + (size_t)split.n_units * kUnitSlots;
+#pragma unroll 1
+        for (int qb = split.n_units * kUnitQuads; qb < n_quads; qb += 32) {  // uniform trip count
+            const int q = qb + lane;
+            unsigned r = 0;
+            if (q < n_quads) r = quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, has_obj, s_lo, s_hi);
+            stage_removed(r, q, lane, stage, removed);
+        }
+        if (lane == 0) {
+            a.counts[total_warps] = removed;
             if (removed) atomicAdd(a.total_removed, removed);
         }
     }
@@ -407,8 +433,7 @@ struct FinishArgs {
     int* top;          // device stack top
     int* scatter_hdr;  // [0] = old top, [1] = total removed, [2] = n_chunks, [3] = running total (input)
     int* status;
-    const int* largest_index_dev;
-    int largest_index;
+    int n_ranges;       // mover warps + 1 (see Split)
     int largest_allowed_slot;
     int n_points;
     double inv_scale;   // 2^-24 / background_density
@@ -426,9 +451,7 @@ __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
         a.acc[j] = 0ull;
     }
     const int total = a.scatter_hdr[3];
-    const int n_slots = (a.largest_index_dev ? *a.largest_index_dev : a.largest_index) + 1;
-    const int n_quads = (n_slots + 3) >> 2;
-    const int n_chunks = (n_quads + kQuadsPerChunk - 1) / kQuadsPerChunk;
+    const int n_chunks = a.n_ranges;
     if (total != 0) {  // uniform
         // each thread owns a contiguous run of counts: sum, block-scan the sums, write offsets
         const int per = (n_chunks + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -472,14 +495,17 @@ __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
     }
 }
 
-// Copies each chunk's staged slot ids to their final position on the stack.
+// Copies each range's staged slot ids to their final position on the stack.
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging,
                                                  const int* __restrict__ offsets,
                                                  const int* __restrict__ hdr, int* __restrict__ empty_slots,
-                                                 int largest_allowed_slot) {
+                                                 int largest_allowed_slot, const int* largest_index_dev,
+                                                 int largest_index, int mover_warps) {
     const int total = hdr[1];
     if (total == 0) return;
     const int old_top = hdr[0], n_chunks = hdr[2];
+    const int n_slots = (largest_index_dev ? *largest_index_dev : largest_index) + 1;
+    const Split split(n_slots, mover_warps);
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -487,7 +513,7 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging
         const int off = offsets[c];
         const int end = (c + 1 < n_chunks) ? offsets[c + 1] : total;
         const int cnt = end - off;
-        const int* src = staging + (size_t)c * kChunkSlots;
+        const int* src = staging + (size_t)(c < mover_warps ? split.first_unit(c) : split.n_units) * kUnitSlots;
         for (int r = lane; r < cnt; r += 32) {
             const int dst = old_top + 1 + off + r;
             if (dst >= 0 && dst <= largest_allowed_slot) empty_slots[dst] = src[r];
@@ -545,10 +571,10 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     if (rc) return rc;
     const int max_slots = largest_index_dev ? storage : (largest_index + 1);
     const int max_quads = (max_slots + 3) >> 2;
-    const int max_chunks = (max_quads + kQuadsPerChunk - 1) / kQuadsPerChunk;
-    rc = ensure(ctx, ctx->staging, (size_t)(max_chunks > 0 ? max_chunks : 1) * kChunkSlots * sizeof(int), "staging");
+    rc = ensure(ctx, ctx->staging, ((size_t)max_quads * 4 + 2 * kUnitSlots) * sizeof(int), "staging");
     if (rc) return rc;
-    rc = ensure(ctx, ctx->chunk_counts, ((size_t)max_chunks + 8) * sizeof(int), "chunk counts");
+    const int max_ranges = 64 * 1024;  // >= warps of any mover grid (SMs x CTAs/SM x 8) + 1
+    rc = ensure(ctx, ctx->chunk_counts, ((size_t)max_ranges + 8) * sizeof(int), "range counts");
     if (rc) return rc;
 
     MoveArgs a{};
@@ -600,8 +626,9 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     f.top = top;
     f.scatter_hdr = (int*)ctx->chunk_counts.ptr;
     f.status = ctx->status;
-    f.largest_index_dev = largest_index_dev;
-    f.largest_index = largest_index;
+    const int mover_warps = ctx->mover_grid * (kMoveThreads / 32);
+    if (mover_warps + 1 > max_ranges) return fail(ctx, ESPIC_E_ARG, "mover grid too large for the range table");
+    f.n_ranges = mover_warps + 1;
     f.largest_allowed_slot = largest_allowed_slot;
     f.n_points = n_points;
     f.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
@@ -609,9 +636,9 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     k_finish<<<1, 1024, 0, ctx->stream>>>(f);
     ctx->launches++;
     ESPIC_CUDA(ctx, cudaGetLastError());
-    const int sgrid = max_chunks < 8 * ctx->sm_count ? (max_chunks + 7) / 8 : ctx->sm_count;
-    k_scatter<<<sgrid > 0 ? sgrid : 1, 256, 0, ctx->stream>>>(a.staging, a.counts, f.scatter_hdr, empty_slots,
-                                                            largest_allowed_slot);
+    k_scatter<<<ctx->sm_count, 256, 0, ctx->stream>>>(a.staging, a.counts, f.scatter_hdr, empty_slots,
+                                                      largest_allowed_slot, largest_index_dev, largest_index,
+                                                      mover_warps);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "mover epilogue launch");
 }
