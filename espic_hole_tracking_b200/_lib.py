@@ -17,6 +17,23 @@ CSRC = os.path.join(HERE, "csrc")
 c_void_p, c_int, c_float, c_double = C.c_void_p, C.c_int, C.c_float, C.c_double
 P = c_void_p  # every array argument is passed as a raw device (or host) address
 
+class Species(C.Structure):
+    """espic_species of include/espic_b200.h."""
+    _fields_ = [("particles", c_void_p), ("empty_slots", c_void_p), ("current_empty_slot", c_void_p),
+                ("largest_index", c_void_p), ("density", c_void_p), ("potential", c_void_p),
+                ("particle_storage_length", c_int), ("largest_allowed_slot", c_int),
+                ("charge_to_mass", c_float), ("dt", c_float)]
+
+
+class StepArgs(C.Structure):
+    """espic_step_args of include/espic_b200.h."""
+    _fields_ = [("grid", c_void_p), ("object_mask", c_void_p), ("potential", c_void_p), ("charge", c_void_p),
+                ("ions", Species), ("electrons", Species), ("n_points", c_int),
+                ("background_density", c_float), ("a_b", c_float), ("debye_length", c_float),
+                ("object_potential", c_float), ("object_transparency", c_float), ("periodic", c_int),
+                ("fix_ions", c_int), ("fix_electrons", c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/espic_b200.h one to one
 SIGNATURES = {
     "espic_abi_version": (c_int, []),
@@ -38,6 +55,7 @@ SIGNATURES = {
     "espic_prepare_charge": (c_int, [c_void_p, P, P, P, c_int, c_int, c_int, c_int]),
     "espic_field_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_float, P, c_float, c_float,
                                   c_int, c_int, c_int]),
+    "espic_pic_step": (c_int, [c_void_p, C.POINTER(StepArgs)]),
     "espic_inject_particles": (c_int, [c_void_p, c_int, P, c_int, c_float, c_float, P, P, c_float, c_int,
                                        P, P, c_int, P, P, P, P]),
     "espic_seed": (c_int, [c_void_p, C.c_ulong]),

@@ -280,6 +280,29 @@ int espic_field_solve(espic_ctx* ctx, const float* grid, const float* object_mas
                               object_transparency, boltzmann_electrons, periodic_potential, n_points);
 }
 
+int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
+    if (!ctx || !a) return ESPIC_E_ARG;
+    if (!a->grid || !a->object_mask || !a->potential || !a->charge) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null grid pointer");
+    const espic_species* sp[2] = {&a->ions, &a->electrons};
+    for (int i = 0; i < 2; ++i)
+        if (!sp[i]->particles || !sp[i]->empty_slots || !sp[i]->current_empty_slot || !sp[i]->largest_index ||
+            !sp[i]->density)
+            return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null species pointer");
+    int rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
+                                a->periodic, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
+                                a->object_potential, a->object_transparency, 0, a->periodic, a->n_points);
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        const espic_species* s = sp[i];
+        rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,
+                         s->charge_to_mass, a->background_density, -1, s->largest_index, s->particles, s->density,
+                         s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic, s->largest_allowed_slot,
+                         a->n_points, s->particle_storage_length);
+        if (rc) return rc;
+    }
+    return ESPIC_OK;
+}
+
 int espic_inject_particles(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt,
                            float background_density, const float* velocities, const float* uniform01, float a_b,
                            int k, int* particles_hist, float* particles, int particle_storage_length,

@@ -29,7 +29,7 @@ import torch
 
 from . import distributed as dd
 from . import operators as ops
-from ._lib import Context
+from ._lib import Context, Species, StepArgs
 
 
 @dataclass
@@ -250,38 +250,52 @@ class Simulation:
             n_e += 1
         return n_i, n_e
 
+    def _step_args(self) -> StepArgs:
+        """The espic_step_args block of the fused host call, built once (pointers never change)."""
+        if getattr(self, "_args", None) is None:
+            c = self.cfg
+            a = StepArgs()
+            a.grid, a.object_mask = self.grid.data_ptr(), self.object_mask.data_ptr()
+            a.potential, a.charge = self.potential.data_ptr(), self.charge_density.data_ptr()
+            for dst, s, den in ((a.ions, self.ions, self.ion_density), (a.electrons, self.electrons,
+                                                                       self.electron_density)):
+                dst.particles, dst.empty_slots = s.particles.data_ptr(), s.empty_slots.data_ptr()
+                dst.current_empty_slot = s.current_empty_slot.tensor.data_ptr()
+                dst.largest_index = s.largest_index.tensor.data_ptr()
+                dst.density, dst.potential = den.data_ptr(), None
+                dst.particle_storage_length = s.storage
+                dst.largest_allowed_slot = s.empty_slots.shape[0] - 1
+                dst.charge_to_mass = s.charge_to_mass
+            a.n_points = self.n_points
+            a.background_density = self.background_density
+            a.debye_length, a.object_potential, a.object_transparency = c.debye_length, -3., 1.
+            a.periodic = int(c.periodic_particles)
+            self._args = a
+        return self._args
+
     def step(self) -> None:
         c, k = self.cfg, self.k
         periodic = c.periodic_particles
         self.reduce_densities()
-        ops.field_solve(self.grid, self.object_mask, self.ion_density, self.electron_density, self.charge_density,
-                        c.debye_length, self.potential, object_potential=-3., object_transparency=1.,
-                        boltzmann_electrons=False, periodic_particles=periodic, periodic_potential=periodic,
-                        fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True,
-                        ctx=self.ctx)                                                          # :763-779, 807, 831-836
-        if self.set_background_acceleration and c.hole_pushing_start_step <= k < c.hole_pushing_end_step:
-            potential_ions = self.potential + self.background_potential                          # :852-855
+        ions_mobile = k <= c.time_steps_immobile_ions                                            # :929-939
+        ramp = self.set_background_acceleration and c.hole_pushing_start_step <= k < c.hole_pushing_end_step
+        if not ramp and not c.phase_space_histograms:
+            # field solve + both pushes as one host call (espic_pic_step); same kernels, same order
+            a = self._step_args()
+            a.a_b = self.a_b
+            a.fix_ions = int(periodic or k <= c.time_steps_immobile_ions)
+            a.fix_electrons = 1
+            a.ions.dt = self.dt if ions_mobile else 0.
+            a.electrons.dt = 0. if k < c.time_steps_immobile_electrons else self.dt
+            self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            self.ctx.check(self.ctx._lib.espic_pic_step(self.ctx.handle, a), "espic_pic_step")
         else:
-            potential_ions = self.potential
-        if c.phase_space_histograms:
-            self.phase_space()
+            self._step_operator_by_operator(k, ions_mobile, ramp)
+        if not ions_mobile:
+            self.ion_density.fill_(1.0)                                                          # :934
         if c.track_hole and k > c.initial_transient_steps and k < self.hole_relative_positions.shape[0]:  # :896-897
             ops.hole_position_tracking(self.potential, self.dz, c.debye_length * 4., self.grid, self.fine_mesh,
                                        out=self.hole_relative_positions[k:k + 1], ctx=self.ctx)
-        s = self.ions
-        ions_mobile = k <= c.time_steps_immobile_ions                                            # :929-939
-        ops.move_particles(self.grid, self.object_mask, potential_ions, self.dt if ions_mobile else 0.,
-                           s.charge_to_mass, self.background_density, s.largest_index, s.particles,
-                           self.ion_density, s.empty_slots, s.current_empty_slot, self.a_b,
-                           periodic_particles=periodic, use_pure_c_version=True, ctx=self.ctx)
-        if not ions_mobile:
-            self.ion_density.fill_(1.0)                                                          # :934
-        s = self.electrons
-        ops.move_particles(self.grid, self.object_mask, self.potential,
-                           0. if k < c.time_steps_immobile_electrons else self.dt, s.charge_to_mass,
-                           self.background_density, s.largest_index, s.particles, self.electron_density,
-                           s.empty_slots, s.current_empty_slot, self.a_b, periodic_particles=periodic,
-                           use_pure_c_version=True, ctx=self.ctx)                                # :940-950
         if not periodic:
             n_i, n_e = self.injection_counts(k)
             if n_i > 0 and ions_mobile:                                                          # :986-1000
@@ -297,6 +311,31 @@ class Simulation:
                                      s.current_empty_slot, s.largest_index, self.electron_density, ctx=self.ctx)
         self.t += self.dt
         self.k += 1
+
+    def _step_operator_by_operator(self, k: int, ions_mobile: bool, ramp: bool) -> None:
+        """The same step through the individual operators, in the reference's order (used when the
+        ion potential carries the background ramp or the per-step histograms are on)."""
+        c = self.cfg
+        periodic = c.periodic_particles
+        ops.field_solve(self.grid, self.object_mask, self.ion_density, self.electron_density, self.charge_density,
+                        c.debye_length, self.potential, object_potential=-3., object_transparency=1.,
+                        boltzmann_electrons=False, periodic_particles=periodic, periodic_potential=periodic,
+                        fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True,
+                        ctx=self.ctx)                                                          # :763-779, 807, 831-836
+        potential_ions = self.potential + self.background_potential if ramp else self.potential  # :852-864
+        if c.phase_space_histograms:
+            self.phase_space()
+        s = self.ions
+        ops.move_particles(self.grid, self.object_mask, potential_ions, self.dt if ions_mobile else 0.,
+                           s.charge_to_mass, self.background_density, s.largest_index, s.particles,
+                           self.ion_density, s.empty_slots, s.current_empty_slot, self.a_b,
+                           periodic_particles=periodic, use_pure_c_version=True, ctx=self.ctx)
+        s = self.electrons
+        ops.move_particles(self.grid, self.object_mask, self.potential,
+                           0. if k < c.time_steps_immobile_electrons else self.dt, s.charge_to_mass,
+                           self.background_density, s.largest_index, s.particles, self.electron_density,
+                           s.empty_slots, s.current_empty_slot, self.a_b, periodic_particles=periodic,
+                           use_pure_c_version=True, ctx=self.ctx)                                # :940-950
 
     def phase_space(self) -> None:
         """The three per-step 100x100 histograms (:865-895); results stay on the device."""

@@ -124,6 +124,44 @@ int espic_field_solve(espic_ctx *ctx, const float *grid, const float *object_mas
                       float *potential, float object_potential, float object_transparency,
                       int boltzmann_electrons, int periodic_potential, int n_points);
 
+/* One whole driver timestep minus injection as ONE host call (ref infMagSim_script.py:763-779,
+ * 807, 831-836, 929-950): espic_field_solve on the two densities, then espic_move_particles_dev
+ * for the ions and for the electrons.  Everything is enqueued on the context's stream; nothing
+ * synchronises.  A species with dt == 0 is frozen the way the driver freezes it (mover called
+ * with dt 0).  species.potential == NULL means "the solved potential". */
+typedef struct {
+    float *particles;            /* float[2][particle_storage_length] */
+    int *empty_slots;            /* int[largest_allowed_slot + 1] */
+    int *current_empty_slot;     /* device int */
+    int *largest_index;          /* device int */
+    float *density;              /* float[n_points], overwritten by the push */
+    const float *potential;      /* potential felt by this species, or NULL */
+    int particle_storage_length;
+    int largest_allowed_slot;
+    float charge_to_mass;
+    float dt;
+} espic_species;
+
+typedef struct {
+    const float *grid;
+    const float *object_mask;
+    float *potential;
+    float *charge;
+    espic_species ions;
+    espic_species electrons;
+    int n_points;
+    float background_density;
+    float a_b;
+    float debye_length;
+    float object_potential;
+    float object_transparency;
+    int periodic;                /* periodic_particles == periodic_potential */
+    int fix_ions;
+    int fix_electrons;
+} espic_step_args;
+
+int espic_pic_step(espic_ctx *ctx, const espic_step_args *args);
+
 /* Replaces the body of inject_particles (ref infMagSim_cython.py:230-285) with both random
  * inputs supplied as device arrays: velocities[n_inject] (signed; the sign picks the wall)
  * and uniform01[n_inject] (partial-step fractions).  particles_hist = int[storage] tags.
