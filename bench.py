@@ -117,7 +117,8 @@ def run_reference(args):
         cpu.build()
     cores = os.cpu_count() or 1
     n_sample = 2_000_000  # per species per process: each step is a bounded sample of the workload
-    res = loop.timed_cpu_sample(kind, n_sample, N_CELLS, True, steps=args.steps, warmup=args.warmup)
+    res = loop.timed_cpu_sample(kind, n_sample, N_CELLS, True, steps=args.steps, warmup=args.warmup,
+                                periodic_potential=False)
     value = res["value"]
     sample = (f"{cores} processes x ({n_sample:.0e} ions + {n_sample:.0e} electrons), {N_CELLS}-cell periodic grid, "
               f"{args.steps} timed steps after {args.warmup} warm-up; same loop as the GPU arm")
@@ -168,7 +169,7 @@ def main():
 
     n = int(args.particles)
     cfg = SimConfig(n_steps=args.steps + args.warmup + 8, n_particles=n, n_cells=args.cells, periodic_particles=True,
-                    extra_storage_factor=1.0, track_hole=False)
+                    periodic_potential=False, extra_storage_factor=1.0, track_hole=False)
     sim = Simulation(cfg, rank=rank, world_size=world, device=device)
     sim.init_synthetic()
     sim.initialize()
@@ -281,6 +282,8 @@ def main():
         "config": {"workload": f"{n:.3g} ions + {n:.3g} electrons per GPU, {args.cells}-cell periodic grid "
                                "(BASELINE configs[1]; N>1 = configs[2]-style weak scaling with the density all-reduce)",
                    "particles_per_species_per_gpu": n, "cells": args.cells, "periodic": True,
+                   "field_solve": "periodic particles, Robin-end potential (periodic_potential=False): the reference's "
+                                  "periodic_potential branch is numerically broken on 4097 points (DESIGN.md s.8)",
                    "l2_policy": "inputs (1.6 GB of particle state per GPU) are larger than the 126 MB L2; no flush needed",
                    "parallelism": f"particle shards x{world}, one fp32 all-reduce of [2,{args.cells + 1}] per step"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
@@ -303,7 +306,7 @@ def main():
             cpu.build()
         cores = os.cpu_count() or 1
         n_sample = 2_000_000
-        res = loop.timed_cpu_sample(kind, n_sample, args.cells, True, steps=8, warmup=1)
+        res = loop.timed_cpu_sample(kind, n_sample, args.cells, True, steps=8, warmup=1, periodic_potential=False)
         line["cpu_baseline"] = {
             "value": res["value"], "unit": "particle-steps/s", "cores": cores, "kind": kind,
             "sample": f"{cores} processes x ({n_sample:.0e} ions + {n_sample:.0e} electrons), {args.cells}-cell periodic "
@@ -348,7 +351,7 @@ def host_array_leg(sim, n, cells):
         d0[0] += d0[-1]; d0[-1] = d0[0]
         d1[0] += d1[-1]; d1[-1] = d1[0]
         rho = d0 - d1
-        L.poisson_solve_c(p(grid), p(mask), p(rho), sim.cfg.debye_length, p(phi), -3.0, 1.0, 0, 1, len(grid))
+        L.poisson_solve_c(p(grid), p(mask), p(rho), sim.cfg.debye_length, p(phi), -3.0, 1.0, 0, 0, len(grid))
 
     one_step()  # warm-up (allocates the staging buffers)
     bytes_h2d = bytes_d2h = 0

@@ -30,7 +30,8 @@ class StepArgs(C.Structure):
     _fields_ = [("grid", c_void_p), ("object_mask", c_void_p), ("potential", c_void_p), ("charge", c_void_p),
                 ("ions", Species), ("electrons", Species), ("n_points", c_int),
                 ("background_density", c_float), ("a_b", c_float), ("debye_length", c_float),
-                ("object_potential", c_float), ("object_transparency", c_float), ("periodic", c_int),
+                ("object_potential", c_float), ("object_transparency", c_float), ("periodic_particles", c_int),
+                ("periodic_potential", c_int),
                 ("fix_ions", c_int), ("fix_electrons", c_int)]
 
 

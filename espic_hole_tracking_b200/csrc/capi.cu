@@ -289,14 +289,14 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
             !sp[i]->density)
             return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null species pointer");
     int rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
-                                a->periodic, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
-                                a->object_potential, a->object_transparency, 0, a->periodic, a->n_points);
+                                a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
+                                a->object_potential, a->object_transparency, 0, a->periodic_potential, a->n_points);
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
         const espic_species* s = sp[i];
         rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,
                          s->charge_to_mass, a->background_density, -1, s->largest_index, s->particles, s->density,
-                         s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic, s->largest_allowed_slot,
+                         s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic_particles, s->largest_allowed_slot,
                          a->n_points, s->particle_storage_length);
         if (rc) return rc;
     }

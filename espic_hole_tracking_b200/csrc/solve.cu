@@ -136,6 +136,7 @@ struct SolveArgs {
     float debye, obj_pot, transparency;
     int boltzmann, periodic, n;
     int fix_i, fix_e;
+    int fold_ends;  // fused prologue: periodic_particles (fold the end nodes) vs walls (double them)
     int use_smem;
 };
 
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         __shared__ float s_end[4];
         if (tid == 0) {
             float i0 = a.ion[0], i1 = a.ion[n - 1], e0 = a.ele[0], e1 = a.ele[n - 1];
-            if (a.periodic) {
+            if (a.fold_ends) {
                 if (a.fix_i) { i0 = __fadd_rn(i0, i1); i1 = i0; }
                 if (a.fix_e) { e0 = __fadd_rn(e0, e1); e1 = e0; }
             } else {
@@ -530,13 +531,7 @@ int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, flo
     a.fix_i = fix_i;
     a.fix_e = fix_e;
     a.n = n_points;
-    if (periodic_particles != periodic_potential) {
-        // the reference ties the two flags together (infMagSim_script.py:146); keep the general case correct
-        int rc = launch_prepare_charge(ctx, ion, ele, charge_out, n_points, periodic_particles, fix_i, fix_e);
-        if (rc) return rc;
-        a.ion = nullptr;
-        a.charge = charge_out;
-    }
+    a.fold_ends = periodic_particles;  // the driver ties the two flags (infMagSim_script.py:146); they are independent here
     return launch_poisson_impl(ctx, a);
 }
 

@@ -57,6 +57,11 @@ class SimConfig:
     density_growth_rate: float = 0.0
     # ---- module-level flags the reference hard-codes (:133-189, 256-273, 396-406, 720-744) ----
     periodic_particles: bool = False
+    # None = tied to periodic_particles as in the reference (:146).  NB the reference's periodic solve
+    # (Sherman-Morrison with two bugs, reproduced bit-compatibly) returns a sawtooth potential on grids of
+    # ~1000+ points that heats the plasma explosively in the reference itself; periodic
+    # particles with periodic_potential=False (Robin ends, ref :407-409, 426-428) is stable.
+    periodic_potential: bool | None = None
     time_steps_immobile_ions: int = 30000
     time_steps_immobile_electrons: int = 0
     create_electron_dimple: bool = True
@@ -171,6 +176,7 @@ class Simulation:
         self.set_background_acceleration = 0 < c.hole_pushing_start_step < c.n_steps  # :149-152
         self.hole_relative_positions = torch.zeros(max(c.n_steps, 1), dtype=torch.float32, device=self.device)
         self.sampler = injection_sampler or DeviceUniformSampler(self.ctx, self.device)
+        self.periodic_potential = c.periodic_particles if c.periodic_potential is None else c.periodic_potential
         self.k = 0
         self.t = 0.0
         self.v_b = c.v_b_0     # box velocity (moving box disabled: constant), :730-736
@@ -269,7 +275,8 @@ class Simulation:
             a.n_points = self.n_points
             a.background_density = self.background_density
             a.debye_length, a.object_potential, a.object_transparency = c.debye_length, -3., 1.
-            a.periodic = int(c.periodic_particles)
+            a.periodic_particles = int(c.periodic_particles)
+            a.periodic_potential = int(self.periodic_potential)
             self._args = a
         return self._args
 
@@ -319,7 +326,8 @@ class Simulation:
         periodic = c.periodic_particles
         ops.field_solve(self.grid, self.object_mask, self.ion_density, self.electron_density, self.charge_density,
                         c.debye_length, self.potential, object_potential=-3., object_transparency=1.,
-                        boltzmann_electrons=False, periodic_particles=periodic, periodic_potential=periodic,
+                        boltzmann_electrons=False, periodic_particles=periodic,
+                        periodic_potential=self.periodic_potential,
                         fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True,
                         ctx=self.ctx)                                                          # :763-779, 807, 831-836
         potential_ions = self.potential + self.background_potential if ramp else self.potential  # :852-864

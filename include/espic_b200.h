@@ -155,7 +155,8 @@ typedef struct {
     float debye_length;
     float object_potential;
     float object_transparency;
-    int periodic;                /* periodic_particles == periodic_potential */
+    int periodic_particles;      /* mover wrap + end-node fold (ref infMagSim_script.py:145, 764-766) */
+    int periodic_potential;      /* solver variant (ref infMagSim_script.py:146 ties it to the above) */
     int fix_ions;
     int fix_electrons;
 } espic_step_args;

@@ -28,9 +28,10 @@ def expected_particle_injection(n_infinity, v_th, v_d, dt):  # infMagSim_script.
 class CpuSimulation:
     def __init__(self, n_particles, n_cells, periodic, kind="reference", n_ranks=1, rank=0, seed=384,
                  mass_ratio=wl.MASS_RATIO, step_size=wl.STEP_SIZE, sigma=1.0, storage_factor=1.25,
-                 time_steps_immobile_ions=30000, v_b=0.0):
+                 time_steps_immobile_ions=30000, v_b=0.0, periodic_potential=None):
         self.k_ = ocpu.load(kind)
         self.periodic = periodic
+        self.periodic_potential = periodic if periodic_potential is None else periodic_potential  # ref :146
         self.n_particles, self.n_cells, self.n_points = n_particles, n_cells, n_cells + 1
         grid64, dz = np.linspace(wl.Z_MIN, wl.Z_MAX, num=n_cells + 1, endpoint=True, retstep=True)
         self.grid, self.dz = grid64.astype(np.float32), float(dz)
@@ -103,7 +104,7 @@ class CpuSimulation:
         np.subtract(self.ion_density, self.electron_density, out=self.charge_density)
         self.k_.poisson_solve(self.grid, self.object_mask, self.charge_density, wl.DEBYE_LENGTH, self.potential,
                               object_potential=-3., object_transparency=1., boltzmann_electrons=False,
-                              periodic_potential=self.periodic)
+                              periodic_potential=self.periodic_potential)
 
     def push_step(self):
         """:929-950."""
@@ -170,8 +171,9 @@ class CpuSimulation:
 # negligible and omitted), all started together and timed by the slowest. -------------------------
 
 def _worker(args):
-    kind, n_particles, n_cells, periodic, steps, warmup, rank, n_ranks = args
-    sim = CpuSimulation(n_particles, n_cells, periodic, kind=kind, n_ranks=n_ranks, rank=rank)
+    kind, n_particles, n_cells, periodic, steps, warmup, rank, n_ranks, periodic_potential = args
+    sim = CpuSimulation(n_particles, n_cells, periodic, kind=kind, n_ranks=n_ranks, rank=rank,
+                        periodic_potential=periodic_potential)
     sim.init_synthetic(seed=rank)
     sim.initialize()
     for _ in range(warmup):
@@ -186,12 +188,12 @@ def _worker(args):
     return dt, (act["ions"] + act["electrons"]) * n_steps_done
 
 
-def timed_cpu_sample(kind, n_particles, n_cells, periodic, steps, warmup=1, processes=None):
+def timed_cpu_sample(kind, n_particles, n_cells, periodic, steps, warmup=1, processes=None, periodic_potential=None):
     """Returns dict(value=particle-steps/s over all processes, cores=P, seconds=max over workers)."""
     import multiprocessing as mp
     P = processes or os.cpu_count() or 1
     ctx = mp.get_context("fork")
-    jobs = [(kind, n_particles, n_cells, periodic, steps, warmup, r, P) for r in range(P)]
+    jobs = [(kind, n_particles, n_cells, periodic, steps, warmup, r, P, periodic_potential) for r in range(P)]
     if P == 1:
         res = [_worker(jobs[0])]
     else:

@@ -267,9 +267,9 @@ def test_prepare_charge(ops):
         assert_bits_equal(gc.cpu().numpy(), ni - ne)
 
 
-@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("periodic,periodic_potential", [(False, False), (True, True), (True, False)])
 @pytest.mark.parametrize("n_points", [513, 4097, 65537])
-def test_field_solve_fused_equals_separate_calls(ops, periodic, n_points):
+def test_field_solve_fused_equals_separate_calls(ops, periodic, periodic_potential, n_points):
     rng = np.random.default_rng(5)
     grid = dev(wl.make_grid(n_points - 1))
     mask = torch.zeros_like(grid)
@@ -278,9 +278,10 @@ def test_field_solve_fused_equals_separate_calls(ops, periodic, n_points):
     a_i, a_e, a_c, a_p = dev(ni), dev(ne), torch.zeros_like(grid), torch.zeros_like(grid)
     b_i, b_e, b_c, b_p = dev(ni), dev(ne), torch.zeros_like(grid), torch.zeros_like(grid)
     ops.prepare_charge(a_i, a_e, a_c, periodic_particles=periodic, fix_ions=True, fix_electrons=True)
-    ops.poisson_solve(grid, mask, a_c, wl.DEBYE_LENGTH, a_p, object_potential=-3., periodic_potential=periodic)
+    ops.poisson_solve(grid, mask, a_c, wl.DEBYE_LENGTH, a_p, object_potential=-3.,
+                      periodic_potential=periodic_potential)
     ops.field_solve(grid, mask, b_i, b_e, b_c, wl.DEBYE_LENGTH, b_p, object_potential=-3.,
-                    periodic_particles=periodic)
+                    periodic_particles=periodic, periodic_potential=periodic_potential)
     for x, y in ((a_i, b_i), (a_e, b_e), (a_c, b_c), (a_p, b_p)):
         assert_bits_equal(x.cpu().numpy(), y.cpu().numpy())
 
