@@ -29,6 +29,7 @@
 // with the kick table in global memory (L1/L2-resident) and 64-bit global reductions for
 // the deposit.
 #include <cstdio>
+#include <cstdlib>
 
 #include "espic_internal.cuh"
 
@@ -38,6 +39,10 @@ constexpr int kMoveThreads = 256;
 constexpr int kMoveMinBlocks = 4;  // 64 registers per thread: four 8-warp CTAs per SM
 constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
 constexpr int kUnitSlots = 4 * kUnitQuads;    // 256 slots
+#ifndef ESPIC_PREFETCH_UNITS
+#define ESPIC_PREFETCH_UNITS 1
+#endif
+constexpr int kPrefetchUnits = ESPIC_PREFETCH_UNITS;  // L2 prefetch distance, in units of this warp's stream
 constexpr int kSmemBytesPerPoint = 12;
 
 struct MoveArgs {
@@ -59,6 +64,7 @@ struct MoveArgs {
     float dt, qm, a_b;
     int update_position;
     int vec_ok;  // 1: float4 path (16-byte aligned rows), 0: scalar path
+    int prefetch_units;  // L2 prefetch distance along a warp's stream, in 256-slot units
 };
 
 enum { ACT_NONE = 0, ACT_DEPOSIT = 1, ACT_REMOVE = 2 };
@@ -356,6 +362,13 @@ __global__ void __launch_bounds__(kMoveThreads, kMoveMinBlocks) k_move(const Mov
 #pragma unroll 1
             for (int u = u0; u < u1; ++u) {
                 const int q0 = u * kUnitQuads + lane, q1 = q0 + 32;
+                // pull a later unit of this warp's range into L2 (16 lines: 8 of x, 8 of v), so that
+                // the register loads below see L2 latency instead of DRAM latency
+                if (lane < 16 && u + a.prefetch_units < split.n_units) {
+                    const float* row = (lane & 8) ? a.pv : a.px;
+                    const float* line = row + (size_t)(u + a.prefetch_units) * kUnitSlots + (lane & 7) * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+                }
                 Quad p0, p1;
                 load_quad(a, q0, p0);  // both quads' loads are issued before either is used
                 load_quad(a, q1, p1);
@@ -596,6 +609,13 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.a_b = a_b;
     a.update_position = update_position;
     a.vec_ok = ((reinterpret_cast<uintptr_t>(particles) & 15u) == 0 && (storage & 3) == 0) ? 1 : 0;
+    static int prefetch_units = -1;
+    if (prefetch_units < 0) {
+        const char* e = getenv("ESPIC_PREFETCH_UNITS");  // tuning knob; default measured on B200
+        prefetch_units = e ? atoi(e) : kPrefetchUnits;
+        if (prefetch_units < 1) prefetch_units = 1 << 28;  // 0 disables
+    }
+    a.prefetch_units = prefetch_units;
 
     const size_t smem = move_smem_bytes(n_points);
     int max_smem = 0;
