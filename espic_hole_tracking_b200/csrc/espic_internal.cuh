@@ -26,6 +26,8 @@ struct Geom {
     float rcp_dz;    // RN(1/dz), for the correctly rounded quotient below
     float half_span, near_span;  // span/2 and 1.49*span: one-compare test for "within a period"
     float q_shift;   // trunc(z_lo/dz): cell index -> quotient estimate of x/dz (deposit weights)
+    float rcp_dz24;  // rcp_dz * 2^24 (exact scaling): remainder -> 24-bit fixed-point share
+    float fold_lo, fold_hi;  // periodic fast path: x1 - z_lo must lie strictly inside (fold_lo, fold_hi)
     int last_cell;   // n_points - 2
     bool fast_div;   // the 3-operation quotient is safe for this dz (normal exponent range)
 };
@@ -44,10 +46,16 @@ __device__ __forceinline__ Geom make_geom(const float* __restrict__ grid, int n_
     g.half_span = 0.5f * g.span;
     g.near_span = 1.49f * g.span;
     g.q_shift = truncf(g.z_lo * g.rcp_dz);
+    g.rcp_dz24 = g.rcp_dz * 16777216.0f;
+    // within one period either side of the domain AND safely below the parked threshold
+    // (a = fl(x - z_lo) is within half an ulp of x - z_lo; 1e-3*span is ample slack)
+    g.fold_lo = -0.99f * g.span;
+    g.fold_hi = fminf(1.99f * g.span, (g.live_thr - g.z_lo) - 1e-3f * g.span);
     g.last_cell = n_points - 2;
     // exponent window in which neither dz, 1/dz, the quotient nor the residual can leave the
     // normal range for |x - z_lo| <= span
-    g.fast_div = (g.dz > 1e-18f) && (g.dz < 1e18f) && (g.span < 1e18f);
+    g.fast_div = (g.dz > 1e-18f) && (g.dz < 1e18f) && (g.span < 1e18f) &&
+                 (g.live_thr - g.z_lo > 1.002f * g.span);  // parked marker well outside the domain
     return g;
 }
 
@@ -105,6 +113,20 @@ __device__ __forceinline__ unsigned left_share_fixed(const Geom& g, float x, int
     t = __fsub_rn(t, floorf(t));                             // in [0,1)
     const float share = pos ? t : __fsub_rn(1.0f, t);
     return __float2uint_rn(__fmul_rn(share, (float)kWeightOne));
+}
+
+// Same share, computed with one float->int conversion: floor(s*2^24) masked to 24 bits is the
+// fractional part for any whole-cell offset of the quotient estimate.  Returns both node
+// weights (w_left + w_right == 2^24 exactly).
+__device__ __forceinline__ void node_weights_fixed(const Geom& g, float x, int cell, unsigned& w_left,
+                                                   unsigned& w_right) {
+    const float q = (float)cell + g.q_shift;
+    const float s24 = __fmul_rn(fmaf(-q, g.dz, x), g.rcp_dz24);  // 2^24 * fmod(x,dz)/dz up to whole cells
+    const bool pos = x > 0.f;
+    const unsigned t = (unsigned)__float2int_rd(pos ? s24 : -s24) & (kWeightOne - 1u);  // 2^24 * frac, in [0, 2^24)
+    const unsigned c = kWeightOne - t;
+    w_left = pos ? t : c;    // x>0: share = frac ; x<=0: share = 1 - frac(-s)  (ref infMagSim_c.c:219-223)
+    w_right = pos ? c : t;
 }
 
 // ---- context -------------------------------------------------------------------------------

@@ -125,28 +125,58 @@ __device__ __forceinline__ int push_generic(const Geom& g, float& x_io, float& v
 }
 
 // lo += w with the carry into hi taken from the value the atomic returns; the carry update is
-// a predicated shared-memory reduction (no branch).
+// a predicated shared-memory reduction.
 __device__ __forceinline__ void smem_add_carry(unsigned* lo, unsigned* hi, unsigned w) {
     const unsigned old = atomicAdd(lo, w);
-    const unsigned carry = (old > ~w) ? 1u : 0u;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}\n" ::"r"(
-            (unsigned)__cvta_generic_to_shared(hi)),
-        "r"(carry)
-        : "memory");
+    if (old > ~w) atomicAdd(hi, 1u);
 }
 
 template <bool SMEM>
 __device__ __forceinline__ void deposit_one(const Geom& g, float x, int cell, unsigned* s_lo,
                                             unsigned* s_hi, unsigned long long* acc) {
-    const unsigned w0 = left_share_fixed(g, x, cell);
-    const unsigned w1 = kWeightOne - w0;
+    unsigned w0, w1;
+    node_weights_fixed(g, x, cell, w0, w1);
     if (SMEM) {
         smem_add_carry(s_lo + cell, s_hi + cell, w0);
         smem_add_carry(s_lo + cell + 1, s_hi + cell + 1, w1);
     } else {
         atomicAdd(acc + cell, (unsigned long long)w0);
         atomicAdd(acc + cell + 1, (unsigned long long)w1);
+    }
+}
+
+// Deposit of a whole quad without per-slot branches: the eight atomics are issued
+// unconditionally and their (practically never set) carries are collected in a bit mask that
+// is resolved behind one warp vote.
+template <bool SMEM>
+__device__ __forceinline__ void deposit_quad_all(const Geom& g, const float* x, const int* cell, unsigned* s_lo,
+                                                 unsigned* s_hi, unsigned long long* acc) {
+    if (SMEM) {
+        unsigned carries = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned w0, w1;
+            node_weights_fixed(g, x[c], cell[c], w0, w1);
+            const unsigned old0 = atomicAdd(s_lo + cell[c], w0);
+            const unsigned old1 = atomicAdd(s_lo + cell[c] + 1, w1);
+            if (old0 > ~w0) carries |= 1u << (2 * c);
+            if (old1 > ~w1) carries |= 2u << (2 * c);
+        }
+        if (__any_sync(0xffffffffu, carries != 0u)) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (carries & (1u << (2 * c))) atomicAdd(s_hi + cell[c], 1u);
+                if (carries & (2u << (2 * c))) atomicAdd(s_hi + cell[c] + 1, 1u);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned w0, w1;
+            node_weights_fixed(g, x[c], cell[c], w0, w1);
+            atomicAdd(acc + cell[c], (unsigned long long)w0);
+            atomicAdd(acc + cell[c] + 1, (unsigned long long)w1);
+        }
     }
 }
 
@@ -185,55 +215,56 @@ __device__ __noinline__ unsigned quad_generic(const MoveArgs& a, int q, int n_sl
 // On return x,v hold the updated slot (unchanged for dead slots), `cell` the deposit cell,
 // and the result says whether the slot deposits; `removed` (non-periodic) whether it was parked.
 // ---------------------------------------------------------------------------------------------
-template <bool PERIODIC>
-__device__ __forceinline__ bool push_fast(const Geom& g, float& x_io, float& v_io, const float* dv, float dt,
-                                          int& cell_out, bool& removed, bool& rare) {
+// Periodic flavour.  Covers a LIVE slot whose position is inside the domain on entry and moves by
+// less than a period; everything else (dead slots included) raises `rare`.  Returns nothing:
+// in the fast path every slot of the quad deposits.
+__device__ __forceinline__ void push_fast_periodic(const Geom& g, float& x_io, float& v_io, const float* dv,
+                                                   float dt, int& cell_out, bool& rare) {
+    const unsigned last = (unsigned)g.last_cell;
+    // ref :146-153 for a position already inside [z_lo, z_hi): fmodf is the identity
+    const float a0 = __fsub_rn(x_io, g.z_lo);
+    const float x0 = __fadd_rn(a0, g.z_lo);
+    const float b0 = __fsub_rn(x0, g.z_lo);                                 // ref :161 (x - z_min)
+    rare |= !(a0 >= 0.f);                 // would wrap from below (or NaN)
+    rare |= !(b0 < g.span);               // would wrap from above, folded onto z_max, or a parked slot
+    const int c0 = (int)min((unsigned)__float2int_rz(quotient_dz<true>(g, b0)), last);
+    const float v1 = __fadd_rn(v_io, dv[c0]);                               // ref :166-168
+    const float x1 = __fadd_rn(x0, __fmul_rn(v1, dt));                      // ref :170
+    // ref :172-179 within one period either side (and below the parked threshold, ref :172)
+    const float a1 = __fsub_rn(x1, g.z_lo);
+    rare |= !(a1 > g.fold_lo);
+    rare |= !(a1 < g.fold_hi);
+    const float off = __fsub_rn(a1, (a1 >= g.span) ? g.span : 0.f);
+    const float x2 = __fadd_rn(off, (off >= 0.f) ? g.z_lo : g.z_hi);
+    const float b2 = __fsub_rn(x2, g.z_lo);                                 // ref :185
+    rare |= !(b2 < g.span);               // folded exactly onto z_max: the reference maps that cell to 0
+    cell_out = (int)min((unsigned)__float2int_rz(quotient_dz<true>(g, b2)), last);
+    x_io = x2;
+    v_io = v1;
+}
+
+// Wall flavour: dead slots are common (removed particles wait for re-injection), so liveness
+// is handled with selects.  Returns whether the slot deposits; `removed` whether it was parked.
+__device__ __forceinline__ bool push_fast_walls(const Geom& g, float& x_io, float& v_io, const float* dv, float dt,
+                                                int& cell_out, bool& removed, bool& rare) {
     const float x_in = x_io, v_in = v_io;
     const unsigned last = (unsigned)g.last_cell;
-    if (PERIODIC) {
-        const bool alive0 = x_in < g.live_thr;                              // ref :146
-        // ref :148-153 for a position already inside the domain: fmodf is the identity
-        const float a0 = __fsub_rn(x_in, g.z_lo);
-        const float x0 = __fadd_rn(a0, g.z_lo);
-        bool odd = !(a0 >= 0.f) || !(a0 < g.span);
-        const int c0r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x0, g.z_lo)));  // ref :161
-        const int c0 = (int)min((unsigned)c0r, last);
-        odd |= (c0 != c0r);
-        const float v1 = __fadd_rn(v_in, dv[c0]);                           // ref :166-168
-        const float x1 = __fadd_rn(x0, __fmul_rn(v1, dt));                  // ref :170
-        const bool alive1 = x1 < g.live_thr;                                // ref :172
-        // ref :174-179 within one period either side of the domain
-        const float a1 = __fsub_rn(x1, g.z_lo);
-        const float off = __fsub_rn(a1, (a1 >= g.span) ? g.span : 0.f);
-        odd |= !(fabsf(a1 - g.half_span) < g.near_span);
-        const float x2 = __fadd_rn(off, (off >= 0.f) ? g.z_lo : g.z_hi);
-        const int c1r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x2, g.z_lo)));  // ref :185
-        const int c1 = (int)min((unsigned)c1r, last);
-        odd |= (c1 != c1r) || !alive1;
-        rare |= odd && alive0;
-        cell_out = c1;
-        removed = false;
-        x_io = alive0 ? x2 : x_in;
-        v_io = alive0 ? v1 : v_in;
-        return alive0;
-    } else {
-        const bool alive0 = (x_in > g.lo_edge) && (x_in < g.hi_edge);        // ref :156
-        const int c0r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x_in, g.z_lo)));  // ref :161
-        const int c0 = (int)min((unsigned)c0r, last);
-        const float v1 = __fadd_rn(v_in, dv[c0]);                           // ref :166-168
-        const float x1 = __fadd_rn(x_in, __fmul_rn(v1, dt));                // ref :170
-        const bool alive1 = (x1 > g.lo_edge) && (x1 < g.hi_edge);           // ref :182
-        const int c1r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x1, g.z_lo)));    // ref :185
-        const int c1 = (int)min((unsigned)c1r, last);
-        rare |= alive0 && ((c0 != c0r) || (alive1 && (c1 != c1r)) || !(x1 == x1));
-        cell_out = c1;
-        // ref :211-217: alive slots that left the domain, and out-of-bounds slots that do not
-        // carry the parked marker, are parked and pushed on the stack
-        removed = alive0 ? !alive1 : (x_in < g.live_thr);
-        x_io = removed ? g.parked : (alive0 ? x1 : x_in);
-        v_io = alive0 ? v1 : v_in;
-        return alive0 && alive1;
-    }
+    const bool alive0 = (x_in > g.lo_edge) && (x_in < g.hi_edge);        // ref :156
+    const int c0r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x_in, g.z_lo)));  // ref :161
+    const int c0 = (int)min((unsigned)c0r, last);
+    const float v1 = __fadd_rn(v_in, dv[c0]);                           // ref :166-168
+    const float x1 = __fadd_rn(x_in, __fmul_rn(v1, dt));                // ref :170
+    const bool alive1 = (x1 > g.lo_edge) && (x1 < g.hi_edge);           // ref :182
+    const int c1r = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x1, g.z_lo)));    // ref :185
+    const int c1 = (int)min((unsigned)c1r, last);
+    rare |= alive0 && ((c0 != c0r) || (alive1 && (c1 != c1r)) || !(x1 == x1));
+    cell_out = c1;
+    // ref :211-217: alive slots that left the domain, and out-of-bounds slots that do not
+    // carry the parked marker, are parked and pushed on the stack
+    removed = alive0 ? !alive1 : (x_in < g.live_thr);
+    x_io = removed ? g.parked : (alive0 ? x1 : x_in);
+    v_io = alive0 ? v1 : v_in;
+    return alive0 && alive1;
 }
 
 struct Quad {
@@ -258,23 +289,35 @@ template <bool PERIODIC, bool SMEM>
 __device__ __forceinline__ unsigned quad_fast(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
                                               const float* dv, unsigned* s_lo, unsigned* s_hi) {
     int cell[4];
-    unsigned dep = 0, rem = 0;
     bool rare = false;
+    if (PERIODIC) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        bool removed;
-        const bool d = push_fast<PERIODIC>(g, p.x[c], p.v[c], dv, a.dt, cell[c], removed, rare);
-        dep |= d ? (1u << c) : 0u;
-        rem |= removed ? (1u << c) : 0u;
-    }
-    if (__any_sync(0xffffffffu, rare)) {  // uniform, practically never taken
-        return quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, false, s_lo, s_hi);
-    }
-    store_quad(a, q, p);
+        for (int c = 0; c < 4; ++c) push_fast_periodic(g, p.x[c], p.v[c], dv, a.dt, cell[c], rare);
+        if (__any_sync(0xffffffffu, rare))  // uniform, practically never taken once the run is under way
+            return quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, false, s_lo, s_hi);
+        store_quad(a, q, p);
+        deposit_quad_all<SMEM>(g, p.x, cell, s_lo, s_hi, a.acc);
+        return 0u;
+    } else {
+        unsigned dep = 0, rem = 0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        if (dep & (1u << c)) deposit_one<SMEM>(g, p.x[c], cell[c], s_lo, s_hi, a.acc);
-    return rem;
+        for (int c = 0; c < 4; ++c) {
+            bool removed;
+            const bool d = push_fast_walls(g, p.x[c], p.v[c], dv, a.dt, cell[c], removed, rare);
+            dep |= d ? (1u << c) : 0u;
+            rem |= removed ? (1u << c) : 0u;
+        }
+        if (__any_sync(0xffffffffu, rare)) return quad_generic<PERIODIC, SMEM>(a, q, n_slots, dv, false, s_lo, s_hi);
+        store_quad(a, q, p);
+        if (__all_sync(0xffffffffu, dep == 0xFu)) {  // uniform: the whole warp deposits
+            deposit_quad_all<SMEM>(g, p.x, cell, s_lo, s_hi, a.acc);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (dep & (1u << c)) deposit_one<SMEM>(g, p.x[c], cell[c], s_lo, s_hi, a.acc);
+        }
+        return rem;
+    }
 }
 
 // Ordered compaction of the removed slot ids of one warp iteration (ascending slot order):
