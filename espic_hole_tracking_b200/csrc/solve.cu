@@ -3,18 +3,19 @@
 // charge density of the driver loop (ref infMagSim_script.py:763-779, 807).
 //
 // The rows are built per grid node exactly as the reference builds them (float/double mix
-// included).  The Thomas algorithm's three sequential recurrences are evaluated as block-wide
-// scans in fp64:
+// included).  The Thomas algorithm's sequential recurrences are evaluated as block-wide scans
+// in fp64:
 //   D[j] = diag[j] - (sup[j-1]*sub[j-1])/D[j-1]        Moebius map  -> scan of 2x2 matrices
-//   y[j] = rhs[j]  - (y[j-1]*sub[j-1])/D[j-1]          affine map   -> scan of (A,B) pairs
-//   z[j] = y[j]    - (z[j+1]*sup[j])/D[j+1]            affine map, reversed
+//   y[j] = rhs[j]  - y[j-1]*(sub[j-1]/D[j-1])          affine map   -> scan of (A,B) pairs
+//   z[j] = y[j]    - z[j+1]*(sup[j]/D[j+1])            affine map, reversed
 // Each of the 1024 threads owns a contiguous run of m = ceil(n/1024) rows: it composes its run,
-// the block scans the 1024 composites, and the thread then re-walks its run with the
-// reference's own expression starting from the exact incoming value, so rounding differs from
-// the sequential sweep only through that incoming value (~1e-16 relative; the potential is
-// float).  Row j = t*m + i of thread t is stored at [i*1024 + t]: conflict-free in shared
-// memory (grids up to 5120 points keep all five fp64 arrays in the CTA's 227 KB), coalesced in
-// the global workspace used for larger grids.
+// the block scans the 1024 composites, and the thread re-walks its run from the exact incoming
+// value.  Row j = t*m + i of thread t is stored at [i*1024 + t] (coalesced / conflict-free).
+// The elimination (D and the multipliers sub/D, sup/D, 1/D) depends only on the matrix, which
+// is constant from step to step; it is kept in the context's workspace under a key the kernel
+// re-validates on the device at every call, so a driver step costs two affine scans.
+// Rounding differs from the reference's sequential sweep at the 1e-16 level (multiplier
+// precomputed instead of (y*sub)/D; scan re-association); the potential is float.
 //
 // Periodic variant: bug-compatible with the reference: the second solve
 // re-eliminates the already eliminated diagonal and v.w is taken as 0 (the reference reads
@@ -131,19 +132,131 @@ struct SolveArgs {
     float* ele;
     float* charge_out;
     float* potential;
-    double* ws;  // 5 * m * 1024 doubles when the arrays do not fit in shared memory
+    double* ws;   // header + 10 planes of m*1024 doubles (see below)
     int* status;
     float debye, obj_pot, transparency;
     int boltzmann, periodic, n;
     int fix_i, fix_e;
     int fold_ends;  // fused prologue: periodic_particles (fold the end nodes) vs walls (double them)
-    int use_smem;
 };
 
 // Transposed run storage: element i of thread t's run.
 #define AT(arr, i) (arr)[(size_t)(i) * kSolveThreads + threadIdx.x]
 
-// D[0] = dg[0]; D[j] = dg[j] - (sup[j-1]*low[j])/D[j-1].  `sup_prev(i)` must give sup[j-1].
+constexpr int kHeaderDoubles = 16;
+constexpr unsigned long long kFactorMagic = 0x45535049434c5531ull;  // "ESPICLU1"
+
+// One row of the system exactly as the reference builds it (ref infMagSim_c.c:385-503):
+// plain [1,-2,1] / Robin / periodic rows, the absorbing-object variants, and their blend by
+// object_transparency.  low = the sub-diagonal element of ROW j (the reference's lower_diagonal[j-1]).
+struct RowConsts {
+    float dz, lam, rhs_scale;
+    double robin_diag, robin_off, near_one, tr, op;
+};
+
+__device__ __forceinline__ RowConsts row_consts(const SolveArgs& a) {
+    RowConsts k;
+    const int n = a.n;
+    k.dz = (__ldg(a.grid + n - 1) - __ldg(a.grid)) / (float)(n - 1);
+    k.lam = a.debye;
+    const float one = 1.f;
+    const float h2 = k.dz * k.dz / k.lam / k.lam;
+    const float h1 = k.dz / k.lam;
+    k.robin_diag = (double)(h2 * one) / 2. + (double)h1;
+    k.robin_off = (double)(h2 * one) / 2. - (double)h1;
+    k.rhs_scale = -k.dz * k.dz / k.lam / k.lam;
+    k.near_one = 1. - (double)1.e-5f;
+    k.tr = (double)a.transparency;
+    k.op = 1. - (double)a.transparency;
+    return k;
+}
+
+__device__ __forceinline__ void build_row(const SolveArgs& a, const RowConsts& k, const float* charge, int j,
+                                          double& low, double& dg, double& sup, double& rhs, int& bad_mask) {
+    const int n = a.n;
+    const float dz = k.dz, lam = k.lam;
+    double p_low = 1., p_dg = -2., p_sup = 1.;
+    double p_rhs = (j == n - 1) ? 0. : (double)charge[j];
+    if (a.boltzmann) {
+        const double ephi = exp((double)a.potential[j]);
+        p_dg -= (double)(dz * dz) * ephi / (double)lam / (double)lam;
+        p_rhs -= ephi * (1. - (double)a.potential[j]);
+    }
+    p_rhs *= (double)k.rhs_scale;
+    if (j == 0) {
+        p_dg = k.robin_diag;
+        p_sup = k.robin_off;
+        p_rhs = 0.;
+    }
+    if (j == n - 1) {
+        if (a.periodic) {
+            p_low = 0.;
+            p_dg = 1.;
+        } else {
+            p_low = k.robin_off;
+            p_dg = k.robin_diag;
+        }
+        p_rhs = 0.;
+    }
+    double o_low = p_low, o_dg = p_dg, o_sup = p_sup, o_rhs = p_rhs;
+    if (k.op != 0. && j >= 1 && j <= n - 2) {  // the object rows only matter when they are blended in
+        const float mk = a.mask[j], mp = a.mask[j - 1];
+        if (mk > 0.f) {
+            if ((double)mk < k.near_one) {
+                if (a.mask[j + 1] > 0.f) {
+                    const float zl = (float)((1. - (double)mk) * (double)dz);
+                    o_low = (double)(zl / dz);
+                    o_dg = -1. - (double)(zl / dz);
+                    o_sup = 0.;
+                    o_rhs *= (double)(zl / dz);
+                    o_rhs -= (double)a.obj_pot;
+                } else if ((double)mp < k.near_one) {
+                    const float zl = (float)((1. - (double)mp) * (double)dz);
+                    const float zr = (float)((1. - (double)mk) * (double)dz);
+                    o_low = -(1. - (double)(zl / dz));
+                    o_dg = (double)(-(zl + zr) / dz);
+                    o_sup = -(1. - (double)(zr / dz));
+                    o_rhs = -2. * (double)a.obj_pot;
+                } else if ((double)mp > k.near_one) {
+                    const float zr = (float)((1. - (double)mk) * (double)dz);
+                    o_low = 0.;
+                    o_dg = -2. * (double)zr / (double)dz;
+                    o_sup = -2. * (1. - (double)(zr / dz));
+                    o_rhs = -2. * (double)a.obj_pot;
+                } else {
+                    bad_mask = 1;
+                }
+            } else if ((double)mk > k.near_one) {
+                if ((double)mp < k.near_one) {
+                    const float zl = (float)((1. - (double)mp) * (double)dz);
+                    o_low = -2. * (1. - (double)(zl / dz));
+                    o_dg = -2. * (double)zl / (double)dz;
+                    o_sup = 0.;
+                    o_rhs = -2. * (double)a.obj_pot;
+                } else if ((double)mp > k.near_one) {
+                    o_rhs = 0.;
+                } else {
+                    bad_mask = 1;
+                }
+            } else {
+                bad_mask = 1;
+            }
+        } else if (mp > 0.f) {
+            const float zr = (float)((1. - (double)mp) * (double)dz);
+            o_low = 0.;
+            o_dg = -1. - (double)(zr / dz);
+            o_sup = (double)(zr / dz);
+            o_rhs *= (double)(zr / dz);
+            o_rhs -= (double)a.obj_pot;
+        }
+    }
+    low = p_low * k.tr + o_low * k.op;
+    dg = p_dg * k.tr + o_dg * k.op;
+    sup = p_sup * k.tr + o_sup * k.op;
+    rhs = p_rhs * k.tr + o_rhs * k.op;
+}
+
+// D[0] = dg[0]; D[j] = dg[j] - (sup[j-1]*low[j])/D[j-1].
 // Runs are m rows per thread: thread t owns rows t*m .. t*m+m-1 (clipped to n).
 __device__ __forceinline__ void eliminate_diagonal(const double* dg, const double* low, const double* sup,
                                                    double* D, int n, int m, Mat2* s_mat, double* s_edge,
@@ -181,20 +294,39 @@ __device__ __forceinline__ void eliminate_diagonal(const double* dg, const doubl
     __syncthreads();
 }
 
-// in place: y[j] -= (y[j-1]*low[j])/D[j-1], j = 1..n-1
-__device__ __forceinline__ void forward_sweep(double* y, const double* low, const double* D, int n, int m,
-                                              Aff* s_aff, double* s_edge, double* s_scalar) {
-    const int t = threadIdx.x;
-    const int j0 = t * m;
+// Multiplier planes of one Thomas factorisation: fwd[j] = low[j]/D[j-1] (j>=1),
+// bwd[j] = sup[j]/D[j+1] (j<=n-2), inv[j] = 1/D[j].
+__device__ __forceinline__ void make_multipliers(const double* low, const double* sup, const double* D,
+                                                 double* fwd, double* bwd, double* inv, int n, int m,
+                                                 double* s_edge) {
+    const int t = threadIdx.x, j0 = t * m;
+    // neighbours across run boundaries: last D of the previous run, first D of the next run
     s_edge[t] = (j0 + m - 1 < n) ? AT(D, m - 1) : 1.;
+    s_edge[kSolveThreads + t] = (j0 < n) ? AT(D, 0) : 1.;
     __syncthreads();
     const double D_before = (t > 0) ? s_edge[t - 1] : 1.;
+    const double D_after = (t + 1 < kSolveThreads) ? s_edge[kSolveThreads + t + 1] : 1.;
+    for (int i = 0; i < m; ++i) {
+        const int j = j0 + i;
+        if (j >= n) break;
+        const double Dp = (i == 0) ? D_before : AT(D, i - 1);
+        const double Dn = (i == m - 1) ? D_after : AT(D, i + 1);
+        AT(fwd, i) = (j >= 1) ? AT(low, i) / Dp : 0.;
+        AT(bwd, i) = (j <= n - 2) ? AT(sup, i) / Dn : 0.;
+        AT(inv, i) = 1. / AT(D, i);
+    }
+    __syncthreads();
+}
+
+// in place: y[j] -= y[j-1]*fwd[j], j = 1..n-1
+__device__ __forceinline__ void forward_sweep(double* y, const double* fwd, int n, int m, Aff* s_aff,
+                                              double* s_scalar) {
+    const int t = threadIdx.x, j0 = t * m;
     Aff comp = aff_identity();
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
         if (j >= n || j == 0) continue;
-        const double Dp = (i == 0) ? D_before : AT(D, i - 1);
-        comp = compose(Aff{-(AT(low, i) / Dp), AT(y, i)}, comp);
+        comp = compose(Aff{-AT(fwd, i), AT(y, i)}, comp);
     }
     const Aff pre = block_exclusive_scan(comp, aff_identity(), s_aff);
     if (t == 0) s_scalar[0] = AT(y, 0);
@@ -206,32 +338,24 @@ __device__ __forceinline__ void forward_sweep(double* y, const double* low, cons
         if (j == 0) {
             prev = AT(y, 0);
         } else {
-            const double Dp = (i == 0) ? D_before : AT(D, i - 1);
-            prev = AT(y, i) - prev * AT(low, i) / Dp;
+            prev = AT(y, i) - prev * AT(fwd, i);
             AT(y, i) = prev;
         }
     }
     __syncthreads();
 }
 
-// in place: z[j] -= (z[j+1]*sup[j])/D[j+1], j = n-2..0.  The scan runs in REVERSE thread
-// order: thread t is scan position 1023-t.
-__device__ __forceinline__ void backward_sweep(double* z, const double* sup, const double* D, int n, int m,
-                                               Aff* s_aff, double* s_edge, double* s_scalar) {
-    const int t = threadIdx.x;
-    const int j0 = t * m;
-    s_edge[t] = (j0 < n) ? AT(D, 0) : 1.;  // D at the first row of each run = D[j+1] for the previous run's last row
-    __syncthreads();
-    const double D_after = (t + 1 < kSolveThreads) ? s_edge[t + 1] : 1.;
+// in place: z[j] -= z[j+1]*bwd[j], j = n-2..0.  The scan runs in REVERSE thread order.
+__device__ __forceinline__ void backward_sweep(double* z, const double* bwd, int n, int m, Aff* s_aff,
+                                               double* s_edge, double* s_scalar) {
+    const int t = threadIdx.x, j0 = t * m;
     Aff comp = aff_identity();
     for (int i = m - 1; i >= 0; --i) {
         const int j = j0 + i;
         if (j >= n - 1) continue;  // row n-1 is the start value; rows past n do not exist
-        const double Dn = (i == m - 1) ? D_after : AT(D, i + 1);
-        comp = compose(Aff{-(AT(sup, i) / Dn), AT(z, i)}, comp);
+        comp = compose(Aff{-AT(bwd, i), AT(z, i)}, comp);
     }
     // reverse-order exclusive scan: hand the composite to the mirrored thread, scan, hand back
-    // (s_edge has been consumed into registers above; its storage is reused)
     Aff* s_rev = reinterpret_cast<Aff*>(s_edge);
     __syncthreads();
     s_rev[kSolveThreads - 1 - t] = comp;
@@ -254,31 +378,42 @@ __device__ __forceinline__ void backward_sweep(double* z, const double* sup, con
         if (j == n - 1) {
             next = AT(z, i);
         } else {
-            const double Dn = (i == m - 1) ? D_after : AT(D, i + 1);
-            next = AT(z, i) - next * AT(sup, i) / Dn;
+            next = AT(z, i) - next * AT(bwd, i);
             AT(z, i) = next;
         }
     }
     __syncthreads();
 }
 
+// Workspace (doubles): [header 16] then planes of m*1024: low, dg, sup, D, D2 (scratch of the
+// factorisation), fwd, bwd, inv, wq (the factorisation itself, kept between calls) and y.
+// The factorisation depends only on (grid ends, n, debye_length, periodic) while the object
+// rows are blended out (object_transparency == 1) and the electrons are not Boltzmann -- every
+// driver step of every configuration -- so it is computed on the first call, recorded under that
+// key in the header, and later calls go straight to the two sweeps.  Both routes end in the
+// same sweeps over the same planes, so a cached and an uncached call return identical bits.
 __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];  // y plane when it fits (m <= 5)
     __shared__ Mat2 s_mat[32];
     __shared__ Aff s_aff[32];
     __shared__ double s_red[32];
     __shared__ double s_scalar[2];
     __shared__ __align__(16) double s_edge[2 * kSolveThreads];  // run-boundary values; reused as Aff[1024]
+    __shared__ int s_cached;
     const int n = a.n, tid = threadIdx.x;
     const int m = (n + kSolveThreads - 1) / kSolveThreads;
     const size_t plane = (size_t)m * kSolveThreads;
-    double* base = a.use_smem ? reinterpret_cast<double*>(smem_raw) : a.ws;
-    double* low = base;  // low[j] = sub-diagonal element of ROW j (the reference's lower_diagonal[j-1])
+    double* hdr = a.ws;
+    double* low = a.ws + kHeaderDoubles;
     double* dg = low + plane;
     double* sup = dg + plane;
-    double* rhs = sup + plane;
-    double* D = rhs + plane;
-    double* D2 = dg;  // periodic only: the plain diagonal is dead once D exists
+    double* D = sup + plane;
+    double* D2 = D + plane;
+    double* fwd = D2 + plane;
+    double* bwd = fwd + plane;
+    double* inv = bwd + plane;
+    double* wq = inv + plane;
+    double* y = (m <= 5) ? reinterpret_cast<double*>(smem_raw) : wq + plane;
 
     // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
     const float* charge = a.charge;
@@ -299,147 +434,117 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         __syncthreads();
         for (int j = tid; j < n; j += blockDim.x) {
             const float x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : a.ion[j];
-            const float y = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
-            a.charge_out[j] = __fsub_rn(x, y);
+            const float yv = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
+            a.charge_out[j] = __fsub_rn(x, yv);
         }
-        __syncthreads();
         charge = a.charge_out;
     }
 
-    // ---- rows (ref :385-503) ------------------------------------------------------------
-    const float dz = (__ldg(a.grid + n - 1) - __ldg(a.grid)) / (float)(n - 1);
-    const float lam = a.debye;
-    const float k = 1.f;
-    const float h2 = dz * dz / lam / lam;
-    const float h1 = dz / lam;
-    const double robin_diag = (double)(h2 * k) / 2. + (double)h1;
-    const double robin_off = (double)(h2 * k) / 2. - (double)h1;
-    const float rhs_scale = -dz * dz / lam / lam;
-    const double near_one = 1. - (double)1.e-5f;
-    const double tr = (double)a.transparency, op = 1. - (double)a.transparency;
+    const RowConsts k = row_consts(a);
+    const bool cacheable = (a.transparency == 1.f) && !a.boltzmann;
+    if (tid == 0) {
+        const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hdr);
+        s_cached = cacheable && h[0] == kFactorMagic && hdr[1] == (double)__ldg(a.grid) &&
+                   hdr[2] == (double)__ldg(a.grid + n - 1) && hdr[3] == (double)a.debye && hdr[4] == (double)n &&
+                   hdr[5] == (double)a.periodic;
+    }
+    __syncthreads();  // also orders the prologue's charge_out writes before the reads below
     int bad_mask = 0;
+
+    if (!s_cached) {
+        // ---- factorisation: rows (ref :385-503), eliminated diagonal (ref :343-349), multipliers
+        for (int i = 0; i < m; ++i) {
+            const int j = tid * m + i;
+            if (j >= n) break;
+            double r_low, r_dg, r_sup, r_rhs;
+            build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
+            AT(low, i) = r_low;
+            AT(dg, i) = r_dg;
+            AT(sup, i) = r_sup;
+        }
+        __syncthreads();
+        eliminate_diagonal(dg, low, sup, D, n, m, s_mat, s_edge, s_scalar);
+        make_multipliers(low, sup, D, fwd, bwd, inv, n, m, s_edge);
+        if (a.periodic) {  // ref :504-507: the second solve re-eliminates the eliminated diagonal (quirk 1)
+            eliminate_diagonal(D, low, sup, D2, n, m, s_mat, s_edge, s_scalar);
+            // w = "solve" of u = e_{n-1} on that matrix: the forward sweep leaves u unchanged, the
+            // backward sweep and the final division act.  dg / low are free now: scratch for them.
+            double* bwd2 = dg;
+            double* wz = low;
+            {
+                const int t = tid, j0 = t * m;
+                s_edge[kSolveThreads + t] = (j0 < n) ? AT(D2, 0) : 1.;
+                __syncthreads();
+                const double D_after = (t + 1 < kSolveThreads) ? s_edge[kSolveThreads + t + 1] : 1.;
+                double supv[1];
+                (void)supv;
+                for (int i = 0; i < m; ++i) {
+                    const int j = j0 + i;
+                    if (j >= n) break;
+                    const double Dn = (i == m - 1) ? D_after : AT(D2, i + 1);
+                    const double sp = AT(sup, i);
+                    AT(bwd2, i) = (j <= n - 2) ? sp / Dn : 0.;
+                }
+                __syncthreads();
+                for (int i = 0; i < m; ++i) {
+                    const int j = j0 + i;
+                    if (j < n) AT(wz, i) = (j == n - 1) ? 1. : 0.;
+                }
+                __syncthreads();
+            }
+            backward_sweep(wz, bwd2, n, m, s_aff, s_edge, s_scalar);
+            for (int i = 0; i < m; ++i)
+                if (tid * m + i < n) AT(wq, i) = AT(wz, i) / AT(D2, i);
+            __syncthreads();
+        }
+        if (tid == 0 && cacheable) {
+            hdr[1] = (double)__ldg(a.grid);
+            hdr[2] = (double)__ldg(a.grid + n - 1);
+            hdr[3] = (double)a.debye;
+            hdr[4] = (double)n;
+            hdr[5] = (double)a.periodic;
+            __threadfence();
+            reinterpret_cast<unsigned long long*>(hdr)[0] = kFactorMagic;
+        } else if (tid == 0) {
+            reinterpret_cast<unsigned long long*>(hdr)[0] = 0ull;  // the planes no longer match any key
+        }
+    }
+
+    // ---- solve: right-hand side, forward and backward sweeps (ref :350-353), output (ref :518-525)
     for (int i = 0; i < m; ++i) {
         const int j = tid * m + i;
         if (j >= n) break;
-        double p_low = 1., p_dg = -2., p_sup = 1.;
-        double p_rhs = (j == n - 1) ? 0. : (double)charge[j];
-        if (a.boltzmann) {
-            const double ephi = exp((double)a.potential[j]);
-            p_dg -= (double)(dz * dz) * ephi / (double)lam / (double)lam;
-            p_rhs -= ephi * (1. - (double)a.potential[j]);
-        }
-        p_rhs *= (double)rhs_scale;
-        if (j == 0) {
-            p_dg = robin_diag;
-            p_sup = robin_off;
-            p_rhs = 0.;
-        }
-        if (j == n - 1) {
-            if (a.periodic) {
-                p_low = 0.;
-                p_dg = 1.;
-            } else {
-                p_low = robin_off;
-                p_dg = robin_diag;
-            }
-            p_rhs = 0.;
-        }
-        double o_low = p_low, o_dg = p_dg, o_sup = p_sup, o_rhs = p_rhs;
-        if (j >= 1 && j <= n - 2) {
-            const float mk = a.mask[j], mp = a.mask[j - 1];
-            if (mk > 0.f) {
-                if ((double)mk < near_one) {
-                    if (a.mask[j + 1] > 0.f) {
-                        const float zl = (float)((1. - (double)mk) * (double)dz);
-                        o_low = (double)(zl / dz);
-                        o_dg = -1. - (double)(zl / dz);
-                        o_sup = 0.;
-                        o_rhs *= (double)(zl / dz);
-                        o_rhs -= (double)a.obj_pot;
-                    } else if ((double)mp < near_one) {
-                        const float zl = (float)((1. - (double)mp) * (double)dz);
-                        const float zr = (float)((1. - (double)mk) * (double)dz);
-                        o_low = -(1. - (double)(zl / dz));
-                        o_dg = (double)(-(zl + zr) / dz);
-                        o_sup = -(1. - (double)(zr / dz));
-                        o_rhs = -2. * (double)a.obj_pot;
-                    } else if ((double)mp > near_one) {
-                        const float zr = (float)((1. - (double)mk) * (double)dz);
-                        o_low = 0.;
-                        o_dg = -2. * (double)zr / (double)dz;
-                        o_sup = -2. * (1. - (double)(zr / dz));
-                        o_rhs = -2. * (double)a.obj_pot;
-                    } else {
-                        bad_mask = 1;
-                    }
-                } else if ((double)mk > near_one) {
-                    if ((double)mp < near_one) {
-                        const float zl = (float)((1. - (double)mp) * (double)dz);
-                        o_low = -2. * (1. - (double)(zl / dz));
-                        o_dg = -2. * (double)zl / (double)dz;
-                        o_sup = 0.;
-                        o_rhs = -2. * (double)a.obj_pot;
-                    } else if ((double)mp > near_one) {
-                        o_rhs = 0.;
-                    } else {
-                        bad_mask = 1;
-                    }
-                } else {
-                    bad_mask = 1;
-                }
-            } else if (mp > 0.f) {
-                const float zr = (float)((1. - (double)mp) * (double)dz);
-                o_low = 0.;
-                o_dg = -1. - (double)(zr / dz);
-                o_sup = (double)(zr / dz);
-                o_rhs *= (double)(zr / dz);
-                o_rhs -= (double)a.obj_pot;
-            }
-        }
-        AT(low, i) = p_low * tr + o_low * op;
-        AT(dg, i) = p_dg * tr + o_dg * op;
-        AT(sup, i) = p_sup * tr + o_sup * op;
-        AT(rhs, i) = p_rhs * tr + o_rhs * op;
+        double r_low, r_dg, r_sup, r_rhs;
+        build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
+        AT(y, i) = r_rhs;
     }
     if (bad_mask) atomicOr(a.status, ESPIC_ST_BAD_OBJECT_MASK);
     __syncthreads();
-
-    // ---- Thomas (ref :343-354) -------------------------------------------------------------
-    eliminate_diagonal(dg, low, sup, D, n, m, s_mat, s_edge, s_scalar);
-    forward_sweep(rhs, low, D, n, m, s_aff, s_edge, s_scalar);
-    backward_sweep(rhs, sup, D, n, m, s_aff, s_edge, s_scalar);
-    for (int i = 0; i < m; ++i)
-        if (tid * m + i < n) AT(rhs, i) = AT(rhs, i) / AT(D, i);
-    __syncthreads();
-
+    forward_sweep(y, fwd, n, m, s_aff, s_scalar);
+    backward_sweep(y, bwd, n, m, s_aff, s_edge, s_scalar);
     double mean = 0.;
-    if (a.periodic) {  // ref :504-514, :518-523
-        eliminate_diagonal(D, low, sup, D2, n, m, s_mat, s_edge, s_scalar);  // quirk (1): second elimination of the same diagonal
-        // w = second "solve" of u = e_{n-1}: the forward sweep leaves u unchanged, so only the
-        // backward sweep and the final division act.  low[] is free now: reuse it for w.
-        double* w = low;
-        for (int i = 0; i < m; ++i) {
-            const int j = tid * m + i;
-            if (j < n) AT(w, i) = (j == n - 1) ? 1. : 0.;
-        }
-        __syncthreads();
-        backward_sweep(w, sup, D2, n, m, s_aff, s_edge, s_scalar);
-        if (tid == 0) s_scalar[1] = AT(rhs, 0);
+    if (a.periodic) {  // ref :508-514, :518-523
+        if (tid == 0) s_scalar[1] = AT(y, 0) * AT(inv, 0);
         __syncthreads();
         const double v_dot_result = -s_scalar[1];
         const double v_dot_w = 0.;  // quirk (2)
         double part = 0.;
         for (int i = 0; i < m; ++i) {
             if (tid * m + i >= n) break;
-            const double r = AT(rhs, i) - v_dot_result / (1. + v_dot_w) * (AT(w, i) / AT(D2, i));
-            AT(rhs, i) = r;
+            const double r = AT(y, i) * AT(inv, i) - v_dot_result / (1. + v_dot_w) * AT(wq, i);
+            AT(y, i) = r;
             part += r;
         }
         mean = block_sum(part, s_red) / (double)n;
-    }
-    for (int i = 0; i < m; ++i) {
-        const int j = tid * m + i;
-        if (j < n) a.potential[j] = (float)(AT(rhs, i) - mean);
+        for (int i = 0; i < m; ++i) {
+            const int j = tid * m + i;
+            if (j < n) a.potential[j] = (float)(AT(y, i) - mean);
+        }
+    } else {
+        for (int i = 0; i < m; ++i) {
+            const int j = tid * m + i;
+            if (j < n) a.potential[j] = (float)(AT(y, i) * AT(inv, i));
+        }
     }
 }
 
@@ -471,25 +576,17 @@ static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
     const int n = a.n;
     if (n < 3) return fail(ctx, ESPIC_E_ARG, "poisson_solve needs n_points >= 3");
     const int m = (n + kSolveThreads - 1) / kSolveThreads;
-    const size_t bytes = (size_t)5 * m * kSolveThreads * sizeof(double);
-    int max_smem = 0;
-    ESPIC_CUDA(ctx, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    const size_t static_smem = 19 * 1024;  // s_edge and the small arrays of the kernel
-    a.use_smem = (bytes + static_smem <= (size_t)max_smem) ? 1 : 0;
-    size_t dyn = 0;
-    if (a.use_smem) {
-        dyn = bytes;
-        static size_t configured = 0;
-        if (dyn > configured) {
-            ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            configured = dyn;
-        }
-    } else {
-        int rc = ensure(ctx, ctx->solve_ws, bytes, "solve workspace");
-        if (rc) return rc;
-        a.ws = (double*)ctx->solve_ws.ptr;
-    }
+    const size_t plane = (size_t)m * kSolveThreads;
+    int rc = ensure(ctx, ctx->solve_ws, (kHeaderDoubles + 10 * plane) * sizeof(double), "solve workspace");
+    if (rc) return rc;
+    a.ws = (double*)ctx->solve_ws.ptr;
     a.status = ctx->status;
+    const size_t dyn = (m <= 5) ? plane * sizeof(double) : 0;  // <= 40 KB: the y plane
+    static bool configured = false;
+    if (!configured) {  // static (18 KB) + dynamic (40 KB) exceeds the 48 KB default
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kSolveThreads * 8));
+        configured = true;
+    }
     k_poisson<<<1, kSolveThreads, dyn, ctx->stream>>>(a);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_poisson launch");
