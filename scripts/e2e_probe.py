@@ -36,3 +36,40 @@ def c():
         if i > 0:
             ev[1 - bb].synchronize(); float(out[1 - bb][0].max())
 timed(c, "steps + D2H + lagged consume")
+
+# detailed CPU-side timeline of the lagged loop
+import collections
+T = collections.defaultdict(float)
+def d():
+    for i in range(K):
+        bb = i & 1
+        t0 = time.perf_counter(); sim.step(); t1 = time.perf_counter()
+        o = out[bb]
+        o[0].copy_(sim.potential, non_blocking=True); o[1:3].copy_(sim.densities, non_blocking=True)
+        ev[bb].record(); t2 = time.perf_counter()
+        if i > 0:
+            ev[1 - bb].synchronize(); t3 = time.perf_counter(); float(out[1 - bb][0].max()); t4 = time.perf_counter()
+            T["wait"] += t3 - t2; T["max"] += t4 - t3
+        T["step"] += t1 - t0; T["copies"] += t2 - t1
+timed(d, "lagged loop (instrumented)")
+print({k: round(v / K * 1e3, 4) for k, v in T.items()})
+def e():
+    for i in range(K):
+        bb = i & 1
+        sim.step(); o = out[bb]
+        o[0].copy_(sim.potential, non_blocking=True); o[1:3].copy_(sim.densities, non_blocking=True)
+        ev[bb].record()
+        if i > 0:
+            ev[1 - bb].synchronize()
+timed(e, "lagged loop without max()")
+import numpy as np
+outn = [o.numpy() for o in out]
+def f():
+    for i in range(K):
+        bb = i & 1
+        sim.step(); o = out[bb]
+        o[0].copy_(sim.potential, non_blocking=True); o[1:3].copy_(sim.densities, non_blocking=True)
+        ev[bb].record()
+        if i > 0:
+            ev[1 - bb].synchronize(); float(outn[1 - bb][0].max())
+timed(f, "lagged loop with numpy max")
