@@ -143,6 +143,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=float, default=N_PER_SPECIES, help="per species per GPU")
     ap.add_argument("--cells", type=int, default=N_CELLS)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1: density exchange fused into the field-solve kernel over NVLink peer memory (p2p, "
+                         "default) or one NCCL all-reduce per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-arrays", action="store_true")
     args = ap.parse_args()
@@ -170,7 +173,7 @@ def main():
     n = int(args.particles)
     cfg = SimConfig(n_steps=args.steps + args.warmup + 8, n_particles=n, n_cells=args.cells, periodic_particles=True,
                     periodic_potential=False, extra_storage_factor=1.0, track_hole=False)
-    sim = Simulation(cfg, rank=rank, world_size=world, device=device)
+    sim = Simulation(cfg, rank=rank, world_size=world, device=device, exchange=args.exchange)
     sim.init_synthetic()
     sim.initialize()
     ctx = sim.ctx
@@ -295,7 +298,11 @@ def main():
                    "field_solve": "periodic particles, Robin-end potential (periodic_potential=False): the reference's "
                                   "periodic_potential branch is numerically broken on 4097 points (DESIGN.md s.8)",
                    "l2_policy": "inputs (1.6 GB of particle state per GPU) are larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"particle shards x{world}, one fp32 all-reduce of [2,{args.cells + 1}] per step"},
+                   "parallelism": (f"particle shards x{world}; density exchange: " +
+                                   {"p2p": "fused into the field-solve kernel (every rank sums all ranks' "
+                                           f"[2,{args.cells + 1}] slots over NVLink peer memory, no collective launch)",
+                                    "nccl": f"one NCCL fp32 all-reduce of [2,{args.cells + 1}] per step",
+                                    "none": "none (single rank)"}[sim.exchange_mode])},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
     }
 

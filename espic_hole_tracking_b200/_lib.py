@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -32,7 +33,9 @@ class StepArgs(C.Structure):
                 ("background_density", c_float), ("a_b", c_float), ("debye_length", c_float),
                 ("object_potential", c_float), ("object_transparency", c_float), ("periodic_particles", c_int),
                 ("periodic_potential", c_int),
-                ("fix_ions", c_int), ("fix_electrons", c_int)]
+                ("fix_ions", c_int), ("fix_electrons", c_int), ("exchange_parity", c_int),
+                ("exchange_step", c_int), ("reduced_ion_density", c_void_p),
+                ("reduced_electron_density", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/espic_b200.h one to one
@@ -56,6 +59,12 @@ SIGNATURES = {
     "espic_prepare_charge": (c_int, [c_void_p, P, P, P, c_int, c_int, c_int, c_int]),
     "espic_field_solve": (c_int, [c_void_p, P, P, P, P, P, c_int, c_int, c_int, c_float, P, c_float, c_float,
                                   c_int, c_int, c_int]),
+    "espic_exchange_create": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "espic_exchange_open": (c_int, [c_void_p, c_void_p]),
+    "espic_exchange_slot": (c_int, [c_void_p, c_int, C.POINTER(c_void_p)]),
+    "espic_exchange_publish": (c_int, [c_void_p, c_int, c_int]),
+    "espic_field_solve_exchange": (c_int, [c_void_p, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, c_float, P,
+                                           c_float, c_float, c_int, c_int, c_int]),
     "espic_pic_step": (c_int, [c_void_p, C.POINTER(StepArgs)]),
     "espic_inject_particles": (c_int, [c_void_p, c_int, P, c_int, c_float, c_float, P, P, c_float, c_int,
                                        P, P, c_int, P, P, P, P]),
@@ -93,10 +102,22 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def _stale() -> bool:
+    """True when a CUDA source or the public header is newer than the built library."""
+    if not os.path.exists(LIB_PATH):
+        return False
+    built = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(HERE), "include", "espic_b200.h"))
+    return any(os.path.exists(f) and os.path.getmtime(f) > built + 1.0 for f in srcs)
+
+
 def lib() -> C.CDLL:
     """The loaded shared library with argument types declared.  Raises if it is not built."""
     global _lib
     if _lib is None:
+        if _stale() and shutil.which("nvcc") or (_stale() and os.path.exists("/usr/local/cuda/bin/nvcc")):
+            build()  # never run kernels older than their sources
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -145,6 +145,9 @@ void espic_destroy(espic_ctx* ctx) {
     free_scratch(ctx->inject_ws);
     free_scratch(ctx->rng_ws);
     free_scratch(ctx->host_stage);
+    for (int r = 0; r < ctx->xch.world; ++r)
+        if (r != ctx->xch.rank && ctx->xch.peer[r]) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
+    if (ctx->xch.local) cudaFree(ctx->xch.local);
     if (ctx->ev) {
         for (int i = 0; i < ctx->ev_cap; ++i) cudaEventDestroy(ctx->ev[i]);
         free(ctx->ev);
@@ -280,6 +283,41 @@ int espic_field_solve(espic_ctx* ctx, const float* grid, const float* object_mas
                               object_transparency, boltzmann_electrons, periodic_potential, n_points);
 }
 
+int espic_exchange_create(espic_ctx* ctx, int n_points, int world, int rank, void* handle_out) {
+    if (!ctx) return ESPIC_E_ARG;
+    return exchange_create(ctx, n_points, world, rank, handle_out);
+}
+
+int espic_exchange_open(espic_ctx* ctx, const void* handles) {
+    if (!ctx) return ESPIC_E_ARG;
+    return exchange_open(ctx, handles);
+}
+
+int espic_exchange_slot(espic_ctx* ctx, int parity, float** slot_out) {
+    if (!ctx || !slot_out || !ctx->xch.local) return ESPIC_E_ARG;
+    *slot_out = static_cast<float*>(ctx->xch.local) + (size_t)(parity & 1) * ctx->xch.slot_floats;
+    return ESPIC_OK;
+}
+
+int espic_exchange_publish(espic_ctx* ctx, int parity, int step) {
+    if (!ctx) return ESPIC_E_ARG;
+    return exchange_publish(ctx, parity, step);
+}
+
+int espic_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* object_mask,
+                               float* ion_density, float* electron_density, float* charge, int periodic_particles,
+                               int fix_ions, int fix_electrons, float debye_length, float* potential,
+                               float object_potential, float object_transparency, int boltzmann_electrons,
+                               int periodic_potential, int n_points) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !object_mask || !ion_density || !electron_density || !charge || !potential)
+        return fail(ctx, ESPIC_E_ARG, "espic_field_solve_exchange: null pointer argument");
+    return launch_field_solve_exchange(ctx, parity, step, grid, object_mask, ion_density, electron_density, charge,
+                                       periodic_particles, fix_ions, fix_electrons, debye_length, potential,
+                                       object_potential, object_transparency, boltzmann_electrons,
+                                       periodic_potential, n_points);
+}
+
 int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
     if (!ctx || !a) return ESPIC_E_ARG;
     if (!a->grid || !a->object_mask || !a->potential || !a->charge) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null grid pointer");
@@ -288,9 +326,20 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         if (!sp[i]->particles || !sp[i]->empty_slots || !sp[i]->current_empty_slot || !sp[i]->largest_index ||
             !sp[i]->density)
             return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null species pointer");
-    int rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
+    int rc;
+    if (a->exchange_parity >= 0) {
+        if (!a->reduced_ion_density || !a->reduced_electron_density)
+            return fail(ctx, ESPIC_E_ARG, "espic_pic_step: exchange mode needs the reduced density buffers");
+        rc = launch_field_solve_exchange(ctx, a->exchange_parity, a->exchange_step, a->grid, a->object_mask,
+                                         a->reduced_ion_density, a->reduced_electron_density, a->charge,
+                                         a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length,
+                                         a->potential, a->object_potential, a->object_transparency, 0,
+                                         a->periodic_potential, a->n_points);
+    } else {
+        rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
                                 a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
                                 a->object_potential, a->object_transparency, 0, a->periodic_potential, a->n_points);
+    }
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
         const espic_species* s = sp[i];

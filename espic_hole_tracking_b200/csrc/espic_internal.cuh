@@ -158,6 +158,15 @@ struct espic_ctx {
     espic::Scratch host_stage;          // device staging for the host-pointer entry points
     int* dev_int2 = nullptr;            // two device ints used by the host-pointer wrappers
 
+    // multi-GPU density exchange (see solve.cu)
+    struct Exchange {
+        int world = 0, rank = 0, n_points = 0;
+        size_t slot_floats = 0;         // floats per parity slot (2 * padded n_points)
+        void* local = nullptr;          // this rank's buffer
+        void* peer[ESPIC_MAX_RANKS] = {nullptr};  // all ranks' buffers as seen from here (peer[rank] == local)
+        bool opened = false;
+    } xch;
+
     // mover launch geometry
     int mover_grid = 0, mover_block = 0;
 
@@ -201,6 +210,13 @@ int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, flo
                        float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
                        float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
                        int n_points);
+int exchange_create(espic_ctx* ctx, int n_points, int world, int rank, void* handle_out);
+int exchange_open(espic_ctx* ctx, const void* handles);
+int exchange_publish(espic_ctx* ctx, int parity, int step);
+int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* mask,
+                                float* ion, float* ele, float* charge_out, int periodic_particles, int fix_i,
+                                int fix_e, float debye, float* potential, float obj_pot, float transparency,
+                                int boltzmann, int periodic_potential, int n_points);
 int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge, int n, int periodic,
                           int fix_i, int fix_e);
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,

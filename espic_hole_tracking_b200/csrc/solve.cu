@@ -20,6 +20,8 @@
 // Periodic variant: bug-compatible with the reference: the second solve
 // re-eliminates the already eliminated diagonal and v.w is taken as 0 (the reference reads
 // one element past its arrays there; with glibc the product underflows to +0.0).
+#include <cstring>
+
 #include "espic_internal.cuh"
 
 namespace espic {
@@ -138,6 +140,12 @@ struct SolveArgs {
     int boltzmann, periodic, n;
     int fix_i, fix_e;
     int fold_ends;  // fused prologue: periodic_particles (fold the end nodes) vs walls (double them)
+    // multi-GPU exchange: the densities are the rank-ordered sum of every rank's published slot
+    int world;
+    unsigned expect;                          // publication counter value to wait for
+    const float* peer_slot[ESPIC_MAX_RANKS];  // [2][n_pad] floats: ion row, electron row
+    const unsigned* peer_flag[ESPIC_MAX_RANKS];
+    int n_pad;
 };
 
 // Transposed run storage: element i of thread t's run.
@@ -415,6 +423,39 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     double* wq = inv + plane;
     double* y = (m <= 5) ? reinterpret_cast<double*>(smem_raw) : wq + plane;
 
+    // ---- multi-GPU: the all-reduce of the two density grids (ref infMagSim_script.py:763, 773),
+    // done by every rank for itself over NVLink peer memory.  Ranks are summed in rank order,
+    // so all ranks obtain bit-identical densities and therefore bit-identical fields.
+    if (a.world > 1) {
+        if (tid < a.world) {
+            // wait until peer `tid` has published its densities for this step (system-scope acquire)
+            const unsigned* flag = a.peer_flag[tid];
+            const long long t0 = clock64();
+            unsigned seen;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                if ((int)(seen - a.expect) >= 0) break;
+                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer died; fail loudly instead of hanging the GPU
+                    atomicOr(a.status, ESPIC_ST_EXCHANGE_TIMEOUT);
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += blockDim.x) {
+            float si = 0.f, se = 0.f;
+            for (int r = 0; r < a.world; ++r) {
+                const float* slot = a.peer_slot[r];
+                si = __fadd_rn(si, __ldcv(slot + j));
+                se = __fadd_rn(se, __ldcv(slot + a.n_pad + j));
+            }
+            a.ion[j] = si;
+            a.ele[j] = se;
+        }
+        __syncthreads();
+    }
+
     // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
     const float* charge = a.charge;
     if (a.ion) {
@@ -629,6 +670,104 @@ int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, flo
     a.fix_e = fix_e;
     a.n = n_points;
     a.fold_ends = periodic_particles;  // the driver ties the two flags (infMagSim_script.py:146); they are independent here
+    return launch_poisson_impl(ctx, a);
+}
+
+// ---- multi-GPU exchange buffers ---------------------------------------------------------------
+// layout of one rank's buffer: [parity 0 slot][parity 1 slot][flags: one 128-byte line per parity]
+static size_t xch_bytes(const espic_ctx::Exchange& x) { return 2 * x.slot_floats * sizeof(float) + 2 * 128; }
+static unsigned* xch_flag(void* base, const espic_ctx::Exchange& x, int parity) {
+    return reinterpret_cast<unsigned*>(static_cast<char*>(base) + 2 * x.slot_floats * sizeof(float) + parity * 128);
+}
+static float* xch_slot(void* base, const espic_ctx::Exchange& x, int parity) {
+    return static_cast<float*>(base) + (size_t)parity * x.slot_floats;
+}
+
+int exchange_create(espic_ctx* ctx, int n_points, int world, int rank, void* handle_out) {
+    if (world < 1 || world > ESPIC_MAX_RANKS || rank < 0 || rank >= world || n_points < 3 || !handle_out)
+        return fail(ctx, ESPIC_E_ARG, "espic_exchange_create: bad arguments (world %d rank %d)", world, rank);
+    if (ctx->xch.local) return fail(ctx, ESPIC_E_ARG, "espic_exchange_create: already created");
+    auto& x = ctx->xch;
+    x.world = world;
+    x.rank = rank;
+    x.n_points = n_points;
+    x.slot_floats = 2 * (size_t)((n_points + 31) & ~31);
+    ESPIC_CUDA(ctx, cudaMalloc(&x.local, xch_bytes(x)));
+    ESPIC_CUDA(ctx, cudaMemset(x.local, 0, xch_bytes(x)));
+    // counters start "one step in the past" so that step 0 has to be published like any other
+    const unsigned minus_one = 0xffffffffu;
+    for (int p = 0; p < 2; ++p)
+        ESPIC_CUDA(ctx, cudaMemcpy(xch_flag(x.local, x, p), &minus_one, sizeof(unsigned), cudaMemcpyHostToDevice));
+    cudaIpcMemHandle_t h;
+    ESPIC_CUDA(ctx, cudaIpcGetMemHandle(&h, x.local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == ESPIC_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &h, sizeof(h));
+    x.peer[rank] = x.local;
+    return 0;
+}
+
+int exchange_open(espic_ctx* ctx, const void* handles) {
+    auto& x = ctx->xch;
+    if (!x.local || !handles) return fail(ctx, ESPIC_E_ARG, "espic_exchange_open: create first");
+    for (int r = 0; r < x.world; ++r) {
+        if (r == x.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)r * ESPIC_IPC_HANDLE_BYTES, sizeof(h));
+        ESPIC_CUDA(ctx, cudaIpcOpenMemHandle(&x.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    x.opened = true;
+    return 0;
+}
+
+__global__ void k_publish(unsigned* flag, unsigned value) {
+    // everything enqueued before this kernel on the stream (pushes, injections) has completed;
+    // make it visible system-wide, then publish
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+int exchange_publish(espic_ctx* ctx, int parity, int step) {
+    auto& x = ctx->xch;
+    if (!x.local) return fail(ctx, ESPIC_E_ARG, "espic_exchange_publish: no exchange");
+    k_publish<<<1, 1, 0, ctx->stream>>>(xch_flag(x.local, x, parity & 1), (unsigned)step);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_publish launch");
+}
+
+int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* mask,
+                                float* ion, float* ele, float* charge_out, int periodic_particles, int fix_i,
+                                int fix_e, float debye, float* potential, float obj_pot, float transparency,
+                                int boltzmann, int periodic_potential, int n_points) {
+    auto& x = ctx->xch;
+    if (!x.opened && x.world > 1) return fail(ctx, ESPIC_E_ARG, "espic_field_solve_exchange: exchange not opened");
+    if (!x.local || n_points != x.n_points) return fail(ctx, ESPIC_E_ARG, "espic_field_solve_exchange: n_points mismatch");
+    SolveArgs a{};
+    a.grid = grid;
+    a.mask = mask;
+    a.ion = ion;
+    a.ele = ele;
+    a.charge_out = charge_out;
+    a.potential = potential;
+    a.debye = debye;
+    a.obj_pot = obj_pot;
+    a.transparency = transparency;
+    a.boltzmann = boltzmann;
+    a.periodic = periodic_potential;
+    a.fix_i = fix_i;
+    a.fix_e = fix_e;
+    a.n = n_points;
+    a.fold_ends = periodic_particles;
+    a.world = x.world;
+    a.expect = (unsigned)step;
+    a.n_pad = (int)(x.slot_floats / 2);
+    for (int r = 0; r < x.world; ++r) {
+        a.peer_slot[r] = xch_slot(x.peer[r], x, parity & 1);
+        a.peer_flag[r] = xch_flag(x.peer[r], x, parity & 1);
+    }
+    if (x.world == 1) {  // single rank: the slot is the density itself
+        ESPIC_CUDA(ctx, cudaMemcpyAsync(ion, a.peer_slot[0], (size_t)n_points * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        ESPIC_CUDA(ctx, cudaMemcpyAsync(ele, a.peer_slot[0] + a.n_pad, (size_t)n_points * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return launch_poisson_impl(ctx, a);
 }
 

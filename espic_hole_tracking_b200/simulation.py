@@ -138,7 +138,10 @@ class SpeciesStore:
 
 class Simulation:
     def __init__(self, cfg: SimConfig, rank: int = 0, world_size: int = 1, device=None, process_group=None,
-                 injection_sampler=None):
+                 injection_sampler=None, exchange: str = "auto"):
+        """exchange: how the per-step density all-reduce is done for world_size > 1 --
+        "p2p" (default via "auto"): fused into the field-solve kernel over NVLink peer memory
+        (distributed.DensityExchange); "nccl": one torch.distributed all-reduce per step."""
         self.cfg = cfg
         self.rank, self.world = rank, world_size
         self.pg = process_group
@@ -176,12 +179,29 @@ class Simulation:
         self.set_background_acceleration = 0 < c.hole_pushing_start_step < c.n_steps  # :149-152
         self.hole_relative_positions = torch.zeros(max(c.n_steps, 1), dtype=torch.float32, device=self.device)
         self.sampler = injection_sampler or DeviceUniformSampler(self.ctx, self.device)
+        if exchange == "auto":
+            exchange = "p2p" if world_size > 1 else "none"
+        self.exchange_mode = exchange if world_size > 1 or exchange == "p2p" else "none"
+        self.xch = None
+        if self.exchange_mode == "p2p":
+            self.ctx = Context(self.device.index)   # the exchange buffers belong to a context of their own
+            ops.seedgenrand_c(self.seed, ctx=self.ctx)
+            self.sampler = injection_sampler or DeviceUniformSampler(self.ctx, self.device)
+            self.xch = dd.DensityExchange(self.ctx, n_points, world_size, rank, self.device, process_group)
         self.periodic_potential = c.periodic_particles if c.periodic_potential is None else c.periodic_potential
         self.k = 0
         self.t = 0.0
         self.v_b = c.v_b_0     # box velocity (moving box disabled: constant), :730-736
         self.a_b = 0.0
         self.hist = {}
+
+    def _deposit_rows(self, k: int):
+        """Where the pushes/injections that produce the densities entering step k deposit: the
+        exchange slot of that step's parity, or the local density buffer."""
+        if self.xch is not None:
+            slot = self.xch.slot(k)
+            return slot[0], slot[1]
+        return self.ion_density, self.electron_density
 
     # ---- particle initialisation ----------------------------------------------------------
     def load_particles(self, ions_xv: np.ndarray, electrons_xv: np.ndarray) -> None:
@@ -223,7 +243,8 @@ class Simulation:
     # ---- start-up (infMagSim_script.py:696-716) --------------------------------------------
     def initialize(self) -> None:
         c = self.cfg
-        for store, den in ((self.ions, self.ion_density), (self.electrons, self.electron_density)):
+        den_i, den_e = self._deposit_rows(0)
+        for store, den in ((self.ions, den_i), (self.electrons, den_e)):
             ops.accumulate_density(self.grid, self.object_mask, self.background_density, store.largest_index,
                                    store.particles, den, store.empty_slots, store.current_empty_slot,
                                    periodic_particles=c.periodic_particles, use_pure_c_version=True, ctx=self.ctx)
@@ -232,10 +253,13 @@ class Simulation:
                                  store.largest_index, store.particles, store.empty_slots,
                                  store.current_empty_slot, v_b=self.v_b, a_b=0.0,
                                  periodic_particles=c.periodic_particles, use_pure_c_version=True, ctx=self.ctx)
+        if self.xch is not None:
+            self.xch.publish(0, 0)
 
     # ---- one timestep (infMagSim_script.py:756-1023) ---------------------------------------
     def reduce_densities(self) -> None:
-        dd.all_reduce_densities(self.densities, self.world, self.pg)   # :763, :773 in one call
+        if self.xch is None:
+            dd.all_reduce_densities(self.densities, self.world, self.pg)   # :763, :773 in one call
 
     def injection_counts(self, k: int):
         """Expected wall flux with stochastic rounding (:965-975, 1005-1009)."""
@@ -289,6 +313,14 @@ class Simulation:
         if not ramp and not c.phase_space_histograms:
             # field solve + both pushes as one host call (espic_pic_step); same kernels, same order
             a = self._step_args()
+            if self.xch is not None:   # densities entering step k: slot k&1 of every rank; pushes fill slot (k+1)&1
+                nxt_i, nxt_e = self._deposit_rows(k + 1)
+                a.ions.density, a.electrons.density = nxt_i.data_ptr(), nxt_e.data_ptr()
+                a.exchange_parity, a.exchange_step = k & 1, k
+                a.reduced_ion_density = self.ion_density.data_ptr()
+                a.reduced_electron_density = self.electron_density.data_ptr()
+            else:
+                a.exchange_parity = -1
             a.a_b = self.a_b
             a.fix_ions = int(periodic or k <= c.time_steps_immobile_ions)
             a.fix_electrons = 1
@@ -298,8 +330,9 @@ class Simulation:
             self.ctx.check(self.ctx._lib.espic_pic_step(self.ctx.handle, a), "espic_pic_step")
         else:
             self._step_operator_by_operator(k, ions_mobile, ramp)
+        den_i, den_e = self._deposit_rows(k + 1)
         if not ions_mobile:
-            self.ion_density.fill_(1.0)                                                          # :934
+            den_i.fill_(1.0)   # :934 (every rank sets ones; the next all-reduce sums them, as in the reference)
         if c.track_hole and k > c.initial_transient_steps and k < self.hole_relative_positions.shape[0]:  # :896-897
             ops.hole_position_tracking(self.potential, self.dz, c.debye_length * 4., self.grid, self.fine_mesh,
                                        out=self.hole_relative_positions[k:k + 1], ctx=self.ctx)
@@ -310,12 +343,14 @@ class Simulation:
                 ops.inject_particles(n_i, self.grid, self.dt, self.v_th_i / math.sqrt(c.sigma),
                                      self.background_density, self.sampler, self.v_b - c.v_d_i, self.a_b, k,
                                      s.tags, s.particles, s.empty_slots, s.current_empty_slot, s.largest_index,
-                                     self.ion_density, ctx=self.ctx)
+                                     den_i, ctx=self.ctx)
             if n_e > 0:                                                                          # :1015-1019
                 s = self.electrons
                 ops.inject_particles(n_e, self.grid, self.dt, self.v_th_e, self.background_density, self.sampler,
                                      self.v_b, self.a_b, k, s.tags, s.particles, s.empty_slots,
-                                     s.current_empty_slot, s.largest_index, self.electron_density, ctx=self.ctx)
+                                     s.current_empty_slot, s.largest_index, den_e, ctx=self.ctx)
+        if self.xch is not None:
+            self.xch.publish(k + 1, k + 1)
         self.t += self.dt
         self.k += 1
 
@@ -324,24 +359,33 @@ class Simulation:
         ion potential carries the background ramp or the per-step histograms are on)."""
         c = self.cfg
         periodic = c.periodic_particles
-        ops.field_solve(self.grid, self.object_mask, self.ion_density, self.electron_density, self.charge_density,
-                        c.debye_length, self.potential, object_potential=-3., object_transparency=1.,
-                        boltzmann_electrons=False, periodic_particles=periodic,
-                        periodic_potential=self.periodic_potential,
-                        fix_ions=periodic or k <= c.time_steps_immobile_ions, fix_electrons=True,
-                        ctx=self.ctx)                                                          # :763-779, 807, 831-836
+        fix_ions = periodic or k <= c.time_steps_immobile_ions
+        if self.xch is not None:
+            self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            P = lambda t: t.data_ptr()
+            self.ctx.check(self.ctx._lib.espic_field_solve_exchange(
+                self.ctx.handle, k & 1, k, P(self.grid), P(self.object_mask), P(self.ion_density),
+                P(self.electron_density), P(self.charge_density), int(periodic), int(fix_ions), 1, c.debye_length,
+                P(self.potential), -3., 1., 0, int(self.periodic_potential), self.n_points), "field_solve_exchange")
+        else:
+            ops.field_solve(self.grid, self.object_mask, self.ion_density, self.electron_density,
+                            self.charge_density, c.debye_length, self.potential, object_potential=-3.,
+                            object_transparency=1., boltzmann_electrons=False, periodic_particles=periodic,
+                            periodic_potential=self.periodic_potential, fix_ions=fix_ions, fix_electrons=True,
+                            ctx=self.ctx)                                                      # :763-779, 807, 831-836
+        den_i, den_e = self._deposit_rows(k + 1)
         potential_ions = self.potential + self.background_potential if ramp else self.potential  # :852-864
         if c.phase_space_histograms:
             self.phase_space()
         s = self.ions
         ops.move_particles(self.grid, self.object_mask, potential_ions, self.dt if ions_mobile else 0.,
                            s.charge_to_mass, self.background_density, s.largest_index, s.particles,
-                           self.ion_density, s.empty_slots, s.current_empty_slot, self.a_b,
+                           den_i, s.empty_slots, s.current_empty_slot, self.a_b,
                            periodic_particles=periodic, use_pure_c_version=True, ctx=self.ctx)
         s = self.electrons
         ops.move_particles(self.grid, self.object_mask, self.potential,
                            0. if k < c.time_steps_immobile_electrons else self.dt, s.charge_to_mass,
-                           self.background_density, s.largest_index, s.particles, self.electron_density,
+                           self.background_density, s.largest_index, s.particles, den_e,
                            s.empty_slots, s.current_empty_slot, self.a_b, periodic_particles=periodic,
                            use_pure_c_version=True, ctx=self.ctx)                                # :940-950
 

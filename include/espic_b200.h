@@ -47,8 +47,12 @@ enum {
     ESPIC_ST_STACK_EMPTY = 4,      /* ref infMagSim_cython.py:255-256 "no empty slots" */
     ESPIC_ST_BAD_INJECT_INDEX = 8, /* ref infMagSim_cython.py:272-273 */
     ESPIC_ST_BAD_OBJECT_MASK = 16, /* ref infMagSim_c.c:468,482,485 */
-    ESPIC_ST_SAMPLER_STALL = 32    /* ref infMagSim_c.c:589-607 (1000 rejections) */
+    ESPIC_ST_SAMPLER_STALL = 32,   /* ref infMagSim_c.c:589-607 (1000 rejections) */
+    ESPIC_ST_EXCHANGE_TIMEOUT = 64 /* a peer never published its densities (multi-GPU exchange) */
 };
+
+#define ESPIC_MAX_RANKS 16
+#define ESPIC_IPC_HANDLE_BYTES 64
 
 typedef struct espic_ctx espic_ctx;
 
@@ -159,9 +163,46 @@ typedef struct {
     int periodic_potential;      /* solver variant (ref infMagSim_script.py:146 ties it to the above) */
     int fix_ions;
     int fix_electrons;
+    int exchange_parity;         /* < 0: single-rank field solve on ions.density / electrons.density.
+                                  * 0/1: multi-GPU -- the field solve sums every rank's exchange slot of
+                                  * this parity (espic_field_solve_exchange) into reduced_ion/_electron,
+                                  * while the pushes deposit into ions.density / electrons.density
+                                  * (the caller points them at the NEXT slot) */
+    int exchange_step;
+    float *reduced_ion_density;  /* only read when exchange_parity >= 0 */
+    float *reduced_electron_density;
 } espic_step_args;
 
 int espic_pic_step(espic_ctx *ctx, const espic_step_args *args);
+
+/* ---- multi-GPU density exchange fused into the field solve (replaces comm.Allreduce of the two
+ * density grids, ref infMagSim_script.py:763, 773) ------------------------------------------------
+ * One process per GPU of one box.  Each rank owns a small symmetric buffer in its own HBM
+ * (two parity slots of [2][n_points] floats + a publication counter), exported to its peers
+ * through CUDA IPC and read by them over NVLink.  Per step a rank's movers deposit into the
+ * current slot, espic_exchange_publish() makes it visible, and espic_field_solve_exchange()
+ * -- one kernel -- waits for every peer's counter, sums the P slots in rank order (so every
+ * rank computes bit-identical fields), applies the end-node fix, forms the charge density and
+ * solves.  No NCCL call, no extra launch, no host synchronisation on the step path.
+ *   espic_exchange_create : allocate the local buffer, return its IPC handle (64 bytes)
+ *   espic_exchange_open   : map the peers' buffers; handles = world x 64 bytes in rank order
+ *   espic_exchange_slot   : device pointer of this rank's [2][n_points] slot of a given parity
+ */
+int espic_exchange_create(espic_ctx *ctx, int n_points, int world, int rank, void *handle_out);
+int espic_exchange_open(espic_ctx *ctx, const void *handles);
+int espic_exchange_slot(espic_ctx *ctx, int parity, float **slot_out);
+/* Marks slot `parity` of this rank as holding the densities that enter step `step` (0-based;
+ * call after the pushes and injections that produced them).  Stream-ordered. */
+int espic_exchange_publish(espic_ctx *ctx, int parity, int step);
+/* espic_field_solve over the rank-ordered sum of all ranks' slots of `parity` for `step`.
+ * ion_density / electron_density (local, n_points each) receive the reduced, end-fixed densities. */
+int espic_field_solve_exchange(espic_ctx *ctx, int parity, int step, const float *grid,
+                               const float *object_mask, float *ion_density,
+                               float *electron_density, float *charge, int periodic_particles,
+                               int fix_ions, int fix_electrons, float debye_length,
+                               float *potential, float object_potential,
+                               float object_transparency, int boltzmann_electrons,
+                               int periodic_potential, int n_points);
 
 /* Replaces the body of inject_particles (ref infMagSim_cython.py:230-285) with both random
  * inputs supplied as device arrays: velocities[n_inject] (signed; the sign picks the wall)
