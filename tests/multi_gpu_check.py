@@ -1,7 +1,7 @@
 """Run under torchrun on >= 2 GPUs: the fused peer-memory density exchange against the NCCL
 all-reduce path, step by step, from identical particle arrays.
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/multi_gpu_check.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 """
 import os
 import sys
