@@ -1,6 +1,8 @@
 """Integration parity on the GPU: N steps of the full driver loop against the oracle loop
 (oracle/loop.py, the Python-3 restatement of infMagSim_script.py:756-1023 over the compiled
 reference kernels), periodic and non-periodic with wall injection."""
+import os
+
 import numpy as np
 import pytest
 
@@ -192,3 +194,37 @@ def test_nonperiodic_simulation_runs_and_conserves(pkg):
     assert e["fe"] > 0 and e["ke_electrons"] > 0
     pos = sim.hole_relative_positions.cpu().numpy()
     assert np.all(np.abs(pos) <= 3.0)
+
+
+def test_npz_output_and_checkpoint_resume(pkg, tmp_path):
+    """The reference's .npz key set (consumed by its analysis notebook) and a checkpoint/resume
+    round trip that continues a periodic run bit-identically."""
+    from espic_hole_tracking_b200 import io as eio
+    from espic_hole_tracking_b200.simulation import SimConfig, Simulation
+    cfg = SimConfig(n_steps=30, n_particles=50_000, n_cells=256, periodic_particles=True, periodic_potential=False,
+                    track_hole=True, initial_transient_steps=3, phase_space_histograms=True)
+    sim = Simulation(cfg)
+    sim.init_synthetic()
+    sim.initialize()
+    rec = eio.Recorder(sim)
+    for _ in range(12):
+        sim.step()
+        rec.record()
+    eio.save_checkpoint(sim, str(tmp_path / "ck.pt"))
+    for _ in range(8):
+        sim.step()
+        rec.record()
+    out = rec.save(str(tmp_path))
+    data = np.load(out)
+    assert set(data.files) == set(eio.NPZ_KEYS)
+    assert data["potentials"].shape == (20, 257) and data["times"].shape == (20,)
+    assert data["electron_distribution_functions"].shape == (20, 100, 100)
+    assert 49_900 <= data["electron_distribution_functions"][0].sum() <= 50_000   # |v| < 4 v_th window
+    assert os.path.basename(out).startswith("l0.1250_Vd0.000_hole_depth")
+    resumed = Simulation(cfg)
+    resumed.init_synthetic()
+    eio.load_checkpoint(resumed, str(tmp_path / "ck.pt"))
+    for _ in range(8):
+        resumed.step()
+    assert_bits_equal(resumed.potential.cpu().numpy(), sim.potential.cpu().numpy(), "resumed potential")
+    assert_bits_equal(resumed.electrons.particles.cpu().numpy(), sim.electrons.particles.cpu().numpy(), "resumed electrons")
