@@ -146,6 +146,9 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1: density exchange fused into the field-solve kernel over NVLink peer memory (p2p, "
                          "default) or one NCCL all-reduce per step")
+    ap.add_argument("--walls", action="store_true",
+                    help="probe, not the headline: absorbing walls + injection (the reference's default mode) "
+                         "instead of periodic particles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-arrays", action="store_true")
     args = ap.parse_args()
@@ -171,8 +174,9 @@ def main():
     from espic_hole_tracking_b200.simulation import SimConfig, Simulation
 
     n = int(args.particles)
-    cfg = SimConfig(n_steps=args.steps + args.warmup + 8, n_particles=n, n_cells=args.cells, periodic_particles=True,
-                    periodic_potential=False, extra_storage_factor=1.0, track_hole=False)
+    cfg = SimConfig(n_steps=2 * (args.steps + args.warmup) + 8, n_particles=n, n_cells=args.cells,
+                    periodic_particles=not args.walls, periodic_potential=False,
+                    extra_storage_factor=1.05 if args.walls else 1.0, track_hole=False)
     sim = Simulation(cfg, rank=rank, world_size=world, device=device, exchange=args.exchange)
     sim.init_synthetic()
     sim.initialize()
@@ -294,7 +298,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n:.3g} ions + {n:.3g} electrons per GPU, {args.cells}-cell periodic grid "
                                "(BASELINE configs[1]; N>1 = configs[2]-style weak scaling with the density all-reduce)",
-                   "particles_per_species_per_gpu": n, "cells": args.cells, "periodic": True,
+                   "particles_per_species_per_gpu": n, "cells": args.cells, "periodic": not args.walls,
                    "field_solve": "periodic particles, Robin-end potential (periodic_potential=False): the reference's "
                                   "periodic_potential branch is numerically broken on 4097 points (DESIGN.md s.8)",
                    "l2_policy": "inputs (1.6 GB of particle state per GPU) are larger than the 126 MB L2; no flush needed",

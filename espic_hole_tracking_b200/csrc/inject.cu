@@ -60,7 +60,11 @@ __global__ void k_uniforms(int n, float* __restrict__ out, unsigned long long se
     }
 }
 
-// One thread per velocity; same constants, window and acceptance test as the reference.
+// One thread per velocity; same side choice, window and acceptance rule as the reference
+// (ref infMagSim_c.c:576-578, 584, 608-614, 648-654).  The reference evaluates the acceptance
+// test log(u) <= log(|v|/|v_max|) + ((v_max+v_d)^2 - (v+v_d)^2)/(2 v_th^2) in double; the stream of
+// uniforms differs from the reference's anyway (see the header), so the test is evaluated in
+// float with the fast log: the accepted distribution changes by O(1e-6) relative.
 __global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restrict__ out,
                                   unsigned long long seed, unsigned long long call, int* status) {
     const float half_window = 5.f;
@@ -70,25 +74,27 @@ __global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restric
     const float ratio = (float)((gauss - b * (1. - erf(b))) / (gauss + b * (1. + erf(b))));
     const double vd = (double)v_d, vt = (double)v_th;
     const double disc = sqrt(pow(vd, 2.) + 4. * pow(vt, 2.));
-    const double two_vt2 = 2. * pow(vt, 2.);
+    const float inv_two_vt2 = (float)(1. / (2. * pow(vt, 2.)));
+    const float side_split = 1.f / (1.f + ratio);
+    // both walls' constants, computed once per thread
+    float mode[2], lo[2], width[2], mode_term[2], log_abs_mode[2];
+    mode[0] = (float)((-vd + disc) / 2.);   // enters at z_min moving right (ref :608-610)
+    lo[0] = (float)fmax((double)(mode[0] - half_window * v_th), 0.);
+    width[0] = (mode[0] + half_window * v_th) - lo[0];
+    mode[1] = (float)((-vd - disc) / 2.);   // enters at z_max moving left (ref :648-650)
+    lo[1] = mode[1] - half_window * v_th;
+    width[1] = (float)fmin((double)(mode[1] + half_window * v_th), 0.) - lo[1];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        mode_term[s] = (mode[s] + v_d) * (mode[s] + v_d);
+        log_abs_mode[s] = __logf(fabsf(mode[s]));
+    }
     Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t r[4];
         uint32_t block = 0;
         ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
-        const float side = u32_to_unit_float(r[0]) - 1.f / (1.f + ratio);
-        float mode, lo, hi;
-        if (side >= 0.f) {
-            mode = (float)((-vd + disc) / 2.);
-            hi = mode + half_window * v_th;
-            lo = (float)fmax((double)(mode - half_window * v_th), 0.);
-        } else {
-            mode = (float)((-vd - disc) / 2.);
-            hi = (float)fmin((double)(mode + half_window * v_th), 0.);
-            lo = mode - half_window * v_th;
-        }
-        const double mode_term = pow((double)(mode + v_d), 2.);
-        const double abs_mode = fabs((double)mode);
+        const int s = (u32_to_unit_float(r[0]) - side_split >= 0.f) ? 0 : 1;   // ref :584-585
         int next = 2;  // first trial uses r[2], r[3] of block 0; later blocks give two trials each
         float v = 0.f;
         for (int tries = 1;; ++tries) {
@@ -99,10 +105,10 @@ __global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restric
             const float u_v = u32_to_unit_float(r[next]);
             const float u_a = u32_to_unit_float(r[next + 1]);
             next += 2;
-            v = __fadd_rn(__fmul_rn(u_v, hi - lo), lo);  // ref :611-612 / :651-652
-            const double bound = log(fabs((double)v) / abs_mode) +
-                                 (mode_term - pow((double)(v + v_d), 2.)) / two_vt2;  // ref :614 / :654
-            if (log((double)u_a) <= bound) break;
+            v = __fadd_rn(__fmul_rn(u_v, width[s]), lo[s]);  // ref :611-612 / :651-652
+            const float vs = v + v_d;
+            const float bound = (__logf(fabsf(v)) - log_abs_mode[s]) + (mode_term[s] - vs * vs) * inv_two_vt2;
+            if (__logf(u_a) <= bound) break;                 // ref :614 / :654
             // ref :589-607: after 1000 rejections the reference prints a warning and keeps
             // looping; we raise a status bit, and give up after 1e6 so a NaN parameter cannot
             // hang the GPU
@@ -167,11 +173,39 @@ __device__ __forceinline__ void deposit_injected(const Geom& g, const Injected& 
     atomicAdd(acc + p.cell + 1, (unsigned long long)(kWeightOne - w0));
 }
 
-__global__ void k_inject_commit(const InjectArgs a) {
+// Injected particles land within |v|*dt of a wall, i.e. on a few hundred nodes: depositing them
+// with global atomics serialises on those addresses.  Each CTA accumulates into a shared-memory
+// copy of the two wall regions first (u32 fixed point, carry to the global accumulator when a
+// word would overflow) and flushes the touched nodes once.
+constexpr int kWallNodes = 2048;  // nodes kept per wall; anything farther in goes to global memory
+
+__device__ __forceinline__ void deposit_injected_tiled(const Geom& g, const Injected& p, unsigned* s_wall,
+                                                       unsigned long long* acc, int n_points) {
+    const unsigned w0 = left_share_fixed(g, p.x, p.cell);
+    const unsigned w[2] = {w0, kWeightOne - w0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int node = p.cell + k;
+        int local = -1;
+        if (node < kWallNodes) local = node;
+        else if (node >= n_points - kWallNodes) local = kWallNodes + (node - (n_points - kWallNodes));
+        if (local >= 0 && n_points >= 2 * kWallNodes) {
+            const unsigned old = atomicAdd(s_wall + local, w[k]);
+            if (old > ~w[k]) atomicAdd(acc + node, 1ull << 32);  // the word wrapped: credit 2^32 globally
+        } else {
+            atomicAdd(acc + node, (unsigned long long)w[k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
+    __shared__ unsigned s_wall[2 * kWallNodes];
     const Geom g = make_geom(a.grid, a.n_points);
     const int top0 = *a.top;
     const int n_bad = a.ws[0];
     if (n_bad == 0) {
+        for (int j = threadIdx.x; j < 2 * kWallNodes; j += blockDim.x) s_wall[j] = 0u;
+        __syncthreads();
         int my_max = -1;
         for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x) {
             const int sp = top0 - l;
@@ -185,12 +219,20 @@ __global__ void k_inject_commit(const InjectArgs a) {
             a.pv[slot] = p.v;
             a.px[slot] = p.x;
             my_max = max(my_max, slot);
-            deposit_injected(g, p, a.acc);
+            deposit_injected_tiled(g, p, s_wall, a.acc, a.n_points);
             a.empty_slots[sp] = -1;
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
         if ((threadIdx.x & 31) == 0 && my_max >= 0) atomicMax(a.largest, my_max);
+        __syncthreads();
+        for (int j = threadIdx.x; j < 2 * kWallNodes; j += blockDim.x) {
+            const unsigned v = s_wall[j];
+            if (v) {
+                const int node = (j < kWallNodes) ? j : (a.n_points - kWallNodes) + (j - kWallNodes);
+                atomicAdd(a.acc + node, (unsigned long long)v);
+            }
+        }
     } else if (blockIdx.x == 0 && threadIdx.x == 0) {
         // replay of the reference's sequential loop (only when a bad left_index occurred)
         int top = top0, last = *a.largest;

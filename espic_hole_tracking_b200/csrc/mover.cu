@@ -35,8 +35,8 @@
 
 namespace espic {
 
-constexpr int kMoveThreads = 256;
-constexpr int kMoveMinBlocks = 4;  // 64 registers per thread: four 8-warp CTAs per SM
+constexpr int kMoveThreads = 256;   // default CTA: four per SM (64 registers per thread)
+constexpr int kMoveMaxThreads = 1024;  // larger grids leave room for fewer tiles per SM: wider CTAs keep 32 warps/SM
 constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
 constexpr int kUnitSlots = 4 * kUnitQuads;    // 256 slots
 #ifndef ESPIC_PREFETCH_UNITS
@@ -356,7 +356,7 @@ struct Split {
 // chunk of the store, unaligned stores, start-up calls with update_position=0, an absorbing
 // object, exotic dz) goes quad by quad through quad_generic.
 template <bool PERIODIC, bool SMEM>
-__global__ void __launch_bounds__(kMoveThreads, kMoveMinBlocks) k_move(const MoveArgs a) {
+__global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_points = a.n_points;
     const int n_pad = (n_points + 3) & ~3;
@@ -589,24 +589,31 @@ static size_t move_smem_bytes(int n_points) {
 template <bool PERIODIC, bool SMEM>
 static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
     auto kern = k_move<PERIODIC, SMEM>;
-    // occupancy of this variant for this tile size, queried once (one device per process)
+    // CTA width and CTAs per SM for this tile size, chosen once (one device per process): as many
+    // 256-thread CTAs as the tile allows, else wider CTAs so that an SM still holds 32 warps
     static size_t cached_smem = (size_t)-1;
-    static int cached_per_sm = 0;
+    static int cached_per_sm = 0, cached_threads = kMoveThreads;
     if (cached_smem != smem) {
         if (smem > 48 * 1024)
             ESPIC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        ESPIC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMoveThreads, smem));
+        int threads = kMoveThreads, per_sm = 0;
+        for (;;) {
+            ESPIC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+            if (per_sm * threads >= 1024 || threads >= kMoveMaxThreads) break;
+            threads *= 2;
+        }
         if (per_sm < 1) return fail(ctx, ESPIC_E_ARG, "mover kernel does not fit on an SM (smem %zu)", smem);
+        if (per_sm * threads > 1024) per_sm = 1024 / threads;
         cached_smem = smem;
         cached_per_sm = per_sm;
+        cached_threads = threads;
     }
     const int grid = ctx->sm_count * cached_per_sm;
     ctx->mover_grid = grid;
-    ctx->mover_block = kMoveThreads;
+    ctx->mover_block = cached_threads;
     const bool timed = ctx->timing_on && ctx->ev_used + 2 <= ctx->ev_cap;
     if (timed) cudaEventRecord(ctx->ev[ctx->ev_used], ctx->stream);
-    kern<<<grid, kMoveThreads, smem, ctx->stream>>>(a);
+    kern<<<grid, cached_threads, smem, ctx->stream>>>(a);
     if (timed) {
         cudaEventRecord(ctx->ev[ctx->ev_used + 1], ctx->stream);
         ctx->ev_used += 2;
@@ -689,7 +696,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     f.top = top;
     f.scatter_hdr = (int*)ctx->chunk_counts.ptr;
     f.status = ctx->status;
-    const int mover_warps = ctx->mover_grid * (kMoveThreads / 32);
+    const int mover_warps = ctx->mover_grid * (ctx->mover_block / 32);
     if (mover_warps + 1 > max_ranges) return fail(ctx, ESPIC_E_ARG, "mover grid too large for the range table");
     f.n_ranges = mover_warps + 1;
     f.largest_allowed_slot = largest_allowed_slot;
