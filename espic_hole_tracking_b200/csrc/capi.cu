@@ -144,6 +144,7 @@ void espic_destroy(espic_ctx* ctx) {
     free_scratch(ctx->solve_ws);
     free_scratch(ctx->inject_ws);
     free_scratch(ctx->rng_ws);
+    free_scratch(ctx->sort_ws);
     free_scratch(ctx->host_stage);
     for (int r = 0; r < ctx->xch.world; ++r)
         if (r != ctx->xch.rank && ctx->xch.peer[r]) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
@@ -246,6 +247,16 @@ int espic_move_particles_dev(espic_ctx* ctx, const float* grid, const float* obj
 int espic_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out) {
     if (!ctx || !grid || !counts_out || n_points < 2) return ESPIC_E_ARG;
     return launch_selftest_quotient(ctx, grid, n_points, counts_out);
+}
+
+int espic_sort_particles(espic_ctx* ctx, const float* grid, int n_points, float* particles,
+                         int particle_storage_length, int* particles_hist, int* empty_slots, int n_stack,
+                         int* current_empty_slot, int* largest_index_dev, int largest_index, int periodic_particles) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !particles || !particles_hist || !empty_slots || !current_empty_slot || !largest_index_dev)
+        return fail(ctx, ESPIC_E_ARG, "espic_sort_particles: null pointer argument");
+    return launch_sort(ctx, grid, n_points, particles, particle_storage_length, particles_hist, empty_slots, n_stack,
+                       current_empty_slot, largest_index_dev, largest_index, periodic_particles);
 }
 
 int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storage_length, int largest_index,

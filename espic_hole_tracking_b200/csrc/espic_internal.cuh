@@ -155,6 +155,7 @@ struct espic_ctx {
     espic::Scratch solve_ws;            // fp64 rows of the field solve
     espic::Scratch inject_ws;
     espic::Scratch rng_ws;              // MT19937 state + stream buffers
+    espic::Scratch sort_ws;             // radix-sort ping-pong buffers and histograms
     espic::Scratch host_stage;          // device staging for the host-pointer entry points
     int* dev_int2 = nullptr;            // two device ints used by the host-pointer wrappers
 
@@ -202,6 +203,8 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage);
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);
+int launch_sort(espic_ctx* ctx, const float* grid, int n_points, float* particles, int storage, int* tags,
+                int* empty_slots, int n_stack, int* top, int* largest, int largest_index, int periodic);
 int launch_shift_velocities(espic_ctx* ctx, float* particles, int storage, int largest_index, double v_b);
 int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const float* charge,
                    float debye, float* potential, float obj_pot, float transparency, int boltzmann,

@@ -313,7 +313,8 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
     int grid_dim = (n_inject + 255) / 256;
     if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
     k_inject_classify<<<grid_dim, 256, 0, ctx->stream>>>(a);
-    k_inject_commit<<<grid_dim, 256, 0, ctx->stream>>>(a);
+    // one CTA per SM at most: every CTA zeroes and flushes its own 16 KB wall tile
+    k_inject_commit<<<grid_dim < ctx->sm_count ? grid_dim : ctx->sm_count, 256, 0, ctx->stream>>>(a);
     k_inject_finish<<<1, 1024, 0, ctx->stream>>>(a);
     ctx->launches += 3;
     return check_cuda(ctx, cudaGetLastError(), "inject launch");

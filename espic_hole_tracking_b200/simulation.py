@@ -403,6 +403,13 @@ class Simulation:
             ctx=self.ctx)[0]
         dd.all_reduce_histograms(self.hist.values(), self.world, self.pg)                        # :876,894,895
 
+    def sort_particles(self) -> None:
+        """Stable cell sort + compaction of both stores (K6).  Physically a no-op: slot numbers
+        change, particle state does not."""
+        for s in (self.ions, self.electrons):
+            ops.sort_particles_by_cell(self.grid, s.particles, s.tags, s.empty_slots, s.current_empty_slot,
+                                       s.largest_index, periodic_particles=self.cfg.periodic_particles, ctx=self.ctx)
+
     def run(self, n_steps: int) -> None:
         for _ in range(n_steps):
             self.step()

@@ -99,6 +99,18 @@ int espic_move_particles_dev(espic_ctx *ctx, const float *grid, const float *obj
                              int periodic_particles, int largest_allowed_slot, int n_points,
                              int particle_storage_length);
 
+/* K6 (no reference counterpart: the reference never reorders its store): stable sort of the
+ * live particles of slots 0..largest_index by cell index (the mover's (int)((x-z_min)/dz), after
+ * the periodic fold when periodic_particles), ties in slot order; dead slots are dropped, the
+ * survivors compacted to slots [0, n_live), x / v / injection tag moved together, everything
+ * behind parked, and the free-slot stack rebuilt as the driver builds it (ref
+ * infMagSim_script.py:486-489).  current_empty_slot and largest_index_dev (device ints) are
+ * rewritten.  The permutation equals a stable argsort of the keys bit for bit. */
+int espic_sort_particles(espic_ctx *ctx, const float *grid, int n_points, float *particles,
+                         int particle_storage_length, int *particles_hist, int *empty_slots,
+                         int n_stack, int *current_empty_slot, int *largest_index_dev,
+                         int largest_index, int periodic_particles);
+
 /* v[i] -= v_b for i <= largest_index: the tail of initialize_mover
  * (ref infMagSim_cython.py:174-176; the subtraction runs in double there). */
 int espic_shift_velocities(espic_ctx *ctx, float *particles, int particle_storage_length,
