@@ -424,3 +424,63 @@ def test_host_pointer_dropins(ops, cpu):
     cpu.poisson_solve(grid, mask, charge, 0.125, p_ref)
     L.poisson_solve_c(p(grid), p(mask), p(charge), 0.125, p(p_h), -4.0, 1.0, 0, 0, len(grid))
     assert np.abs(p_h - p_ref).max() <= REL * np.abs(p_ref).max()
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_edge_cases_empty_tiny_and_dead_stores(ops, cpu, periodic):
+    """Empty store (largest_index = -1), a single particle, a store of dead slots only, and a
+    ragged store whose live particles end in the middle of a quad."""
+    n_cells = 64
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid)
+    for n_live, storage, last in ((0, 8, -1), (1, 5, 0), (0, 16, 11), (7, 16, 9), (259, 300, 258)):
+        p = np.full((2, storage), 6.0, np.float32)
+        p[1] = 0.0
+        rng = np.random.default_rng(storage + n_live)
+        p[0, :n_live] = rng.uniform(-2.9, 2.9, n_live).astype(np.float32)
+        p[1, :n_live] = rng.standard_normal(n_live).astype(np.float32) * 40
+        stack = -np.ones(storage, np.int32)
+        free = np.arange(storage - 1, n_live - 1, -1, dtype=np.int32)
+        stack[:len(free)] = free
+        c_p, c_stack, c_top, d_ref = p.copy(), stack.copy(), [len(free) - 1], np.zeros_like(grid)
+        g_p, g_stack, g_top, g_den = dev(p), dev(stack), [len(free) - 1], torch.full((len(grid),), 3.0, device="cuda")
+        for _ in range(2):
+            cpu.move_particles(grid, mask, phi, 1e-3, -1836.0, 2.0, [last], c_p, d_ref, c_stack, c_top, a_b=0.0,
+                               periodic_particles=periodic)
+            ops.move_particles(dev(grid), dev(mask), dev(phi), 1e-3, -1836.0, 2.0, [last], g_p, g_den, g_stack, g_top, 0.0,
+                               periodic_particles=periodic)
+        assert g_top == c_top
+        assert_bits_equal(g_p.cpu().numpy(), c_p, f"particles n_live={n_live}")
+        assert_bits_equal(g_stack.cpu().numpy()[:g_top[0] + 1], c_stack[:c_top[0] + 1], "stack")
+        np.testing.assert_allclose(g_den.cpu().numpy(), d_ref, rtol=0, atol=1e-6 * max(d_ref.max(), 1e-30))
+    assert ops.default_context().status() == 0
+
+
+def test_status_word_reports_what_the_reference_prints(ops):
+    """Stack exhaustion on injection and stack overflow on removal only print in the reference
+    (and then index out of bounds); here they raise status bits and stay in bounds."""
+    grid = wl.make_grid(64)
+    ctx = ops.default_context()
+    ctx.status()
+    # injection with more particles than free slots
+    p = torch.full((2, 8), 6.0, device="cuda")
+    tags = torch.zeros((1, 8), dtype=torch.int32, device="cuda")
+    stack = torch.tensor([7, 6, -1, -1, -1, -1, -1, -1], dtype=torch.int32, device="cuda")
+    top, last = [1], [5]
+    den = torch.zeros(65, device="cuda")
+    vel = torch.tensor([1.0, -1.0, 2.0, 3.0], device="cuda")
+    uni = torch.full((4,), 0.5, device="cuda")
+    ops.inject_particles_given(4, dev(grid), 0.01, 1.0, vel, uni, 0.0, 1, tags, p, stack, top, last, den)
+    assert ctx.status() & 4          # ESPIC_ST_STACK_EMPTY
+    assert top == [-1] and last == [7]
+    assert abs(float(den.sum()) - 2.0) < 1e-5   # the two particles that found a slot were deposited
+    # removal of more particles than the stack can hold
+    p = dev(np.array([[9.0, 9.5, 10.0, 8.0], [0, 0, 0, 0]], np.float32) * 0 + np.array([[4.0], [0.0]], np.float32))
+    stack = torch.tensor([-1, -1], dtype=torch.int32, device="cuda")
+    top = [-1]
+    ops.move_particles(dev(grid), torch.zeros(65, device="cuda"), torch.zeros(65, device="cuda"), 1e-3, 1.0, 1.0, [3], p,
+                       den, stack, top, 0.0)
+    assert ctx.status() & 2          # ESPIC_ST_STACK_OVERFLOW
+    assert top == [3]                # the reference's counter also runs past the end
+    assert stack.cpu().tolist() == [0, 1]
