@@ -35,8 +35,8 @@
 
 namespace espic {
 
-constexpr int kMoveThreads = 256;   // default CTA: four per SM (64 registers per thread)
-constexpr int kMoveMaxThreads = 1024;  // larger grids leave room for fewer tiles per SM: wider CTAs keep 32 warps/SM
+constexpr int kMoveThreads = 1024;  // one 32-warp CTA per SM (64 registers per thread): one tile to zero and flush per SM
+constexpr int kMoveMaxThreads = 1024;
 constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
 constexpr int kUnitSlots = 4 * kUnitQuads;    // 256 slots
 #ifndef ESPIC_PREFETCH_UNITS
@@ -597,6 +597,10 @@ static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
         if (smem > 48 * 1024)
             ESPIC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int threads = kMoveThreads, per_sm = 0;
+        if (const char* e = getenv("ESPIC_MOVE_THREADS")) {  // tuning knob
+            const int t = atoi(e);
+            if (t == 256 || t == 512 || t == 1024) threads = t;
+        }
         for (;;) {
             ESPIC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
             if (per_sm * threads >= 1024 || threads >= kMoveMaxThreads) break;
