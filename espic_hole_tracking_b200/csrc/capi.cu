@@ -360,6 +360,31 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
                          a->n_points, s->particle_storage_length);
         if (rc) return rc;
     }
+    if (a->hole_position_out) {
+        if (!a->fine_mesh || !a->filter_scratch) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: tracking buffers missing");
+        rc = launch_hole_position(ctx, a->n_points, a->grid, a->potential, a->tracking_dz, a->tracking_width,
+                                  a->n_fine, a->fine_mesh, a->filter_scratch, a->hole_position_out);
+        if (rc) return rc;
+    }
+    const int n_inj[2] = {a->n_inject_ions, a->n_inject_electrons};
+    const float v_th[2] = {a->v_th_ions, a->v_th_electrons}, v_d[2] = {a->v_d_ions, a->v_d_electrons};
+    int* tags[2] = {a->ion_tags, a->electron_tags};
+    for (int i = 0; i < 2; ++i) {
+        if (n_inj[i] <= 0) continue;
+        if (!tags[i]) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: injection needs the tag array");
+        rc = ensure(ctx, ctx->rng_ws, (size_t)2 * ((n_inj[i] + 63) & ~63) * sizeof(float), "injection random inputs");
+        if (rc) return rc;
+        float* uni = (float*)ctx->rng_ws.ptr;
+        float* vel = uni + ((n_inj[i] + 63) & ~63);
+        // same draw order as the reference wrapper: fractions first, then velocities (ref infMagSim_cython.py:245-248)
+        if ((rc = rng_uniforms(ctx, n_inj[i], uni))) return rc;
+        if ((rc = rng_draw_velocities(ctx, n_inj[i], v_th[i], v_d[i], vel))) return rc;
+        const espic_species* s = sp[i];
+        rc = launch_inject(ctx, n_inj[i], a->grid, a->n_points, a->inject_dt, a->background_density, vel, uni, a->a_b,
+                           a->step_index, tags[i], s->particles, s->particle_storage_length, s->empty_slots,
+                           s->current_empty_slot, s->largest_index, s->density);
+        if (rc) return rc;
+    }
     return ESPIC_OK;
 }
 

@@ -301,6 +301,11 @@ class Simulation:
             a.debye_length, a.object_potential, a.object_transparency = c.debye_length, -3., 1.
             a.periodic_particles = int(c.periodic_particles)
             a.periodic_potential = int(self.periodic_potential)
+            a.ion_tags, a.electron_tags = self.ions.tags.data_ptr(), self.electrons.tags.data_ptr()
+            a.v_th_ions, a.v_th_electrons = self.v_th_i / math.sqrt(c.sigma), self.v_th_e
+            self._filter_scratch = torch.empty_like(self.fine_mesh)
+            a.fine_mesh, a.filter_scratch = self.fine_mesh.data_ptr(), self._filter_scratch.data_ptr()
+            a.n_fine, a.tracking_dz, a.tracking_width = self.fine_mesh.shape[0], self.dz, c.debye_length * 4.
             self._args = a
         return self._args
 
@@ -326,17 +331,29 @@ class Simulation:
             a.fix_electrons = 1
             a.ions.dt = self.dt if ions_mobile else 0.
             a.electrons.dt = 0. if k < c.time_steps_immobile_electrons else self.dt
+            track = c.track_hole and k > c.initial_transient_steps and k < self.hole_relative_positions.shape[0]
+            a.hole_position_out = self.hole_relative_positions[k:k + 1].data_ptr() if track else None   # :896-897
+            device_inject = (not periodic) and isinstance(self.sampler, DeviceUniformSampler) and ions_mobile
+            if device_inject:   # counts on the host (:965-975, 1005-1009), everything else in the same host call
+                a.n_inject_ions, a.n_inject_electrons = self.injection_counts(k)
+                a.v_d_ions, a.v_d_electrons = self.v_b - c.v_d_i, self.v_b
+                a.step_index, a.inject_dt = k, self.dt
+            else:
+                a.n_inject_ions = a.n_inject_electrons = 0
             self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
             self.ctx.check(self.ctx._lib.espic_pic_step(self.ctx.handle, a), "espic_pic_step")
+            done_tracking, done_inject = True, device_inject
         else:
             self._step_operator_by_operator(k, ions_mobile, ramp)
+            done_tracking = done_inject = False
         den_i, den_e = self._deposit_rows(k + 1)
         if not ions_mobile:
             den_i.fill_(1.0)   # :934 (every rank sets ones; the next all-reduce sums them, as in the reference)
-        if c.track_hole and k > c.initial_transient_steps and k < self.hole_relative_positions.shape[0]:  # :896-897
+        if (not done_tracking and c.track_hole and k > c.initial_transient_steps
+                and k < self.hole_relative_positions.shape[0]):                                   # :896-897
             ops.hole_position_tracking(self.potential, self.dz, c.debye_length * 4., self.grid, self.fine_mesh,
                                        out=self.hole_relative_positions[k:k + 1], ctx=self.ctx)
-        if not periodic:
+        if not periodic and not done_inject:
             n_i, n_e = self.injection_counts(k)
             if n_i > 0 and ions_mobile:                                                          # :986-1000
                 s = self.ions

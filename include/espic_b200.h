@@ -183,6 +183,23 @@ typedef struct {
     int exchange_step;
     float *reduced_ion_density;  /* only read when exchange_parity >= 0 */
     float *reduced_electron_density;
+    /* wall injection after the pushes (ref infMagSim_script.py:986-1019) with the device sampler:
+     * counts come from the host (expected flux + stochastic rounding, ref :965-975, 1005-1009) */
+    int n_inject_ions;
+    int n_inject_electrons;
+    float v_th_ions, v_d_ions;           /* sampler parameters, ref :997-1000 */
+    float v_th_electrons, v_d_electrons; /* ref :1016-1019 */
+    float inject_dt;                     /* the driver's dt (partial-step placement), independent of a frozen species */
+    int step_index;                      /* k: written into the injection tags */
+    int *ion_tags;                       /* int[storage] injection histories; may be NULL when nothing is injected */
+    int *electron_tags;
+    /* hole tracking after the solve (ref :896-897): position_out == NULL switches it off */
+    const float *fine_mesh;
+    float *filter_scratch;               /* n_fine floats */
+    float *hole_position_out;            /* one float */
+    int n_fine;
+    double tracking_dz;
+    float tracking_width;
 } espic_step_args;
 
 int espic_pic_step(espic_ctx *ctx, const espic_step_args *args);
