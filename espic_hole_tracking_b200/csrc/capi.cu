@@ -460,6 +460,33 @@ static void die(espic_ctx* ctx, const char* where, int rc) {
     abort();
 }
 
+// The reference's driver passes the same numpy arrays at every step.  Page-locking them once lets
+// the copies below run at PCIe speed instead of through the driver's pageable bounce buffers.
+// Registration failures (foreign allocators, read-only pages, ...) simply leave the range pageable.
+struct PinnedRange {
+    const void* ptr;
+    size_t bytes;
+};
+static PinnedRange g_pinned[32];
+static int g_n_pinned = 0;
+
+static void pin_host_range(const void* ptr, size_t bytes) {
+    if (!ptr || bytes < (8u << 20)) return;  // small arrays are not worth a registration
+    for (int i = 0; i < g_n_pinned; ++i)
+        if (g_pinned[i].ptr == ptr && g_pinned[i].bytes >= bytes) return;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("ESPIC_PIN_HOST");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || g_n_pinned >= 32) return;
+    if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+        g_pinned[g_n_pinned++] = PinnedRange{ptr, bytes};
+    } else {
+        cudaGetLastError();  // leave it pageable
+    }
+}
+
 static void report_status(espic_ctx* ctx) {
     int st = 0;
     if (espic_status(ctx, &st)) return;
@@ -498,6 +525,10 @@ void move_particles_c(float* grid, float* object_mask, float* potential, float d
     int* d_stack = cv.take<int>(n_stack);
     int* d_top = ctx->dev_int2;
     const size_t used = (size_t)(largest_index + 1);
+    if (used) {
+        pin_host_range(particles, used * sizeof(float));
+        pin_host_range(particles + S, used * sizeof(float));
+    }
     H2D(d_grid, grid, n, float);
     H2D(d_mask, object_mask, n, float);
     H2D(d_phi, potential, n, float);
@@ -505,7 +536,9 @@ void move_particles_c(float* grid, float* object_mask, float* potential, float d
         H2D(d_part, particles, used, float);
         H2D(d_part + S, particles + S, used, float);
     }
-    H2D(d_stack, empty_slots, n_stack, int);
+    // the mover only APPENDS to the stack (ref infMagSim_c.c:214-217): nothing to upload, and only
+    // the entries between the old and the new top come back
+    const int top_in = *current_empty_slot;
     H2D(d_top, current_empty_slot, 1, int);
     rc = espic_move_particles(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, largest_index,
                               d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles,
@@ -516,8 +549,14 @@ void move_particles_c(float* grid, float* object_mask, float* potential, float d
         D2H(particles + S, d_part + S, used, float);
     }
     D2H(density, d_den, n, float);
-    D2H(empty_slots, d_stack, n_stack, int);
     D2H(current_empty_slot, d_top, 1, int);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    {
+        const long long first = (long long)top_in + 1;
+        long long last = *current_empty_slot;
+        if (last > largest_allowed_slot) last = largest_allowed_slot;
+        if (first >= 0 && last >= first) D2H(empty_slots + first, d_stack + first, last - first + 1, int);
+    }
     if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
     report_status(ctx);
 }
