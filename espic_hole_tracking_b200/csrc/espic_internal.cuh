@@ -170,6 +170,7 @@ struct espic_ctx {
 
     // mover launch geometry
     int mover_grid = 0, mover_block = 0;
+    int mover_ranges = 0;  // ranges of the work split of the last mover launch (see Split)
 
     // per-launch timing of the mover kernel
     int timing_on = 0;

@@ -1,0 +1,311 @@
+// K1w: the mover for grids whose tables do not fit in shared memory (more than ~19k points, e.g.
+// the 65536-cell hole-tracking runs).  Same arithmetic as k_move (mover.cu), same results bit
+// for bit; what changes is where the grid tables live.
+//
+// The store is cut into segments of 32 consecutive ranges (one per warp of a CTA).  CTAs take
+// segments from a device counter.  For each segment the CTA
+//   1. samples 1024 positions of the segment, histograms their cells into 64 buckets and picks
+//      the circular window of kWinCells cells (start on a bucket boundary) that holds the most
+//      samples, centre-weighted;
+//   2. builds the window's tables in shared memory: kick per cell (copied from the global kick
+//      table k_build_dv made) and the two u32 planes of the fixed-point deposit;
+//   3. runs the fast slot update on its ranges.  A slot whose gather cell or deposit cell is
+//      outside the window is served per lane from global memory (kick table load, 64-bit
+//      reductions into ctx->acc) -- the warp keeps going, nothing is re-done;
+//   4. flushes the planes into ctx->acc.
+// The window is circular (cell index modulo n_cells, with the two end NODES kept apart), so a
+// segment of freshly injected particles -- half at each wall -- or a periodic segment straddling
+// the seam still fits one window.
+//
+// After espic_sort_particles() a segment's particles sit within a few hundred cells of each
+// other and drift apart by |v| dt per step; the window leaves ~9000 cells of margin either side,
+// so nearly all slots stay on the shared-memory path for many steps.  On an unsorted store about
+// kWinCells/n_cells of the slots do, the rest behave like the all-global kernel.  Because the
+// deposit accumulates integers the density does not depend on which path a slot took, nor on the
+// window, the segment schedule or the particle order.
+#include <cstdio>
+#include <cstdlib>
+
+#include "mover_common.cuh"
+
+namespace espic {
+
+constexpr int kWinCells = 18432;
+constexpr int kWinNodes = kWinCells + 2;  // both nodes of every cell, plus one when the window wraps past the seam
+constexpr int kWinBuckets = 64;
+constexpr int kWinThreads = 1024;
+
+// cell -> index into the window tables.  Cells at or above w_lo map to cell - w_lo; cells that
+// wrapped (below w_lo) map one further so that node n_cells (right end) and node 0 (left end)
+// stay distinct.  `inside` says whether the cell belongs to the window at all.
+struct WinMap {
+    int w_lo, n_cells;
+    __device__ __forceinline__ int operator()(int cell, bool& inside) const {
+        const int t = cell - w_lo;
+        const int m = t >> 31;
+        const int rel = t + (n_cells & m);
+        inside = (unsigned)rel < (unsigned)kWinCells;
+        return rel - m;
+    }
+    // table index -> grid node (inverse of the above for the left node of a cell)
+    __device__ __forceinline__ int node_of(int j) const {
+        const int seam = n_cells - w_lo;  // index of node n_cells when the window reaches it
+        return j <= seam ? w_lo + j : j - seam - 1;
+    }
+};
+
+struct KickWindow {
+    const float* s_dv;
+    const float* dv_global;
+    WinMap map;
+    __device__ __forceinline__ float operator()(int c) const {
+        bool inside;
+        const int j = map(c, inside);
+        if (inside) return s_dv[j];
+        return __ldg(dv_global + c);
+    }
+};
+
+// Deposit of the slots of a quad named by `dep`: window cells through the shared-memory planes,
+// the others straight into the global accumulators.
+__device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, const int* cell, unsigned dep,
+                                                 const WinMap& map, unsigned* s_lo, unsigned* s_hi,
+                                                 unsigned long long* acc) {
+    unsigned carries = 0, outside = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned w0, w1;
+        node_weights_fixed(g, x[c], cell[c], w0, w1);
+        bool inside;
+        const int j = map(cell[c], inside);
+        const bool on = (dep >> c) & 1u;
+        if (on && inside) {
+            const unsigned old0 = atomicAdd(s_lo + j, w0);
+            const unsigned old1 = atomicAdd(s_lo + j + 1, w1);
+            if (old0 > ~w0) carries |= 1u << (2 * c);
+            if (old1 > ~w1) carries |= 2u << (2 * c);
+        }
+        if (on && !inside) outside |= 1u << c;
+    }
+    if (__any_sync(0xffffffffu, (carries | outside) != 0u)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (carries & (3u << (2 * c))) {
+                bool inside;
+                const int j = map(cell[c], inside);
+                if (carries & (1u << (2 * c))) atomicAdd(s_hi + j, 1u);
+                if (carries & (2u << (2 * c))) atomicAdd(s_hi + j + 1, 1u);
+            }
+            if (outside & (1u << c)) {
+                unsigned w0, w1;
+                node_weights_fixed(g, x[c], cell[c], w0, w1);
+                atomicAdd(acc + cell[c], (unsigned long long)w0);
+                atomicAdd(acc + cell[c] + 1, (unsigned long long)w1);
+            }
+        }
+    }
+}
+
+template <bool PERIODIC>
+__device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
+                                                  const KickWindow& kick, unsigned* s_lo, unsigned* s_hi) {
+    int cell[4];
+    bool rare = false;
+    if (PERIODIC) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) push_fast_periodic(g, p.x[c], p.v[c], kick, a.dt, cell[c], rare);
+        if (__any_sync(0xffffffffu, rare))
+            return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
+        store_quad(a, q, p);
+        deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, s_hi, a.acc);
+        return 0u;
+    } else {
+        unsigned dep = 0, rem = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            bool removed;
+            const bool d = push_fast_walls(g, p.x[c], p.v[c], kick, a.dt, cell[c], removed, rare);
+            dep |= d ? (1u << c) : 0u;
+            rem |= removed ? (1u << c) : 0u;
+        }
+        if (__any_sync(0xffffffffu, rare))
+            return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
+        store_quad(a, q, p);
+        deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, s_hi, a.acc);
+        return rem;
+    }
+}
+
+template <bool PERIODIC>
+__global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_dv = reinterpret_cast<float*>(smem_raw);
+    unsigned* s_lo = reinterpret_cast<unsigned*>(s_dv + kWinNodes);
+    unsigned* s_hi = s_lo + kWinNodes;
+    __shared__ int s_bucket[kWinBuckets];
+    __shared__ int s_score[kWinBuckets];
+    __shared__ int s_seg, s_w_lo;
+
+    const int n_points = a.n_points, n_cells = n_points - 1;
+    const Geom g = make_geom(a.grid, n_points);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int n_ranges = a.n_segments * warps_per_cta;
+    const int n_slots = (a.largest_index_dev ? *a.largest_index_dev : a.largest_index) + 1;
+    const int n_quads = (n_slots + 3) >> 2;
+    const Split split(n_slots, n_ranges);
+    const bool has_obj = a.flags_global[0] != 0;
+    const bool fast = !has_obj && g.fast_div;  // uniform; the launcher has checked the rest
+    const int bucket_cells = (n_cells + kWinBuckets - 1) / kWinBuckets;
+    const int window_buckets = kWinCells / bucket_cells;
+
+    for (;;) {
+        if (tid == 0) s_seg = atomicAdd(a.seg_counter, 1);
+        if (tid < kWinBuckets) s_bucket[tid] = 0;
+        __syncthreads();
+        const int seg = s_seg;
+        if (seg >= a.n_segments) break;
+        const int r0 = seg * warps_per_cta;
+        const int seg_u0 = split.first_unit(r0), seg_u1 = split.first_unit(r0 + warps_per_cta);
+
+        // 1. where are this segment's particles?
+        const long long seg_slots = (long long)(seg_u1 - seg_u0) * kUnitSlots;
+        if (seg_slots == 0 && seg != a.n_segments - 1) {  // uniform: nothing here (a store much smaller than the grid)
+            if (lane == 0) a.counts[r0 + warp] = 0;
+            __syncthreads();
+            continue;
+        }
+        if (seg_slots > 0) {
+            const float x = __ldg(a.px + (size_t)seg_u0 * kUnitSlots + (size_t)((tid * seg_slots) / blockDim.x));
+            const bool live = PERIODIC ? (x < g.live_thr) : (x > g.lo_edge && x < g.hi_edge);
+            if (live) {
+                bool bad = false;
+                const int c = cell_of<PERIODIC, false>(g, PERIODIC ? fold_periodic(g, x) : x, bad);
+                atomicAdd(&s_bucket[c / bucket_cells], 1);
+            }
+        }
+        __syncthreads();
+        if (tid < kWinBuckets) {
+            int score = 0;
+            for (int i = 0; i < window_buckets; ++i)
+                score += s_bucket[(tid + i) & (kWinBuckets - 1)] * min(i + 1, window_buckets - i);
+            s_score[tid] = score;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = 0;
+            for (int b = 1; b < kWinBuckets; ++b)
+                if (s_score[b] > s_score[best]) best = b;
+            s_w_lo = best * bucket_cells;
+        }
+        __syncthreads();
+        const WinMap map{s_w_lo, n_cells};
+
+        // 2. the window's tables
+        for (int j = tid; j < kWinNodes; j += blockDim.x) {
+            const int node = map.node_of(j);
+            s_dv[j] = (node >= 0 && node < n_cells) ? __ldg(a.dv_global + node) : 0.f;
+            s_lo[j] = 0u;
+            s_hi[j] = 0u;
+        }
+        __syncthreads();
+
+        // 3. this warp's range
+        {
+            const KickWindow kick{s_dv, a.dv_global, map};
+            const int range = r0 + warp;
+            int removed = 0;
+            const int u0 = split.first_unit(range), u1 = u0 + split.unit_count(range);
+            int* stage_ids = a.staging + (size_t)u0 * kUnitSlots;
+            if (fast) {
+#pragma unroll 1
+                for (int u = u0; u < u1; ++u) {
+                    const int q0 = u * kUnitQuads + lane, q1 = q0 + 32;
+                    if (lane < 16 && u + a.prefetch_units < u1) {
+                        const float* row = (lane & 8) ? a.pv : a.px;
+                        const float* line = row + (size_t)(u + a.prefetch_units) * kUnitSlots + (lane & 7) * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+                    }
+                    Quad p0, p1;
+                    load_quad(a, q0, p0);
+                    load_quad(a, q1, p1);
+                    const unsigned rem0 = quad_fast_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, s_hi);
+                    const unsigned rem1 = quad_fast_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, s_hi);
+                    if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
+                        stage_removed(rem0, q0, lane, stage_ids, removed);
+                        stage_removed(rem1, q1, lane, stage_ids, removed);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int q = u0 * kUnitQuads + lane; q < u1 * kUnitQuads; q += 32) {
+                    const unsigned r = quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, has_obj, nullptr, nullptr);
+                    stage_removed(r, q, lane, stage_ids, removed);
+                }
+            }
+            if (lane == 0) {
+                a.counts[range] = removed;
+                if (removed) atomicAdd(a.total_removed, removed);
+            }
+            if (range == n_ranges - 1) {
+                // the slots behind the last complete unit: generic, bounds-checked, all global
+                int removed_tail = 0;
+                int* stage = a.staging + (size_t)split.n_units * kUnitSlots;
+#pragma unroll 1
+                for (int qb = split.n_units * kUnitQuads; qb < n_quads; qb += 32) {
+                    const int q = qb + lane;
+                    unsigned r = 0;
+                    if (q < n_quads)
+                        r = quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, has_obj, nullptr, nullptr);
+                    stage_removed(r, q, lane, stage, removed_tail);
+                }
+                if (lane == 0) {
+                    a.counts[n_ranges] = removed_tail;
+                    if (removed_tail) atomicAdd(a.total_removed, removed_tail);
+                }
+            }
+        }
+        __syncthreads();
+
+        // 4. flush
+        for (int j = tid; j < kWinNodes; j += blockDim.x) {
+            const unsigned lo = s_lo[j], hi = s_hi[j];
+            if (lo | hi) atomicAdd(a.acc + map.node_of(j), ((unsigned long long)hi << 32) | lo);
+        }
+        __syncthreads();
+    }
+}
+
+bool move_window_applicable(int n_points) { return n_points - 1 > kWinCells; }
+
+int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic) {
+    const size_t smem = (size_t)kWinNodes * 12;
+    static bool configured = false;
+    static int segs_per_cta = 4;
+    if (!configured) {
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_move_win<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_move_win<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (const char* e = getenv("ESPIC_WINDOW_SEGMENTS")) {  // tuning knob: segments per CTA
+            const int s = atoi(e);
+            if (s >= 1 && s <= 64) segs_per_cta = s;
+        }
+        configured = true;
+    }
+    a.n_segments = ctx->sm_count * segs_per_cta;
+    a.seg_counter = const_cast<int*>(a.flags_global) + 1;
+    ctx->mover_grid = ctx->sm_count;
+    ctx->mover_block = kWinThreads;
+    ctx->mover_ranges = a.n_segments * (kWinThreads / 32);
+    const bool timed = ctx->timing_on && ctx->ev_used + 2 <= ctx->ev_cap;
+    if (timed) cudaEventRecord(ctx->ev[ctx->ev_used], ctx->stream);
+    if (periodic) k_move_win<true><<<ctx->sm_count, kWinThreads, smem, ctx->stream>>>(a);
+    else k_move_win<false><<<ctx->sm_count, kWinThreads, smem, ctx->stream>>>(a);
+    if (timed) {
+        cudaEventRecord(ctx->ev[ctx->ev_used + 1], ctx->stream);
+        ctx->ev_used += 2;
+    }
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_move_win launch");
+}
+
+}  // namespace espic
