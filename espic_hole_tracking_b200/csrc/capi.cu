@@ -182,6 +182,11 @@ int espic_device_info(espic_ctx* ctx, int* sm_count, int* mover_grid, int* mover
     return ESPIC_OK;
 }
 
+int espic_mover_window_cells(espic_ctx* ctx, int n_points) {
+    if (!ctx || n_points < 2) return 0;
+    return move_window_cells(ctx, n_points);
+}
+
 long long espic_launch_count(espic_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 int espic_timing_enable(espic_ctx* ctx, int on) {
@@ -256,7 +261,18 @@ int espic_sort_particles(espic_ctx* ctx, const float* grid, int n_points, float*
     if (!grid || !particles || !particles_hist || !empty_slots || !current_empty_slot || !largest_index_dev)
         return fail(ctx, ESPIC_E_ARG, "espic_sort_particles: null pointer argument");
     return launch_sort(ctx, grid, n_points, particles, particle_storage_length, particles_hist, empty_slots, n_stack,
-                       current_empty_slot, largest_index_dev, largest_index, periodic_particles);
+                       current_empty_slot, largest_index_dev, largest_index, periodic_particles, 0);
+}
+
+int espic_sort_particles_coarse(espic_ctx* ctx, const float* grid, int n_points, float* particles,
+                                int particle_storage_length, int* particles_hist, int* empty_slots, int n_stack,
+                                int* current_empty_slot, int* largest_index_dev, int largest_index,
+                                int periodic_particles, int key_shift) {
+    if (!ctx) return ESPIC_E_ARG;
+    if (!grid || !particles || !empty_slots || !current_empty_slot || !largest_index_dev)
+        return fail(ctx, ESPIC_E_ARG, "espic_sort_particles_coarse: null pointer argument");
+    return launch_sort(ctx, grid, n_points, particles, particle_storage_length, particles_hist, empty_slots, n_stack,
+                       current_empty_slot, largest_index_dev, largest_index, periodic_particles, key_shift);
 }
 
 int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storage_length, int largest_index,

@@ -219,16 +219,18 @@ struct FinishArgs {
     int* flags_global;  // [0] object flag, [1] segment counter: reset for the next large-grid launch
 };
 
-// One CTA: fixed-point accumulators -> float density (and re-zero them); exclusive scan of the
-// per-chunk removal counts (skipped when the mover removed nothing); stack-top update.
+// Fixed-point accumulators -> float density (and re-zero them), by all CTAs; then CTA 0:
+// exclusive scan of the per-range removal counts (skipped when the mover removed nothing) and
+// stack-top update.
 __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
     __shared__ int s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int j = tid; j < a.n_points; j += blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + tid; j < a.n_points; j += gridDim.x * blockDim.x) {
         const unsigned long long v = a.acc[j];
         a.density[j] = (float)((double)v * a.inv_scale);
         a.acc[j] = 0ull;
     }
+    if (blockIdx.x != 0) return;  // large grids: the other CTAs only help with the conversion
     const int total = a.scatter_hdr[3];
     const int n_chunks = a.n_ranges;
     if (total != 0) {  // uniform
@@ -310,6 +312,13 @@ __global__ void k_shift_velocities(float* __restrict__ v, int n, double v_b) {
 
 static size_t move_smem_bytes(int n_points) {
     return (size_t)((n_points + 3) & ~3) * kSmemBytesPerPoint;
+}
+
+int move_window_cells(espic_ctx* ctx, int n_points) {
+    int max_smem = 0;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) != cudaSuccess) return 0;
+    if (move_smem_bytes(n_points) <= (size_t)max_smem) return 0;
+    return move_window_size(n_points);
 }
 
 template <bool PERIODIC, bool SMEM>
@@ -432,7 +441,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
         const char* e = getenv("ESPIC_WINDOW");  // 0: always the all-global kernel
         window_env = e ? atoi(e) : 1;
     }
-    if (!use_smem && window_env && a.vec_ok && update_position && move_window_applicable(n_points)) {
+    if (!use_smem && window_env && a.vec_ok && update_position && move_window_size(n_points) > 0) {
         rc = launch_move_window(ctx, a, periodic);
     } else if (periodic) {
         rc = use_smem ? launch_move_variant<true, true>(ctx, a, smem) : launch_move_variant<true, false>(ctx, a, 0);
@@ -455,7 +464,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     f.n_points = n_points;
     f.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
     f.flags_global = flags;
-    k_finish<<<1, 1024, 0, ctx->stream>>>(f);
+    k_finish<<<n_points <= 8192 ? 1 : (n_points + 4095) / 4096, 1024, 0, ctx->stream>>>(f);
     ctx->launches++;
     ESPIC_CUDA(ctx, cudaGetLastError());
     k_scatter<<<ctx->sm_count, 256, 0, ctx->stream>>>(a.staging, a.counts, f.scatter_hdr, empty_slots,

@@ -347,7 +347,7 @@ struct Split {
 };
 
 // mover_win.cu
-bool move_window_applicable(int n_points);
+int move_window_size(int n_points);  // window cells, 0 when the windowed kernel does not apply
 int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic);
 
 }  // namespace espic

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     }
 }
 
-bool move_window_applicable(int n_points) { return n_points - 1 > kWinCells; }
+int move_window_size(int n_points) { return n_points - 1 > kWinCells ? kWinCells : 0; }
 
 int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic) {
     const size_t smem = (size_t)kWinNodes * 12;

@@ -326,28 +326,38 @@ __device__ __forceinline__ void make_multipliers(const double* low, const double
     __syncthreads();
 }
 
+// The sweeps below are written without data-dependent control flow and unrolled by 8 so that the
+// plane loads of the next iterations are in flight while the recurrence of the current one runs:
+// with m = 65 rows per thread (65537 points) the solve is otherwise one exposed memory latency per
+// row per loop.  AT(p, i) is inside the plane for every i < m, so rows past n may be loaded; they
+// are masked out of the arithmetic and never stored.
+
 // in place: y[j] -= y[j-1]*fwd[j], j = 1..n-1
 __device__ __forceinline__ void forward_sweep(double* y, const double* fwd, int n, int m, Aff* s_aff,
                                               double* s_scalar) {
     const int t = threadIdx.x, j0 = t * m;
     Aff comp = aff_identity();
+#pragma unroll 8
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
-        if (j >= n || j == 0) continue;
-        comp = compose(Aff{-AT(fwd, i), AT(y, i)}, comp);
+        const double f = AT(fwd, i), yy = AT(y, i);
+        const Aff next = compose(Aff{-f, yy}, comp);
+        const bool on = (j < n) && (j != 0);
+        comp.A = on ? next.A : comp.A;
+        comp.B = on ? next.B : comp.B;
     }
     const Aff pre = block_exclusive_scan(comp, aff_identity(), s_aff);
     if (t == 0) s_scalar[0] = AT(y, 0);
     __syncthreads();
     double prev = pre.A * s_scalar[0] + pre.B;
+#pragma unroll 8
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
-        if (j >= n) break;
-        if (j == 0) {
-            prev = AT(y, 0);
-        } else {
-            prev = AT(y, i) - prev * AT(fwd, i);
-            AT(y, i) = prev;
+        const double f = AT(fwd, i), yy = AT(y, i);
+        const double r = (j == 0) ? yy : yy - prev * f;
+        if (j < n) {
+            prev = r;
+            AT(y, i) = r;
         }
     }
     __syncthreads();
@@ -358,10 +368,14 @@ __device__ __forceinline__ void backward_sweep(double* z, const double* bwd, int
                                                double* s_edge, double* s_scalar) {
     const int t = threadIdx.x, j0 = t * m;
     Aff comp = aff_identity();
+#pragma unroll 8
     for (int i = m - 1; i >= 0; --i) {
         const int j = j0 + i;
-        if (j >= n - 1) continue;  // row n-1 is the start value; rows past n do not exist
-        comp = compose(Aff{-AT(bwd, i), AT(z, i)}, comp);
+        const double b = AT(bwd, i), zz = AT(z, i);
+        const Aff next = compose(Aff{-b, zz}, comp);
+        const bool on = j < n - 1;  // row n-1 is the start value; rows past n do not exist
+        comp.A = on ? next.A : comp.A;
+        comp.B = on ? next.B : comp.B;
     }
     // reverse-order exclusive scan: hand the composite to the mirrored thread, scan, hand back
     Aff* s_rev = reinterpret_cast<Aff*>(s_edge);
@@ -380,14 +394,14 @@ __device__ __forceinline__ void backward_sweep(double* z, const double* bwd, int
     }
     __syncthreads();
     double next = pre.A * s_scalar[0] + pre.B;
+#pragma unroll 8
     for (int i = m - 1; i >= 0; --i) {
         const int j = j0 + i;
-        if (j > n - 1) continue;
-        if (j == n - 1) {
-            next = AT(z, i);
-        } else {
-            next = AT(z, i) - next * AT(bwd, i);
-            AT(z, i) = next;
+        const double b = AT(bwd, i), zz = AT(z, i);
+        const double r = (j == n - 1) ? zz : zz - next * b;
+        if (j <= n - 1) {
+            next = r;
+            AT(z, i) = r;
         }
     }
     __syncthreads();
@@ -552,9 +566,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     }
 
     // ---- solve: right-hand side, forward and backward sweeps (ref :350-353), output (ref :518-525)
+#pragma unroll 4
     for (int i = 0; i < m; ++i) {
-        const int j = tid * m + i;
-        if (j >= n) break;
+        const int j = min(tid * m + i, n - 1);  // rows past n: a copy of the last row, never used
         double r_low, r_dg, r_sup, r_rhs;
         build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
         AT(y, i) = r_rhs;
@@ -582,9 +596,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             if (j < n) a.potential[j] = (float)(AT(y, i) - mean);
         }
     } else {
+#pragma unroll 8
         for (int i = 0; i < m; ++i) {
             const int j = tid * m + i;
-            if (j < n) a.potential[j] = (float)(AT(y, i) * AT(inv, i));
+            const double r = AT(y, i) * AT(inv, i);
+            if (j < n) a.potential[j] = (float)r;
         }
     }
 }

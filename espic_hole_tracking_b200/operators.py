@@ -189,21 +189,25 @@ def initialize_mover(grid, object_mask, potential, dt, chage_to_mass, largest_in
 
 
 def sort_particles_by_cell(grid, particles, particles_hist, empty_slots, current_empty_slot_list,
-                           largest_index_list, periodic_particles=False, ctx=None):
+                           largest_index_list, periodic_particles=False, ctx=None, key_shift=0):
     """Stable cell sort + compaction of a particle store (K6, espic_sort_particles); in place.
-    No reference counterpart -- the reference never reorders its store; physically a no-op."""
+    No reference counterpart -- the reference never reorders its store; physically a no-op.
+    key_shift > 0 sorts by (cell >> key_shift) only (espic_sort_particles_coarse); particles_hist
+    may then be None."""
     dev = particles.device
     _check(particles, "particles", torch.float32, 2, None)
     _check(grid, "grid", torch.float32, 1, dev)
-    _check(particles_hist, "particles_hist", torch.int32, 2, dev)
+    if particles_hist is not None:
+        _check(particles_hist, "particles_hist", torch.int32, 2, dev)
     _check(empty_slots, "empty_slots", torch.int32, 1, dev)
     ctx = ctx or default_context(dev)
     _enter(ctx, dev)
     top = _Scalar(current_empty_slot_list, dev)
     last = _Scalar(largest_index_list, dev)
-    rc = ctx._lib.espic_sort_particles(ctx.handle, _ptr(grid), grid.shape[0], _ptr(particles), particles.shape[1],
-                                       _ptr(particles_hist), _ptr(empty_slots), empty_slots.shape[0], top.ptr,
-                                       last.ptr, int(largest_index_list[0]), int(bool(periodic_particles)))
+    rc = ctx._lib.espic_sort_particles_coarse(
+        ctx.handle, _ptr(grid), grid.shape[0], _ptr(particles), particles.shape[1],
+        _ptr(particles_hist) if particles_hist is not None else None, _ptr(empty_slots), empty_slots.shape[0],
+        top.ptr, last.ptr, int(largest_index_list[0]), int(bool(periodic_particles)), int(key_shift))
     ctx.check(rc, "sort_particles_by_cell")
     top.exit()
     last.exit()

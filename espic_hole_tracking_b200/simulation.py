@@ -74,6 +74,11 @@ class SimConfig:
     track_hole: bool = True
     phase_space_histograms: bool = False
     seed: int = 384
+    # Coarse cell sort of the stores (no reference counterpart; physically a no-op).  Steps between
+    # sorts per species: None = automatic (never when the whole grid fits the mover's shared-memory
+    # tables; otherwise often enough that thermal drift keeps a segment inside its window), 0 = never.
+    sort_interval_ions: int | None = None
+    sort_interval_electrons: int | None = None
 
     _KEYS = {"n_steps": int, "n_particles": int, "step_size": float, "v_d_i": float,
              "dimple_velocity": float, "dimple_height": float, "dimple_velocity_width": float,
@@ -191,6 +196,8 @@ class Simulation:
         self.periodic_potential = c.periodic_particles if c.periodic_potential is None else c.periodic_potential
         self.k = 0
         self.t = 0.0
+        self.sort_intervals = {"ions": 0, "electrons": 0}   # set by initialize() (_plan_sorting)
+        self.sort_key_shift = 0
         self.v_b = c.v_b_0     # box velocity (moving box disabled: constant), :730-736
         self.a_b = 0.0
         self.hist = {}
@@ -255,6 +262,29 @@ class Simulation:
                                  periodic_particles=c.periodic_particles, use_pure_c_version=True, ctx=self.ctx)
         if self.xch is not None:
             self.xch.publish(0, 0)
+        self._plan_sorting()
+        if self.sort_intervals["ions"] or self.sort_intervals["electrons"]:
+            self.sort_particles([n for n, k in self.sort_intervals.items() if k], key_shift=self.sort_key_shift)
+
+    def _plan_sorting(self) -> None:
+        """Sort intervals for the large-grid mover (csrc/mover_win.cu): a segment of a sorted store
+        spreads by v*dt per step; re-sort before 2.3 thermal speeds have used up the window's margin."""
+        c = self.cfg
+        window = self.ctx._lib.espic_mover_window_cells(self.ctx.handle, self.n_points)
+        self.sort_key_shift = 0
+        while (((self.n_points - 2) >> self.sort_key_shift) + 1) >= 512:   # one radix pass
+            self.sort_key_shift += 1
+        auto = {}
+        for name, v_th in (("ions", self.v_th_i / math.sqrt(c.sigma)), ("electrons", self.v_th_e)):
+            if window <= 0:
+                auto[name] = 0
+                continue
+            margin = 0.5 * window - (1 << self.sort_key_shift)
+            drift = max(v_th, abs(self.v_b)) * self.dt / self.dz          # cells per step at one thermal speed
+            auto[name] = int(min(1000, max(1, margin / (2.3 * drift))))
+        self.sort_intervals = {
+            "ions": auto["ions"] if c.sort_interval_ions is None else c.sort_interval_ions,
+            "electrons": auto["electrons"] if c.sort_interval_electrons is None else c.sort_interval_electrons}
 
     # ---- one timestep (infMagSim_script.py:756-1023) ---------------------------------------
     def reduce_densities(self) -> None:
@@ -370,6 +400,9 @@ class Simulation:
             self.xch.publish(k + 1, k + 1)
         self.t += self.dt
         self.k += 1
+        due = [n for n, every in self.sort_intervals.items() if every and self.k % every == 0]
+        if due:
+            self.sort_particles(due, key_shift=self.sort_key_shift)
 
     def _step_operator_by_operator(self, k: int, ions_mobile: bool, ramp: bool) -> None:
         """The same step through the individual operators, in the reference's order (used when the
@@ -420,12 +453,14 @@ class Simulation:
             ctx=self.ctx)[0]
         dd.all_reduce_histograms(self.hist.values(), self.world, self.pg)                        # :876,894,895
 
-    def sort_particles(self) -> None:
-        """Stable cell sort + compaction of both stores (K6).  Physically a no-op: slot numbers
-        change, particle state does not."""
-        for s in (self.ions, self.electrons):
+    def sort_particles(self, species=("ions", "electrons"), key_shift: int = 0) -> None:
+        """Stable cell sort + compaction of the named stores (K6).  Physically a no-op: slot numbers
+        change, particle state does not.  key_shift > 0 groups by blocks of 2**key_shift cells only."""
+        for name in species:
+            s = getattr(self, name)
             ops.sort_particles_by_cell(self.grid, s.particles, s.tags, s.empty_slots, s.current_empty_slot,
-                                       s.largest_index, periodic_particles=self.cfg.periodic_particles, ctx=self.ctx)
+                                       s.largest_index, periodic_particles=self.cfg.periodic_particles, ctx=self.ctx,
+                                       key_shift=key_shift)
 
     def run(self, n_steps: int) -> None:
         for _ in range(n_steps):

@@ -68,6 +68,10 @@ const char *espic_last_error(espic_ctx *ctx);
 int espic_status(espic_ctx *ctx, int *status_out);
 /* Multiprocessor count and the persistent grid the mover uses (for bench bookkeeping). */
 int espic_device_info(espic_ctx *ctx, int *sm_count, int *mover_grid, int *mover_block);
+/* Cells of the shared-memory window the mover keeps per segment of the store when the grid is
+ * too large for whole-grid tables (0 when the whole grid fits, i.e. up to ~19k points).  Drivers
+ * use it to decide how often to call espic_sort_particles_coarse. */
+int espic_mover_window_cells(espic_ctx *ctx, int n_points);
 /* Kernels launched on this context since creation (bench's gpu_launches). */
 long long espic_launch_count(espic_ctx *ctx);
 /* Per-launch CUDA-event timing of the mover kernel: enable, run, then read the mean launch
@@ -110,6 +114,16 @@ int espic_sort_particles(espic_ctx *ctx, const float *grid, int n_points, float 
                          int particle_storage_length, int *particles_hist, int *empty_slots,
                          int n_stack, int *current_empty_slot, int *largest_index_dev,
                          int largest_index, int periodic_particles);
+
+/* The same with the key coarsened to (cell index >> key_shift): particles end up grouped by
+ * blocks of 2^key_shift cells, in slot order inside a block.  That is all the large-grid mover
+ * needs (it keeps a window of the grid in shared memory per segment of the store) and it is one
+ * radix pass instead of two on a 65536-cell grid.  particles_hist may be NULL.  key_shift = 0 is
+ * espic_sort_particles. */
+int espic_sort_particles_coarse(espic_ctx *ctx, const float *grid, int n_points, float *particles,
+                                int particle_storage_length, int *particles_hist, int *empty_slots,
+                                int n_stack, int *current_empty_slot, int *largest_index_dev,
+                                int largest_index, int periodic_particles, int key_shift);
 
 /* v[i] -= v_b for i <= largest_index: the tail of initialize_mover
  * (ref infMagSim_cython.py:174-176; the subtraction runs in double there). */

@@ -16,8 +16,12 @@ def mover_ms(steps=1):
     r = sim.ctx.timing_read(); sim.ctx.timing_enable(False)
     return r["mean_ms"]
 print("periodic" if periodic else "walls", "mover ms/launch unsorted", round(mover_ms(3), 4), flush=True)
-torch.cuda.synchronize(); t0 = time.perf_counter(); sim.sort_particles(); torch.cuda.synchronize()
-print("sort both species ms", round((time.perf_counter() - t0) * 1e3, 2))
+shift = int(os.environ.get("PROBE_SHIFT", "0"))
+sim.sort_particles(key_shift=shift); torch.cuda.synchronize()
+for _ in range(2): sim.step()
+for name in ("ions", "electrons"):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); sim.sort_particles((name,), key_shift=shift); torch.cuda.synchronize()
+    print("sort", name, "key_shift", shift, "ms", round((time.perf_counter() - t0) * 1e3, 3))
 for k in range(int(os.environ.get("PROBE_STEPS", "24"))):
     print(f"step {k} after sort: mover ms/launch (mean of ions, electrons)", round(mover_ms(), 4), flush=True)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -173,6 +173,42 @@ def test_mover_large_grid_path(ops, cpu, periodic):
     check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, periodic)
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+def test_mover_window_on_sorted_store(ops, cpu, periodic):
+    """65537 grid points, store coarse-sorted first: the large-grid mover then serves nearly every
+    slot from its per-segment shared-memory window (mover_win.cu), the fast electrons that outrun
+    the window and -- periodic -- the segments straddling the seam included.  Same bars."""
+    n_cells = 65536
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid, amplitude=1.0)
+    n = 400_000
+    _, sp = wl.make_plasma(n, n_cells, seed=11, holes=0.01)
+    bg = wl.background_density(n, 1, n_cells)
+    g = to_dev(sp, torch)
+    top_g, last_g = list(sp.current_empty_slot), list(sp.largest_index)
+    ops.sort_particles_by_cell(dev(grid), g["particles"], g["tags"], g["empty_slots"], top_g, last_g,
+                               periodic_particles=periodic, key_shift=8)
+    c = sp.copy()   # the oracle starts from the sorted store
+    c.particles[:] = g["particles"].cpu().numpy()
+    c.empty_slots[:] = g["empty_slots"].cpu().numpy()
+    c.current_empty_slot[0], c.largest_index[0] = top_g[0], last_g[0]
+    n_live = last_g[0] + 1
+    assert np.all(np.diff((c.particles[0, :n_live] - grid[0]) // ((grid[-1] - grid[0]) / n_cells * 256)) >= 0)
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    dt = 4 * wl.timestep()   # fast electrons cover thousands of cells in the 4 steps
+    for _ in range(4):
+        cpu.move_particles(grid, mask, phi, dt, sp.charge_to_mass, bg, c.largest_index, c.particles,
+                           d_ref, c.empty_slots, c.current_empty_slot, a_b=0.0, periodic_particles=periodic)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), dt, sp.charge_to_mass, bg, last_g,
+                           g["particles"], g_den, g["empty_slots"], top_g, 0.0, periodic_particles=periodic)
+    assert top_g == c.current_empty_slot
+    assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+    assert_bits_equal(g["empty_slots"].cpu().numpy()[:top_g[0] + 1], c.empty_slots[:top_g[0] + 1], "stack")
+    check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n_live], bg, periodic)
+
+
 @pytest.mark.parametrize("n_cells", [500, 512, 1000, 4096, 65536])
 def test_fast_quotient_is_ieee_division_exhaustively(ops, n_cells):
     """The mover replaces the division in (x - z_min)/dz by a 3-operation sequence; this checks

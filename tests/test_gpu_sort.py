@@ -19,7 +19,7 @@ def ops():
     return pkg
 
 
-def reference_sort(grid, p, tags, n_slots, periodic):
+def reference_sort(grid, p, tags, n_slots, periodic, key_shift=0):
     """numpy statement of the sort: keys with the mover's float32 arithmetic, stable argsort."""
     z_lo, z_hi = np.float32(grid[0]), np.float32(grid[-1])
     dz = np.float32((z_hi - z_lo) / np.float32(len(grid) - 1))
@@ -33,7 +33,7 @@ def reference_sort(grid, p, tags, n_slots, periodic):
     if periodic:
         cell[cell > len(grid) - 2] = 0
     cell = np.clip(cell, 0, len(grid) - 2)
-    key = np.where(live, cell, len(grid) - 1)
+    key = np.where(live, cell >> key_shift, len(grid) - 1)
     order = np.argsort(key, kind="stable")
     n_live = int(live.sum())
     order = order[:n_live]
@@ -50,9 +50,10 @@ def reference_sort(grid, p, tags, n_slots, periodic):
     return out, out_tags, stack, n_live, key[order]
 
 
-@pytest.mark.parametrize("n_cells", [500, 4096, 65536])
+@pytest.mark.parametrize("n_cells,key_shift", [(500, 0), (4096, 0), (65536, 0), (65536, 8), (65536, 5), (4096, 3),
+                                               (500, 20)])
 @pytest.mark.parametrize("periodic", [False, True])
-def test_sort_is_stable_argsort(ops, n_cells, periodic):
+def test_sort_is_stable_argsort(ops, n_cells, key_shift, periodic):
     grid = wl.make_grid(n_cells)
     rng = np.random.default_rng(n_cells)
     n, S = 150_001, 180_004
@@ -62,12 +63,28 @@ def test_sort_is_stable_argsort(ops, n_cells, periodic):
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     g = dict(p=dev(sp.particles), tags=dev(sp.tags), stack=dev(sp.empty_slots))
     top, last = list(sp.current_empty_slot), list(sp.largest_index)
-    ops.sort_particles_by_cell(dev(grid), g["p"], g["tags"], g["stack"], top, last, periodic_particles=periodic)
-    want_p, want_tags, want_stack, n_live, keys = reference_sort(grid, sp.particles, sp.tags, n, periodic)
+    ops.sort_particles_by_cell(dev(grid), g["p"], g["tags"], g["stack"], top, last, periodic_particles=periodic,
+                               key_shift=key_shift)
+    want_p, want_tags, want_stack, n_live, keys = reference_sort(grid, sp.particles, sp.tags, n, periodic, key_shift)
     assert last == [n_live - 1] and top == [S - n_live - 1]
     assert np.all(np.diff(keys) >= 0)
     assert_bits_equal(g["p"].cpu().numpy(), want_p, "sorted particles")
     assert_bits_equal(g["tags"].cpu().numpy(), want_tags, "sorted tags")
+    assert_bits_equal(g["stack"].cpu().numpy(), want_stack, "rebuilt stack")
+
+
+def test_coarse_sort_without_tags(ops):
+    grid = wl.make_grid(65536)
+    rng = np.random.default_rng(5)
+    n, S = 70_000, 80_000
+    sp = wl.make_species(n, S, rng, 40.0, -1836.0, holes=0.1)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    g = dict(p=dev(sp.particles), stack=dev(sp.empty_slots))
+    top, last = list(sp.current_empty_slot), list(sp.largest_index)
+    ops.sort_particles_by_cell(dev(grid), g["p"], None, g["stack"], top, last, periodic_particles=True, key_shift=8)
+    want_p, _, want_stack, n_live, _ = reference_sort(grid, sp.particles, sp.tags, n, True, 8)
+    assert last == [n_live - 1] and top == [S - n_live - 1]
+    assert_bits_equal(g["p"].cpu().numpy(), want_p, "sorted particles")
     assert_bits_equal(g["stack"].cpu().numpy(), want_stack, "rebuilt stack")
 
 
