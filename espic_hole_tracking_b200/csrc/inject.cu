@@ -261,14 +261,14 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
 }
 
 __global__ void __launch_bounds__(1024) k_inject_finish(const InjectArgs a) {
-    for (int j = threadIdx.x; j < a.n_points; j += blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_points; j += gridDim.x * blockDim.x) {
         const unsigned long long v = a.acc[j];
         if (v) {
             a.density[j] = __fadd_rn(a.density[j], (float)((double)v * a.inv_scale));
             a.acc[j] = 0ull;
         }
     }
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         const int top0 = *a.top;
         if (a.ws[0] == 0) {
             const int n_ok = min(a.n_inject, top0 + 1);
@@ -315,7 +315,7 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
     k_inject_classify<<<grid_dim, 256, 0, ctx->stream>>>(a);
     // one CTA per SM at most: every CTA zeroes and flushes its own 16 KB wall tile
     k_inject_commit<<<grid_dim < ctx->sm_count ? grid_dim : ctx->sm_count, 256, 0, ctx->stream>>>(a);
-    k_inject_finish<<<1, 1024, 0, ctx->stream>>>(a);
+    k_inject_finish<<<n_points <= 8192 ? 1 : (n_points + 4095) / 4096, 1024, 0, ctx->stream>>>(a);
     ctx->launches += 3;
     return check_cuda(ctx, cudaGetLastError(), "inject launch");
 }
