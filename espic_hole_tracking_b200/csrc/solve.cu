@@ -1,4 +1,4 @@
-// K5: grid Poisson solve as one CTA.  Replaces poisson_solve_c + tridiagonal_solve_c
+// K5: grid Poisson solve as one thread-block cluster.  Replaces poisson_solve_c + tridiagonal_solve_c
 // (ref infMagSim_c.c:343-354, 356-541) and, fused in front of it, the density end-node fix /
 // charge density of the driver loop (ref infMagSim_script.py:763-779, 807).
 //
@@ -8,9 +8,15 @@
 //   D[j] = diag[j] - (sup[j-1]*sub[j-1])/D[j-1]        Moebius map  -> scan of 2x2 matrices
 //   y[j] = rhs[j]  - y[j-1]*(sub[j-1]/D[j-1])          affine map   -> scan of (A,B) pairs
 //   z[j] = y[j]    - z[j+1]*(sup[j]/D[j+1])            affine map, reversed
-// Each of the 1024 threads owns a contiguous run of m = ceil(n/1024) rows: it composes its run,
-// the block scans the 1024 composites, and the thread re-walks its run from the exact incoming
-// value.  Row j = t*m + i of thread t is stored at [i*1024 + t] (coalesced / conflict-free).
+// The kernel runs as a cluster of C <= 8 CTAs of 1024 threads acting as one team of Tn = C*1024
+// threads (C = 1 up to 1024 points, 8 from 3585 points on).  Each thread owns a contiguous run of
+// m = ceil(n/Tn) rows: it composes its run, the team scans the Tn composites (warp shuffles, then
+// the CTA's 32 warp totals, then the C CTA totals, which every CTA writes into every other CTA's
+// shared memory -- DSMEM -- ahead of one cluster barrier), and the thread re-walks its run from
+// the exact incoming value.  Row j = T*m + i of team thread T is stored at [i*Tn + T] (coalesced);
+// run-boundary neighbours are read from the neighbouring CTA's shared memory.  At 4097 points
+// m = 1 (rows live in registers / one shared-memory plane), at 65537 points m = 9 instead of the
+// 65 a single CTA would walk through one SM's L2 port.
 // The elimination (D and the multipliers sub/D, sup/D, 1/D) depends only on the matrix, which
 // is constant from step to step; it is kept in the context's workspace under a key the kernel
 // re-validates on the device at every call, so a driver step costs two affine scans.
@@ -20,13 +26,18 @@
 // Periodic variant: bug-compatible with the reference: the second solve
 // re-eliminates the already eliminated diagonal and v.w is taken as 0 (the reference reads
 // one element past its arrays there; with glibc the product underflows to +0.0).
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include <cstring>
 
 #include "espic_internal.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace espic {
 
 constexpr int kSolveThreads = 1024;
+constexpr int kSolveSmemRows = 16;  // the y plane lives in shared memory up to this many rows per thread (128 KB)
 
 struct Mat2 {
     double a, b, c, d;
@@ -148,8 +159,115 @@ struct SolveArgs {
     int n_pad;
 };
 
-// Transposed run storage: element i of thread t's run.
-#define AT(arr, i) (arr)[(size_t)(i) * kSolveThreads + threadIdx.x]
+constexpr int kMaxTeam = 8;  // portable cluster size
+
+// The CTAs of the cluster acting as one block of Tn threads.
+struct Team {
+    int rank, size;  // CTA rank in the cluster, CTAs in the cluster
+    int T, Tn;       // team thread index, team thread count
+};
+__device__ __forceinline__ Team make_team() {
+    cg::cluster_group c = cg::this_cluster();
+    Team tm;
+    tm.rank = (int)c.block_rank();
+    tm.size = (int)c.num_blocks();
+    tm.T = tm.rank * kSolveThreads + (int)threadIdx.x;
+    tm.Tn = tm.size * kSolveThreads;
+    return tm;
+}
+__device__ __forceinline__ void team_sync(const Team& tm) {
+    if (tm.size > 1) cg::this_cluster().sync();
+    else __syncthreads();
+}
+template <class T>
+__device__ __forceinline__ T* remote(T* p, int rank) {
+    return cg::this_cluster().map_shared_rank(p, rank);
+}
+
+// Transposed run storage: element i of a team thread's run, in a global plane (stride Tn) or in
+// this CTA's shared memory (stride 1024).
+struct Plane {
+    double* p;
+    int stride, idx;
+    __device__ __forceinline__ double& operator()(int i) const { return p[(size_t)i * stride + idx]; }
+};
+
+// Cluster-level exchange buffers (per CTA; every CTA holds a full copy, written by its peers).
+// Two parities: exchange k+2 reuses the buffers of exchange k, which every CTA has finished
+// reading before any CTA can pass the barrier of exchange k+1.
+struct TeamShared {
+    Mat2 mat_warp[32];
+    Aff aff_warp[32];
+    Mat2 mat_tot[2][kMaxTeam];
+    Aff aff_tot[2][kMaxTeam];
+    double bcast[2][2];
+    double sum[2][kMaxTeam];
+    double red[32];
+};
+__device__ __forceinline__ Mat2* warp_buf(TeamShared& sh, const Mat2&) { return sh.mat_warp; }
+__device__ __forceinline__ Aff* warp_buf(TeamShared& sh, const Aff&) { return sh.aff_warp; }
+__device__ __forceinline__ Mat2* tot_buf(TeamShared& sh, int par, const Mat2&) { return sh.mat_tot[par]; }
+__device__ __forceinline__ Aff* tot_buf(TeamShared& sh, int par, const Aff&) { return sh.aff_tot[par]; }
+
+// One value from one thread to every CTA of the team; visible after the next team exchange
+// (team_exclusive_scan / team_barrier_exchange) of the same phase.
+__device__ __forceinline__ void team_publish(const Team& tm, TeamShared& sh, int phase, int slot, double v) {
+    for (int r = 0; r < tm.size; ++r) remote(&sh.bcast[phase & 1][0], r)[slot] = v;
+}
+
+// Exclusive scan over the team in team-thread order (reverse: CTAs in descending rank order; the
+// caller mirrors the threads inside the CTA).  Advances `phase`.
+template <class T>
+__device__ __forceinline__ T team_exclusive_scan(const Team& tm, TeamShared& sh, T mine, T identity, int& phase,
+                                                 bool reverse) {
+    const T res = block_exclusive_scan(mine, identity, warp_buf(sh, mine));
+    const int par = phase & 1;
+    ++phase;
+    if (tm.size == 1) {
+        __syncthreads();  // publishes of this phase
+        return res;
+    }
+    if (threadIdx.x == kSolveThreads - 1) {
+        const T tot = compose(mine, res);
+        for (int r = 0; r < tm.size; ++r) remote(tot_buf(sh, par, mine), r)[tm.rank] = tot;
+    }
+    cg::this_cluster().sync();
+    T pre = identity;
+    const T* tot = tot_buf(sh, par, mine);
+    if (!reverse) {
+        for (int r = 0; r < tm.rank; ++r) pre = compose(tot[r], pre);
+    } else {
+        for (int r = tm.size - 1; r > tm.rank; --r) pre = compose(tot[r], pre);
+    }
+    return compose(res, pre);
+}
+
+// Sum over the team, CTAs added in rank order (deterministic).  Advances `phase`.
+__device__ __forceinline__ double team_sum(const Team& tm, TeamShared& sh, double v, int& phase) {
+    const double mine = block_sum(v, sh.red);
+    const int par = phase & 1;
+    ++phase;
+    if (tm.size == 1) return mine;
+    if (threadIdx.x == 0)
+        for (int r = 0; r < tm.size; ++r) remote(&sh.sum[par][0], r)[tm.rank] = mine;
+    cg::this_cluster().sync();
+    double tot = 0.;
+    for (int r = 0; r < tm.size; ++r) tot += sh.sum[par][r];
+    return tot;
+}
+
+// s_arr[t] as published by the previous / next team thread (run-boundary neighbours); the caller
+// has written s_arr and passed team_sync().
+__device__ __forceinline__ double prev_thread_value(const Team& tm, double* s_arr, double fallback) {
+    const int t = threadIdx.x;
+    if (t > 0) return s_arr[t - 1];
+    return tm.rank > 0 ? remote(s_arr, tm.rank - 1)[kSolveThreads - 1] : fallback;
+}
+__device__ __forceinline__ double next_thread_value(const Team& tm, double* s_arr, double fallback) {
+    const int t = threadIdx.x;
+    if (t + 1 < kSolveThreads) return s_arr[t + 1];
+    return tm.rank + 1 < tm.size ? remote(s_arr, tm.rank + 1)[0] : fallback;
+}
 
 constexpr int kHeaderDoubles = 16;
 constexpr unsigned long long kFactorMagic = 0x45535049434c5531ull;  // "ESPICLU1"
@@ -265,28 +383,28 @@ __device__ __forceinline__ void build_row(const SolveArgs& a, const RowConsts& k
 }
 
 // D[0] = dg[0]; D[j] = dg[j] - (sup[j-1]*low[j])/D[j-1].
-// Runs are m rows per thread: thread t owns rows t*m .. t*m+m-1 (clipped to n).
-__device__ __forceinline__ void eliminate_diagonal(const double* dg, const double* low, const double* sup,
-                                                   double* D, int n, int m, Mat2* s_mat, double* s_edge,
-                                                   double* s_scalar) {
+// Runs are m rows per team thread: thread T owns rows T*m .. T*m+m-1 (clipped to n).
+__device__ __forceinline__ void eliminate_diagonal(const Team& tm, TeamShared& sh, int& phase, const Plane& dg,
+                                                   const Plane& low, const Plane& sup, const Plane& D, int n, int m,
+                                                   double* s_edge) {
     const int t = threadIdx.x;
-    const int j0 = t * m;
+    const int j0 = tm.T * m;
     // sup[j0-1] lives in the previous thread's run: publish each run's last sup
-    s_edge[t] = (j0 + m - 1 < n) ? AT(sup, m - 1) : 0.;
-    __syncthreads();
-    const double sup_before = (t > 0) ? s_edge[t - 1] : 0.;
+    s_edge[t] = (j0 + m - 1 < n) ? sup(m - 1) : 0.;
+    team_sync(tm);
+    const double sup_before = prev_thread_value(tm, s_edge, 0.);
     Mat2 comp = mat_identity();
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
         if (j >= n || j == 0) continue;
-        const double sp = (i == 0) ? sup_before : AT(sup, i - 1);
-        comp = compose(Mat2{AT(dg, i), -(sp * AT(low, i)), 1., 0.}, comp);
+        const double sp = (i == 0) ? sup_before : sup(i - 1);
+        comp = compose(Mat2{dg(i), -(sp * low(i)), 1., 0.}, comp);
     }
-    const Mat2 pre = block_exclusive_scan(comp, mat_identity(), s_mat);
-    // value entering this run: D[j0-1] = pre applied to D[0] = dg[0] (thread 0's first element)
-    if (t == 0) s_scalar[0] = AT(dg, 0);
-    __syncthreads();
-    const double d0 = s_scalar[0];
+    // value entering the first run: D[0] = dg[0]
+    if (tm.T == 0) team_publish(tm, sh, phase, 0, dg(0));
+    const int par = phase & 1;
+    const Mat2 pre = team_exclusive_scan(tm, sh, comp, mat_identity(), phase, false);
+    const double d0 = sh.bcast[par][0];
     double d = (pre.a * d0 + pre.b) / (pre.c * d0 + pre.d);
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
@@ -294,84 +412,83 @@ __device__ __forceinline__ void eliminate_diagonal(const double* dg, const doubl
         if (j == 0) {
             d = d0;
         } else {
-            const double sp = (i == 0) ? sup_before : AT(sup, i - 1);
-            d = AT(dg, i) - sp * AT(low, i) / d;
+            const double sp = (i == 0) ? sup_before : sup(i - 1);
+            d = dg(i) - sp * low(i) / d;
         }
-        AT(D, i) = d;
+        D(i) = d;
     }
-    __syncthreads();
+    team_sync(tm);
 }
 
 // Multiplier planes of one Thomas factorisation: fwd[j] = low[j]/D[j-1] (j>=1),
 // bwd[j] = sup[j]/D[j+1] (j<=n-2), inv[j] = 1/D[j].
-__device__ __forceinline__ void make_multipliers(const double* low, const double* sup, const double* D,
-                                                 double* fwd, double* bwd, double* inv, int n, int m,
+__device__ __forceinline__ void make_multipliers(const Team& tm, const Plane& low, const Plane& sup, const Plane& D,
+                                                 const Plane& fwd, const Plane& bwd, const Plane& inv, int n, int m,
                                                  double* s_edge) {
-    const int t = threadIdx.x, j0 = t * m;
+    const int t = threadIdx.x, j0 = tm.T * m;
     // neighbours across run boundaries: last D of the previous run, first D of the next run
-    s_edge[t] = (j0 + m - 1 < n) ? AT(D, m - 1) : 1.;
-    s_edge[kSolveThreads + t] = (j0 < n) ? AT(D, 0) : 1.;
-    __syncthreads();
-    const double D_before = (t > 0) ? s_edge[t - 1] : 1.;
-    const double D_after = (t + 1 < kSolveThreads) ? s_edge[kSolveThreads + t + 1] : 1.;
+    s_edge[t] = (j0 + m - 1 < n) ? D(m - 1) : 1.;
+    s_edge[kSolveThreads + t] = (j0 < n) ? D(0) : 1.;
+    team_sync(tm);
+    const double D_before = prev_thread_value(tm, s_edge, 1.);
+    const double D_after = next_thread_value(tm, s_edge + kSolveThreads, 1.);
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
         if (j >= n) break;
-        const double Dp = (i == 0) ? D_before : AT(D, i - 1);
-        const double Dn = (i == m - 1) ? D_after : AT(D, i + 1);
-        AT(fwd, i) = (j >= 1) ? AT(low, i) / Dp : 0.;
-        AT(bwd, i) = (j <= n - 2) ? AT(sup, i) / Dn : 0.;
-        AT(inv, i) = 1. / AT(D, i);
+        const double Dp = (i == 0) ? D_before : D(i - 1);
+        const double Dn = (i == m - 1) ? D_after : D(i + 1);
+        fwd(i) = (j >= 1) ? low(i) / Dp : 0.;
+        bwd(i) = (j <= n - 2) ? sup(i) / Dn : 0.;
+        inv(i) = 1. / D(i);
     }
-    __syncthreads();
+    team_sync(tm);
 }
 
 // The sweeps below are written without data-dependent control flow and unrolled by 8 so that the
-// plane loads of the next iterations are in flight while the recurrence of the current one runs:
-// with m = 65 rows per thread (65537 points) the solve is otherwise one exposed memory latency per
-// row per loop.  AT(p, i) is inside the plane for every i < m, so rows past n may be loaded; they
-// are masked out of the arithmetic and never stored.
+// plane loads of the next iterations are in flight while the recurrence of the current one runs.
+// Plane element i < m exists for every thread, so rows past n may be loaded; they are masked
+// out of the arithmetic and never stored.
 
 // in place: y[j] -= y[j-1]*fwd[j], j = 1..n-1
-__device__ __forceinline__ void forward_sweep(double* y, const double* fwd, int n, int m, Aff* s_aff,
-                                              double* s_scalar) {
-    const int t = threadIdx.x, j0 = t * m;
+__device__ __forceinline__ void forward_sweep(const Team& tm, TeamShared& sh, int& phase, const Plane& y,
+                                              const Plane& fwd, int n, int m) {
+    const int j0 = tm.T * m;
     Aff comp = aff_identity();
 #pragma unroll 8
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
-        const double f = AT(fwd, i), yy = AT(y, i);
+        const double f = fwd(i), yy = y(i);
         const Aff next = compose(Aff{-f, yy}, comp);
         const bool on = (j < n) && (j != 0);
         comp.A = on ? next.A : comp.A;
         comp.B = on ? next.B : comp.B;
     }
-    const Aff pre = block_exclusive_scan(comp, aff_identity(), s_aff);
-    if (t == 0) s_scalar[0] = AT(y, 0);
-    __syncthreads();
-    double prev = pre.A * s_scalar[0] + pre.B;
+    if (tm.T == 0) team_publish(tm, sh, phase, 0, y(0));
+    const int par = phase & 1;
+    const Aff pre = team_exclusive_scan(tm, sh, comp, aff_identity(), phase, false);
+    double prev = pre.A * sh.bcast[par][0] + pre.B;
 #pragma unroll 8
     for (int i = 0; i < m; ++i) {
         const int j = j0 + i;
-        const double f = AT(fwd, i), yy = AT(y, i);
+        const double f = fwd(i), yy = y(i);
         const double r = (j == 0) ? yy : yy - prev * f;
         if (j < n) {
             prev = r;
-            AT(y, i) = r;
+            y(i) = r;
         }
     }
     __syncthreads();
 }
 
-// in place: z[j] -= z[j+1]*bwd[j], j = n-2..0.  The scan runs in REVERSE thread order.
-__device__ __forceinline__ void backward_sweep(double* z, const double* bwd, int n, int m, Aff* s_aff,
-                                               double* s_edge, double* s_scalar) {
-    const int t = threadIdx.x, j0 = t * m;
+// in place: z[j] -= z[j+1]*bwd[j], j = n-2..0.  The scan runs in REVERSE team-thread order.
+__device__ __forceinline__ void backward_sweep(const Team& tm, TeamShared& sh, int& phase, const Plane& z,
+                                               const Plane& bwd, int n, int m, double* s_edge) {
+    const int t = threadIdx.x, j0 = tm.T * m;
     Aff comp = aff_identity();
 #pragma unroll 8
     for (int i = m - 1; i >= 0; --i) {
         const int j = j0 + i;
-        const double b = AT(bwd, i), zz = AT(z, i);
+        const double b = bwd(i), zz = z(i);
         const Aff next = compose(Aff{-b, zz}, comp);
         const bool on = j < n - 1;  // row n-1 is the start value; rows past n do not exist
         comp.A = on ? next.A : comp.A;
@@ -384,30 +501,30 @@ __device__ __forceinline__ void backward_sweep(double* z, const double* bwd, int
     __syncthreads();
     const Aff mine_rev = s_rev[t];
     __syncthreads();
-    const Aff pre_rev = block_exclusive_scan(mine_rev, aff_identity(), s_aff);
+    {
+        const int Tl = (n - 1) / m, il = (n - 1) - Tl * m;  // owner of row n-1
+        if (tm.T == Tl) team_publish(tm, sh, phase, 0, z(il));
+    }
+    const int par = phase & 1;
+    const Aff pre_rev = team_exclusive_scan(tm, sh, mine_rev, aff_identity(), phase, true);
     s_rev[kSolveThreads - 1 - t] = pre_rev;
     __syncthreads();
     const Aff pre = s_rev[t];
-    {
-        const int tl = (n - 1) / m, il = (n - 1) - tl * m;  // owner of row n-1
-        if (t == tl) s_scalar[0] = AT(z, il);
-    }
-    __syncthreads();
-    double next = pre.A * s_scalar[0] + pre.B;
+    double next = pre.A * sh.bcast[par][0] + pre.B;
 #pragma unroll 8
     for (int i = m - 1; i >= 0; --i) {
         const int j = j0 + i;
-        const double b = AT(bwd, i), zz = AT(z, i);
+        const double b = bwd(i), zz = z(i);
         const double r = (j == n - 1) ? zz : zz - next * b;
         if (j <= n - 1) {
             next = r;
-            AT(z, i) = r;
+            z(i) = r;
         }
     }
     __syncthreads();
 }
 
-// Workspace (doubles): [header 16] then planes of m*1024: low, dg, sup, D, D2 (scratch of the
+// Workspace (doubles): [header 16] then planes of m*Tn: low, dg, sup, D, D2 (scratch of the
 // factorisation), fwd, bwd, inv, wq (the factorisation itself, kept between calls) and y.
 // The factorisation depends only on (grid ends, n, debye_length, periodic) while the object
 // rows are blended out (object_transparency == 1) and the electrons are not Boltzmann -- every
@@ -415,27 +532,23 @@ __device__ __forceinline__ void backward_sweep(double* z, const double* bwd, int
 // key in the header, and later calls go straight to the two sweeps.  Both routes end in the
 // same sweeps over the same planes, so a cached and an uncached call return identical bits.
 __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];  // y plane when it fits (m <= 5)
-    __shared__ Mat2 s_mat[32];
-    __shared__ Aff s_aff[32];
-    __shared__ double s_red[32];
-    __shared__ double s_scalar[2];
+    extern __shared__ __align__(16) unsigned char smem_raw[];  // y plane when it fits (m <= kSolveSmemRows)
+    __shared__ TeamShared sh;
     __shared__ __align__(16) double s_edge[2 * kSolveThreads];  // run-boundary values; reused as Aff[1024]
     __shared__ int s_cached;
+    __shared__ float s_end[4];
+    const Team tm = make_team();
+    int phase = 0;
     const int n = a.n, tid = threadIdx.x;
-    const int m = (n + kSolveThreads - 1) / kSolveThreads;
-    const size_t plane = (size_t)m * kSolveThreads;
+    const int m = (n + tm.Tn - 1) / tm.Tn;
+    const size_t plane = (size_t)m * tm.Tn;
     double* hdr = a.ws;
-    double* low = a.ws + kHeaderDoubles;
-    double* dg = low + plane;
-    double* sup = dg + plane;
-    double* D = sup + plane;
-    double* D2 = D + plane;
-    double* fwd = D2 + plane;
-    double* bwd = fwd + plane;
-    double* inv = bwd + plane;
-    double* wq = inv + plane;
-    double* y = (m <= 5) ? reinterpret_cast<double*>(smem_raw) : wq + plane;
+    double* base = a.ws + kHeaderDoubles;
+    const Plane low{base, tm.Tn, tm.T}, dg{base + plane, tm.Tn, tm.T}, sup{base + 2 * plane, tm.Tn, tm.T},
+        D{base + 3 * plane, tm.Tn, tm.T}, D2{base + 4 * plane, tm.Tn, tm.T}, fwd{base + 5 * plane, tm.Tn, tm.T},
+        bwd{base + 6 * plane, tm.Tn, tm.T}, inv{base + 7 * plane, tm.Tn, tm.T}, wq{base + 8 * plane, tm.Tn, tm.T};
+    const Plane y = (m <= kSolveSmemRows) ? Plane{reinterpret_cast<double*>(smem_raw), kSolveThreads, tid}
+                                          : Plane{base + 9 * plane, tm.Tn, tm.T};
 
     // ---- multi-GPU: the all-reduce of the two density grids (ref infMagSim_script.py:763, 773),
     // done by every rank for itself over NVLink peer memory.  Ranks are summed in rank order,
@@ -457,7 +570,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             }
         }
         __syncthreads();
-        for (int j = tid; j < n; j += blockDim.x) {
+        for (int j = tm.T; j < n; j += tm.Tn) {
             float si = 0.f, se = 0.f;
             for (int r = 0; r < a.world; ++r) {
                 const float* slot = a.peer_slot[r];
@@ -467,14 +580,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             a.ion[j] = si;
             a.ele[j] = se;
         }
-        __syncthreads();
+        __threadfence();
+        team_sync(tm);
     }
 
     // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
     const float* charge = a.charge;
     if (a.ion) {
-        __shared__ float s_end[4];
-        if (tid == 0) {
+        if (tid == 0) {  // every CTA works the fixed end values out for itself; CTA 0 stores them
             float i0 = a.ion[0], i1 = a.ion[n - 1], e0 = a.ele[0], e1 = a.ele[n - 1];
             if (a.fold_ends) {
                 if (a.fix_i) { i0 = __fadd_rn(i0, i1); i1 = i0; }
@@ -484,15 +597,18 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
                 if (a.fix_e) { e0 = __fmul_rn(e0, 2.f); e1 = __fmul_rn(e1, 2.f); }
             }
             s_end[0] = i0; s_end[1] = i1; s_end[2] = e0; s_end[3] = e1;
-            a.ion[0] = i0; a.ion[n - 1] = i1; a.ele[0] = e0; a.ele[n - 1] = e1;
         }
-        __syncthreads();
-        for (int j = tid; j < n; j += blockDim.x) {
+        team_sync(tm);  // every CTA has read the raw end values
+        if (tm.T == 0) {
+            a.ion[0] = s_end[0]; a.ion[n - 1] = s_end[1]; a.ele[0] = s_end[2]; a.ele[n - 1] = s_end[3];
+        }
+        for (int j = tm.T; j < n; j += tm.Tn) {
             const float x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : a.ion[j];
             const float yv = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
             a.charge_out[j] = __fsub_rn(x, yv);
         }
         charge = a.charge_out;
+        __threadfence();
     }
 
     const RowConsts k = row_consts(a);
@@ -501,66 +617,63 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hdr);
         s_cached = cacheable && h[0] == kFactorMagic && hdr[1] == (double)__ldg(a.grid) &&
                    hdr[2] == (double)__ldg(a.grid + n - 1) && hdr[3] == (double)a.debye && hdr[4] == (double)n &&
-                   hdr[5] == (double)a.periodic;
+                   hdr[5] == (double)a.periodic && hdr[6] == (double)tm.size;
     }
-    __syncthreads();  // also orders the prologue's charge_out writes before the reads below
+    team_sync(tm);  // also orders the prologue's charge_out writes before the reads below
     int bad_mask = 0;
 
     if (!s_cached) {
         // ---- factorisation: rows (ref :385-503), eliminated diagonal (ref :343-349), multipliers
         for (int i = 0; i < m; ++i) {
-            const int j = tid * m + i;
+            const int j = tm.T * m + i;
             if (j >= n) break;
             double r_low, r_dg, r_sup, r_rhs;
             build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
-            AT(low, i) = r_low;
-            AT(dg, i) = r_dg;
-            AT(sup, i) = r_sup;
+            low(i) = r_low;
+            dg(i) = r_dg;
+            sup(i) = r_sup;
         }
         __syncthreads();
-        eliminate_diagonal(dg, low, sup, D, n, m, s_mat, s_edge, s_scalar);
-        make_multipliers(low, sup, D, fwd, bwd, inv, n, m, s_edge);
+        eliminate_diagonal(tm, sh, phase, dg, low, sup, D, n, m, s_edge);
+        make_multipliers(tm, low, sup, D, fwd, bwd, inv, n, m, s_edge);
         if (a.periodic) {  // ref :504-507: the second solve re-eliminates the eliminated diagonal (quirk 1)
-            eliminate_diagonal(D, low, sup, D2, n, m, s_mat, s_edge, s_scalar);
+            eliminate_diagonal(tm, sh, phase, D, low, sup, D2, n, m, s_edge);
             // w = "solve" of u = e_{n-1} on that matrix: the forward sweep leaves u unchanged, the
             // backward sweep and the final division act.  dg / low are free now: scratch for them.
-            double* bwd2 = dg;
-            double* wz = low;
+            const Plane bwd2 = dg, wz = low;
             {
-                const int t = tid, j0 = t * m;
-                s_edge[kSolveThreads + t] = (j0 < n) ? AT(D2, 0) : 1.;
-                __syncthreads();
-                const double D_after = (t + 1 < kSolveThreads) ? s_edge[kSolveThreads + t + 1] : 1.;
-                double supv[1];
-                (void)supv;
+                const int j0 = tm.T * m;
+                s_edge[kSolveThreads + tid] = (j0 < n) ? D2(0) : 1.;
+                team_sync(tm);
+                const double D_after = next_thread_value(tm, s_edge + kSolveThreads, 1.);
                 for (int i = 0; i < m; ++i) {
                     const int j = j0 + i;
                     if (j >= n) break;
-                    const double Dn = (i == m - 1) ? D_after : AT(D2, i + 1);
-                    const double sp = AT(sup, i);
-                    AT(bwd2, i) = (j <= n - 2) ? sp / Dn : 0.;
+                    const double Dn = (i == m - 1) ? D_after : D2(i + 1);
+                    const double sp = sup(i);
+                    bwd2(i) = (j <= n - 2) ? sp / Dn : 0.;
                 }
-                __syncthreads();
                 for (int i = 0; i < m; ++i) {
                     const int j = j0 + i;
-                    if (j < n) AT(wz, i) = (j == n - 1) ? 1. : 0.;
+                    if (j < n) wz(i) = (j == n - 1) ? 1. : 0.;
                 }
-                __syncthreads();
+                team_sync(tm);
             }
-            backward_sweep(wz, bwd2, n, m, s_aff, s_edge, s_scalar);
+            backward_sweep(tm, sh, phase, wz, bwd2, n, m, s_edge);
             for (int i = 0; i < m; ++i)
-                if (tid * m + i < n) AT(wq, i) = AT(wz, i) / AT(D2, i);
+                if (tm.T * m + i < n) wq(i) = wz(i) / D2(i);
             __syncthreads();
         }
-        if (tid == 0 && cacheable) {
+        if (tm.T == 0 && cacheable) {
             hdr[1] = (double)__ldg(a.grid);
             hdr[2] = (double)__ldg(a.grid + n - 1);
             hdr[3] = (double)a.debye;
             hdr[4] = (double)n;
             hdr[5] = (double)a.periodic;
+            hdr[6] = (double)tm.size;
             __threadfence();
             reinterpret_cast<unsigned long long*>(hdr)[0] = kFactorMagic;
-        } else if (tid == 0) {
+        } else if (tm.T == 0) {
             reinterpret_cast<unsigned long long*>(hdr)[0] = 0ull;  // the planes no longer match any key
         }
     }
@@ -568,38 +681,40 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     // ---- solve: right-hand side, forward and backward sweeps (ref :350-353), output (ref :518-525)
 #pragma unroll 4
     for (int i = 0; i < m; ++i) {
-        const int j = min(tid * m + i, n - 1);  // rows past n: a copy of the last row, never used
+        const int j = min(tm.T * m + i, n - 1);  // rows past n: a copy of the last row, never used
         double r_low, r_dg, r_sup, r_rhs;
         build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
-        AT(y, i) = r_rhs;
+        y(i) = r_rhs;
     }
     if (bad_mask) atomicOr(a.status, ESPIC_ST_BAD_OBJECT_MASK);
     __syncthreads();
-    forward_sweep(y, fwd, n, m, s_aff, s_scalar);
-    backward_sweep(y, bwd, n, m, s_aff, s_edge, s_scalar);
-    double mean = 0.;
+    forward_sweep(tm, sh, phase, y, fwd, n, m);
+    backward_sweep(tm, sh, phase, y, bwd, n, m, s_edge);
     if (a.periodic) {  // ref :508-514, :518-523
-        if (tid == 0) s_scalar[1] = AT(y, 0) * AT(inv, 0);
-        __syncthreads();
-        const double v_dot_result = -s_scalar[1];
+        if (tm.T == 0) team_publish(tm, sh, phase, 1, y(0) * inv(0));
+        const int par = phase & 1;
+        // (the sum below is the team exchange that makes the published value visible; it needs the
+        // value itself, so the publication gets its own exchange first)
+        (void)team_sum(tm, sh, 0., phase);
+        const double v_dot_result = -sh.bcast[par][1];
         const double v_dot_w = 0.;  // quirk (2)
         double part = 0.;
         for (int i = 0; i < m; ++i) {
-            if (tid * m + i >= n) break;
-            const double r = AT(y, i) * AT(inv, i) - v_dot_result / (1. + v_dot_w) * AT(wq, i);
-            AT(y, i) = r;
+            if (tm.T * m + i >= n) break;
+            const double r = y(i) * inv(i) - v_dot_result / (1. + v_dot_w) * wq(i);
+            y(i) = r;
             part += r;
         }
-        mean = block_sum(part, s_red) / (double)n;
+        const double mean = team_sum(tm, sh, part, phase) / (double)n;
         for (int i = 0; i < m; ++i) {
-            const int j = tid * m + i;
-            if (j < n) a.potential[j] = (float)(AT(y, i) - mean);
+            const int j = tm.T * m + i;
+            if (j < n) a.potential[j] = (float)(y(i) - mean);
         }
     } else {
 #pragma unroll 8
         for (int i = 0; i < m; ++i) {
-            const int j = tid * m + i;
-            const double r = AT(y, i) * AT(inv, i);
+            const int j = tm.T * m + i;
+            const double r = y(i) * inv(i);
             if (j < n) a.potential[j] = (float)r;
         }
     }
@@ -629,22 +744,68 @@ __global__ void k_prepare_charge(float* __restrict__ ion, float* __restrict__ el
     }
 }
 
+// CTAs in the solving cluster for n grid points: the smallest power of two (up to the portable
+// cluster size) that gives every point its own thread, i.e. one row per thread up to 8192 points.
+static int team_size_for(int n) {
+    int c = 1;
+    while (c < kMaxTeam && c * kSolveThreads < n) c *= 2;
+    return c;
+}
+
 static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
     const int n = a.n;
     if (n < 3) return fail(ctx, ESPIC_E_ARG, "poisson_solve needs n_points >= 3");
-    const int m = (n + kSolveThreads - 1) / kSolveThreads;
-    const size_t plane = (size_t)m * kSolveThreads;
+    static bool configured = false;
+    static int max_team = kMaxTeam;
+    if (!configured) {  // static (19 KB) + dynamic (up to 128 KB) exceeds the 48 KB default
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSolveSmemRows * kSolveThreads * 8));
+        if (const char* e = getenv("ESPIC_SOLVE_TEAM")) {  // tuning knob: largest cluster to use
+            const int t = atoi(e);
+            if (t == 1 || t == 2 || t == 4 || t == 8) max_team = t;
+        }
+        // the largest cluster this device can co-schedule with the biggest shared-memory footprint
+        while (max_team > 1) {
+            cudaLaunchConfig_t probe = {};
+            probe.gridDim = dim3(max_team);
+            probe.blockDim = dim3(kSolveThreads);
+            probe.dynamicSmemBytes = kSolveSmemRows * kSolveThreads * 8;
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeClusterDimension;
+            pa[0].val.clusterDim.x = max_team;
+            pa[0].val.clusterDim.y = 1;
+            pa[0].val.clusterDim.z = 1;
+            probe.attrs = pa;
+            probe.numAttrs = 1;
+            int clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&clusters, k_poisson, &probe) == cudaSuccess && clusters >= 1) break;
+            cudaGetLastError();
+            max_team /= 2;
+        }
+        configured = true;
+    }
+    int team = team_size_for(n);
+    if (team > max_team) team = max_team;
+    const int tn = team * kSolveThreads;
+    const int m = (n + tn - 1) / tn;
+    const size_t plane = (size_t)m * tn;
     int rc = ensure(ctx, ctx->solve_ws, (kHeaderDoubles + 10 * plane) * sizeof(double), "solve workspace");
     if (rc) return rc;
     a.ws = (double*)ctx->solve_ws.ptr;
     a.status = ctx->status;
-    const size_t dyn = (m <= 5) ? plane * sizeof(double) : 0;  // <= 40 KB: the y plane
-    static bool configured = false;
-    if (!configured) {  // static (18 KB) + dynamic (40 KB) exceeds the 48 KB default
-        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kSolveThreads * 8));
-        configured = true;
-    }
-    k_poisson<<<1, kSolveThreads, dyn, ctx->stream>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(team);
+    cfg.blockDim = dim3(kSolveThreads);
+    cfg.dynamicSmemBytes = (m <= kSolveSmemRows) ? (size_t)m * kSolveThreads * sizeof(double) : 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ESPIC_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_poisson, a));
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_poisson launch");
 }
