@@ -61,7 +61,8 @@ SIGNATURES = {
                                          c_float, c_int, c_int, c_int, c_int, c_int]),
     "espic_mover_window_cells": (c_int, [c_void_p, c_int]),
     "espic_sort_particles": (c_int, [c_void_p, P, c_int, P, c_int, P, P, c_int, P, P, c_int, c_int]),
-    "espic_sort_particles_coarse": (c_int, [c_void_p, P, c_int, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int]),
+    "espic_sort_particles_coarse": (c_int, [c_void_p, P, c_int, P, c_int, P, P, c_int, P, P, c_int, c_int, c_int,
+                                            c_float]),
     "espic_shift_velocities": (c_int, [c_void_p, P, c_int, c_int, c_double]),
     "espic_poisson_solve": (c_int, [c_void_p, P, P, P, c_float, P, c_float, c_float, c_int, c_int, c_int]),
     "espic_prepare_charge": (c_int, [c_void_p, P, P, P, c_int, c_int, c_int, c_int]),

@@ -261,18 +261,18 @@ int espic_sort_particles(espic_ctx* ctx, const float* grid, int n_points, float*
     if (!grid || !particles || !particles_hist || !empty_slots || !current_empty_slot || !largest_index_dev)
         return fail(ctx, ESPIC_E_ARG, "espic_sort_particles: null pointer argument");
     return launch_sort(ctx, grid, n_points, particles, particle_storage_length, particles_hist, empty_slots, n_stack,
-                       current_empty_slot, largest_index_dev, largest_index, periodic_particles, 0);
+                       current_empty_slot, largest_index_dev, largest_index, periodic_particles, 0, 0.f);
 }
 
 int espic_sort_particles_coarse(espic_ctx* ctx, const float* grid, int n_points, float* particles,
                                 int particle_storage_length, int* particles_hist, int* empty_slots, int n_stack,
                                 int* current_empty_slot, int* largest_index_dev, int largest_index,
-                                int periodic_particles, int key_shift) {
+                                int periodic_particles, int key_shift, float lookahead) {
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !particles || !empty_slots || !current_empty_slot || !largest_index_dev)
         return fail(ctx, ESPIC_E_ARG, "espic_sort_particles_coarse: null pointer argument");
     return launch_sort(ctx, grid, n_points, particles, particle_storage_length, particles_hist, empty_slots, n_stack,
-                       current_empty_slot, largest_index_dev, largest_index, periodic_particles, key_shift);
+                       current_empty_slot, largest_index_dev, largest_index, periodic_particles, key_shift, lookahead);
 }
 
 int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storage_length, int largest_index,

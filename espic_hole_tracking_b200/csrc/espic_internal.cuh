@@ -207,7 +207,7 @@ int move_window_cells(espic_ctx* ctx, int n_points);  // 0: whole-grid tables fi
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);
 int launch_sort(espic_ctx* ctx, const float* grid, int n_points, float* particles, int storage, int* tags,
                 int* empty_slots, int n_stack, int* top, int* largest, int largest_index, int periodic,
-                int key_shift);
+                int key_shift, float lookahead);
 int launch_shift_velocities(espic_ctx* ctx, float* particles, int storage, int largest_index, double v_b);
 int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const float* charge,
                    float debye, float* potential, float obj_pot, float transparency, int boltzmann,

@@ -30,14 +30,21 @@ constexpr unsigned kSortNone = 0xFFFFu;
 
 // key of a slot: (cell index >> key_shift) of a live particle -- the same (int)((x-z_min)/dz) the
 // mover computes on entry -- or dead_key for a parked slot (sorts last)
+// With lookahead != 0 the cell is that of x + v*lookahead (clamped into the grid, or folded when
+// periodic): sorting by where a particle will be half-way to the next sort keeps a segment of the
+// store together for twice as many steps.
 template <bool PERIODIC>
-__device__ __forceinline__ int sort_key(const Geom& g, float x, int key_shift, int dead_key) {
+__device__ __forceinline__ int sort_key(const Geom& g, float x, float v, float lookahead, int key_shift,
+                                        int dead_key) {
     if (!(x < g.live_thr)) return dead_key;  // ref infMagSim_c.c:146 / :211
     bool bad = false;
-    const float xf = PERIODIC ? fold_periodic(g, x) : x;
-    // same truncated quotient either way (espic_selftest_quotient); the 3-operation form keeps the
-    // sort memory-bound
-    const int cell = g.fast_div ? cell_of<PERIODIC, true>(g, xf, bad) : cell_of<PERIODIC, false>(g, xf, bad);
+    const float xp = (lookahead != 0.f) ? __fadd_rn(x, __fmul_rn(v, lookahead)) : x;
+    const float xf = PERIODIC ? fold_periodic(g, xp) : xp;
+    // same truncated quotient either way (espic_selftest_quotient, positions inside the domain); the
+    // 3-operation form keeps the sort memory-bound.  A look-ahead position beyond a wall is outside
+    // the range that self-test covers: division instruction there.
+    const bool fast = g.fast_div && (PERIODIC || lookahead == 0.f);
+    const int cell = fast ? cell_of<PERIODIC, true>(g, xf, bad) : cell_of<PERIODIC, false>(g, xf, bad);
     return cell >> key_shift;
 }
 
@@ -59,10 +66,12 @@ __device__ __forceinline__ unsigned same_digit_lanes(unsigned d, int digit_bits)
 struct SortKeying {
     const float* grid;
     int n_points, key_shift, dead_key, shift, bins;
+    float lookahead;
 };
 
 template <bool PERIODIC>
-__global__ void __launch_bounds__(256) k_sort_hist(const SortKeying kk, const float* __restrict__ px, int n,
+__global__ void __launch_bounds__(256) k_sort_hist(const SortKeying kk, const float* __restrict__ px,
+                                                   const float* __restrict__ pv, int n,
                                                    int n_tiles, int* __restrict__ hist /* [bins][n_tiles] */,
                                                    int* __restrict__ n_live /* may be null */) {
     __shared__ int s_cnt[kSortMaxBins];
@@ -73,17 +82,18 @@ __global__ void __launch_bounds__(256) k_sort_hist(const SortKeying kk, const fl
         __syncthreads();
         const int base = tile * kSortTile;
         for (int i0 = 0; i0 < kSortTile; i0 += 16 * 256) {  // 16 loads in flight per thread
-            float xr[16];
+            float xr[16], vr[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int idx = base + i0 + k * 256 + (int)threadIdx.x;
                 xr[k] = idx < n ? __ldcs(px + idx) : 0.f;
+                vr[k] = (idx < n && kk.lookahead != 0.f) ? __ldcs(pv + idx) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int idx = base + i0 + k * 256 + (int)threadIdx.x;
                 if (idx < n) {
-                    const int key = sort_key<PERIODIC>(g, xr[k], kk.key_shift, kk.dead_key);
+                    const int key = sort_key<PERIODIC>(g, xr[k], vr[k], kk.lookahead, kk.key_shift, kk.dead_key);
                     live += key != kk.dead_key;
                     atomicAdd(&s_cnt[(key >> kk.shift) & (kk.bins - 1)], 1);
                 }
@@ -199,12 +209,18 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_sort_scatter(const SortKeyi
             const int li = wbase + r * 32 + lane;
             xr[r] = (li < n_tile) ? __ldcs(in.x + base + li) : 0.f;
         }
+        float vr[kSortRows];
+#pragma unroll
+        for (int r = 0; r < kSortRows; ++r) {
+            const int li = wbase + r * 32 + lane;
+            vr[r] = (li < n_tile && kk.lookahead != 0.f) ? __ldg(in.v + base + li) : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < kSortRows; ++r) {
             const int li = wbase + r * 32 + lane;
             unsigned d = kSortNone;
             if (li < n_tile) {
-                const int key = sort_key<PERIODIC>(g, xr[r], kk.key_shift, kk.dead_key);
+                const int key = sort_key<PERIODIC>(g, xr[r], vr[r], kk.lookahead, kk.key_shift, kk.dead_key);
                 d = (unsigned)((key >> kk.shift) & (bins - 1));
             }
             s_pos[li] = (unsigned short)d;
@@ -333,7 +349,7 @@ __global__ void k_sort_finalize(const float* __restrict__ grid, int n_points, fl
 
 int launch_sort(espic_ctx* ctx, const float* grid, int n_points, float* particles, int storage, int* tags,
                 int* empty_slots, int n_stack, int* top, int* largest, int largest_index, int periodic,
-                int key_shift) {
+                int key_shift, float lookahead) {
     const int n = largest_index + 1;
     if (n_points < 2 || storage < 1 || n > storage) return fail(ctx, ESPIC_E_ARG, "espic_sort_particles: bad sizes");
     if (key_shift < 0 || key_shift > 30) return fail(ctx, ESPIC_E_ARG, "espic_sort_particles: bad key_shift");
@@ -373,12 +389,12 @@ int launch_sort(espic_ctx* ctx, const float* grid, int n_points, float* particle
         const int hg = n_tiles < 8 * ctx->sm_count ? n_tiles : 8 * ctx->sm_count;
         const int sg = n_tiles < 2 * ctx->sm_count ? n_tiles : 2 * ctx->sm_count;
         for (int pass = 0; pass < passes; ++pass) {
-            const SortKeying kk{grid, n_points, key_shift, dead_key, pass * digit_bits, bins};
+            const SortKeying kk{grid, n_points, key_shift, dead_key, pass * digit_bits, bins, lookahead};
             const SortArrays in = pass == 0 ? SortArrays{px, pv, tags} : SortArrays{x1, v1, tags ? tag1 : nullptr};
             const SortOut out = pass == 0 ? SortOut{x1, v1, tag1} : SortOut{px, pv, tags};
             int* live_out = pass == 0 ? n_live : nullptr;
-            if (periodic) k_sort_hist<true><<<hg, 256, 0, st>>>(kk, in.x, n, n_tiles, hist, live_out);
-            else k_sort_hist<false><<<hg, 256, 0, st>>>(kk, in.x, n, n_tiles, hist, live_out);
+            if (periodic) k_sort_hist<true><<<hg, 256, 0, st>>>(kk, in.x, in.v, n, n_tiles, hist, live_out);
+            else k_sort_hist<false><<<hg, 256, 0, st>>>(kk, in.x, in.v, n, n_tiles, hist, live_out);
             k_sort_row_totals<<<bins, 256, 0, st>>>(hist, n_tiles, totals);
             k_sort_offsets<<<bins, 256, 0, st>>>(hist, n_tiles, bins, totals);
             if (periodic) k_sort_scatter<true><<<sg, kSortWarps * 32, kSortScatterSmem, st>>>(kk, in, out, n, n_tiles, hist);

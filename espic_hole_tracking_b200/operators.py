@@ -189,11 +189,11 @@ def initialize_mover(grid, object_mask, potential, dt, chage_to_mass, largest_in
 
 
 def sort_particles_by_cell(grid, particles, particles_hist, empty_slots, current_empty_slot_list,
-                           largest_index_list, periodic_particles=False, ctx=None, key_shift=0):
+                           largest_index_list, periodic_particles=False, ctx=None, key_shift=0, lookahead=0.0):
     """Stable cell sort + compaction of a particle store (K6, espic_sort_particles); in place.
     No reference counterpart -- the reference never reorders its store; physically a no-op.
     key_shift > 0 sorts by (cell >> key_shift) only (espic_sort_particles_coarse); particles_hist
-    may then be None."""
+    may then be None.  lookahead != 0 sorts by the cell of x + v*lookahead."""
     dev = particles.device
     _check(particles, "particles", torch.float32, 2, None)
     _check(grid, "grid", torch.float32, 1, dev)
@@ -207,7 +207,8 @@ def sort_particles_by_cell(grid, particles, particles_hist, empty_slots, current
     rc = ctx._lib.espic_sort_particles_coarse(
         ctx.handle, _ptr(grid), grid.shape[0], _ptr(particles), particles.shape[1],
         _ptr(particles_hist) if particles_hist is not None else None, _ptr(empty_slots), empty_slots.shape[0],
-        top.ptr, last.ptr, int(largest_index_list[0]), int(bool(periodic_particles)), int(key_shift))
+        top.ptr, last.ptr, int(largest_index_list[0]), int(bool(periodic_particles)), int(key_shift),
+        float(lookahead))
     ctx.check(rc, "sort_particles_by_cell")
     top.exit()
     last.exit()

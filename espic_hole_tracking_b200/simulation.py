@@ -264,11 +264,15 @@ class Simulation:
             self.xch.publish(0, 0)
         self._plan_sorting()
         if self.sort_intervals["ions"] or self.sort_intervals["electrons"]:
-            self.sort_particles([n for n, k in self.sort_intervals.items() if k], key_shift=self.sort_key_shift)
+            for n, every in self.sort_intervals.items():
+                if every:
+                    self.sort_particles((n,), key_shift=self.sort_key_shift, lookahead_steps=0.5 * every)
 
     def _plan_sorting(self) -> None:
         """Sort intervals for the large-grid mover (csrc/mover_win.cu): a segment of a sorted store
-        spreads by v*dt per step; re-sort before 2.3 thermal speeds have used up the window's margin."""
+        spreads by v*dt per step.  Stores are sorted by where the particles will be half an interval
+        later, so the spread first shrinks, then grows; re-sort before 2.3 thermal speeds have used
+        up the window's margin on either side."""
         c = self.cfg
         window = self.ctx._lib.espic_mover_window_cells(self.ctx.handle, self.n_points)
         self.sort_key_shift = 0
@@ -281,7 +285,7 @@ class Simulation:
                 continue
             margin = 0.5 * window - (1 << self.sort_key_shift)
             drift = max(v_th, abs(self.v_b)) * self.dt / self.dz          # cells per step at one thermal speed
-            auto[name] = int(min(1000, max(1, margin / (2.3 * drift))))
+            auto[name] = int(min(1000, max(1, 2 * margin / (2.3 * drift))))
         self.sort_intervals = {
             "ions": auto["ions"] if c.sort_interval_ions is None else c.sort_interval_ions,
             "electrons": auto["electrons"] if c.sort_interval_electrons is None else c.sort_interval_electrons}
@@ -400,9 +404,9 @@ class Simulation:
             self.xch.publish(k + 1, k + 1)
         self.t += self.dt
         self.k += 1
-        due = [n for n, every in self.sort_intervals.items() if every and self.k % every == 0]
-        if due:
-            self.sort_particles(due, key_shift=self.sort_key_shift)
+        for n, every in self.sort_intervals.items():
+            if every and self.k % every == 0:
+                self.sort_particles((n,), key_shift=self.sort_key_shift, lookahead_steps=0.5 * every)
 
     def _step_operator_by_operator(self, k: int, ions_mobile: bool, ramp: bool) -> None:
         """The same step through the individual operators, in the reference's order (used when the
@@ -453,14 +457,15 @@ class Simulation:
             ctx=self.ctx)[0]
         dd.all_reduce_histograms(self.hist.values(), self.world, self.pg)                        # :876,894,895
 
-    def sort_particles(self, species=("ions", "electrons"), key_shift: int = 0) -> None:
+    def sort_particles(self, species=("ions", "electrons"), key_shift: int = 0, lookahead_steps: float = 0.0) -> None:
         """Stable cell sort + compaction of the named stores (K6).  Physically a no-op: slot numbers
-        change, particle state does not.  key_shift > 0 groups by blocks of 2**key_shift cells only."""
+        change, particle state does not.  key_shift > 0 groups by blocks of 2**key_shift cells only;
+        lookahead_steps sorts by the cell each particle reaches that many steps from now."""
         for name in species:
             s = getattr(self, name)
             ops.sort_particles_by_cell(self.grid, s.particles, s.tags, s.empty_slots, s.current_empty_slot,
                                        s.largest_index, periodic_particles=self.cfg.periodic_particles, ctx=self.ctx,
-                                       key_shift=key_shift)
+                                       key_shift=key_shift, lookahead=lookahead_steps * self.dt)
 
     def run(self, n_steps: int) -> None:
         for _ in range(n_steps):

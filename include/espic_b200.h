@@ -118,12 +118,15 @@ int espic_sort_particles(espic_ctx *ctx, const float *grid, int n_points, float 
 /* The same with the key coarsened to (cell index >> key_shift): particles end up grouped by
  * blocks of 2^key_shift cells, in slot order inside a block.  That is all the large-grid mover
  * needs (it keeps a window of the grid in shared memory per segment of the store) and it is one
- * radix pass instead of two on a 65536-cell grid.  particles_hist may be NULL.  key_shift = 0 is
- * espic_sort_particles. */
+ * radix pass instead of two on a 65536-cell grid.  With lookahead != 0 the cell is that of
+ * fl(x + fl(v*lookahead)), folded into the domain (periodic) or clamped to the end cells: sorted by
+ * where the particles will be half-way to the next sort, a segment stays together twice as long.
+ * particles_hist may be NULL.  key_shift = 0, lookahead = 0 is espic_sort_particles. */
 int espic_sort_particles_coarse(espic_ctx *ctx, const float *grid, int n_points, float *particles,
                                 int particle_storage_length, int *particles_hist, int *empty_slots,
                                 int n_stack, int *current_empty_slot, int *largest_index_dev,
-                                int largest_index, int periodic_particles, int key_shift);
+                                int largest_index, int periodic_particles, int key_shift,
+                                float lookahead);
 
 /* v[i] -= v_b for i <= largest_index: the tail of initialize_mover
  * (ref infMagSim_cython.py:174-176; the subtraction runs in double there). */

@@ -19,17 +19,20 @@ def ops():
     return pkg
 
 
-def reference_sort(grid, p, tags, n_slots, periodic, key_shift=0):
+def reference_sort(grid, p, tags, n_slots, periodic, key_shift=0, lookahead=0.0):
     """numpy statement of the sort: keys with the mover's float32 arithmetic, stable argsort."""
     z_lo, z_hi = np.float32(grid[0]), np.float32(grid[-1])
     dz = np.float32((z_hi - z_lo) / np.float32(len(grid) - 1))
     x = p[0, :n_slots].copy()
     live = x.astype(np.float64) < 0.99 * float(np.float32(2 * z_hi))
     xs = x.copy()
+    if lookahead:
+        xs = (xs + (p[1, :n_slots] * np.float32(lookahead)).astype(np.float32)).astype(np.float32)
     if periodic:
         off = np.fmod(xs - z_lo, z_hi - z_lo)
         xs = np.where(off >= 0, off + z_lo, off + z_hi).astype(np.float32)
-    cell = ((xs - z_lo) / dz).astype(np.int64)
+    with np.errstate(invalid="ignore"):
+        cell = np.trunc(np.clip((xs - z_lo) / dz, -1e9, 1e9)).astype(np.int64)
     if periodic:
         cell[cell > len(grid) - 2] = 0
     cell = np.clip(cell, 0, len(grid) - 2)
@@ -68,6 +71,30 @@ def test_sort_is_stable_argsort(ops, n_cells, key_shift, periodic):
     want_p, want_tags, want_stack, n_live, keys = reference_sort(grid, sp.particles, sp.tags, n, periodic, key_shift)
     assert last == [n_live - 1] and top == [S - n_live - 1]
     assert np.all(np.diff(keys) >= 0)
+    assert_bits_equal(g["p"].cpu().numpy(), want_p, "sorted particles")
+    assert_bits_equal(g["tags"].cpu().numpy(), want_tags, "sorted tags")
+    assert_bits_equal(g["stack"].cpu().numpy(), want_stack, "rebuilt stack")
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_sort_with_lookahead_key(ops, periodic):
+    """Key = cell of fl(x + fl(v*lookahead)): fast particles are filed where they are going (clamped
+    to the end cells at walls, folded when periodic)."""
+    n_cells, key_shift, lookahead = 65536, 8, 4.5 * wl.timestep()
+    grid = wl.make_grid(n_cells)
+    rng = np.random.default_rng(9)
+    n, S = 120_000, 150_000
+    sp = wl.make_species(n, S, rng, 43.0, -1836.0, holes=0.05)
+    sp.tags[0, :n] = rng.integers(0, 1000, n)
+    sp.particles[:, :4] = np.array([[-2.9999, 2.9999, 0.0, 2.5], [-400.0, 400.0, 90.0, 3000.0]], np.float32)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    g = dict(p=dev(sp.particles), tags=dev(sp.tags), stack=dev(sp.empty_slots))
+    top, last = list(sp.current_empty_slot), list(sp.largest_index)
+    ops.sort_particles_by_cell(dev(grid), g["p"], g["tags"], g["stack"], top, last, periodic_particles=periodic,
+                               key_shift=key_shift, lookahead=lookahead)
+    want_p, want_tags, want_stack, n_live, keys = reference_sort(grid, sp.particles, sp.tags, n, periodic, key_shift,
+                                                                 lookahead)
+    assert last == [n_live - 1] and top == [S - n_live - 1]
     assert_bits_equal(g["p"].cpu().numpy(), want_p, "sorted particles")
     assert_bits_equal(g["tags"].cpu().numpy(), want_tags, "sorted tags")
     assert_bits_equal(g["stack"].cpu().numpy(), want_stack, "rebuilt stack")
