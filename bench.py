@@ -222,8 +222,12 @@ def main():
     peak, peak_src = measured_peak()
     mover_ms = timing["mean_ms"]
     achieved = ALGO_BYTES_PER_PARTICLE_STEP * n / (mover_ms * 1e-3) / 1e9 if mover_ms > 0 else 0.0
+    window = ctx._lib.espic_mover_window_cells(ctx.handle, sim.n_points)
+    flavour = "walls" if args.walls else "periodic"
+    kernel = (f"espic::k_move_win<{flavour}> ({window}-cell shared-memory window per store segment)" if window
+              else f"espic::k_move<{flavour}, smem tables>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "espic::k_move<periodic, smem tables>",
+                "traffic": None, "kernel": kernel,
                 "launch_ms_mean": mover_ms, "launches_timed": timing["launches"],
                 "mover_share_of_step": timing["total_ms"] / ms if ms > 0 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * n}
@@ -232,7 +236,7 @@ def main():
         try:
             with open(traffic_path) as fh:
                 tr = json.load(fh)
-            if int(tr.get("particles_per_launch", 0)) == n:
+            if int(tr.get("particles_per_launch", 0)) == n and not window and not args.walls:
                 roofline["traffic"] = tr["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -296,7 +300,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{n:.3g} ions + {n:.3g} electrons per GPU, {args.cells}-cell periodic grid "
+        "config": {"workload": f"{n:.3g} ions + {n:.3g} electrons per GPU, {args.cells}-cell "
+                               f"{'wall-bounded grid with injection' if args.walls else 'periodic grid'} "
                                "(BASELINE configs[1]; N>1 = configs[2]-style weak scaling with the density all-reduce)",
                    "particles_per_species_per_gpu": n, "cells": args.cells, "periodic": not args.walls,
                    "field_solve": "periodic particles, Robin-end potential (periodic_potential=False): the reference's "
