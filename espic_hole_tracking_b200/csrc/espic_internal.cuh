@@ -28,6 +28,7 @@ struct Geom {
     float q_shift;   // trunc(z_lo/dz): cell index -> quotient estimate of x/dz (deposit weights)
     float rcp_dz24;  // rcp_dz * 2^24 (exact scaling): remainder -> 24-bit fixed-point share
     float fold_lo, fold_hi;  // periodic fast path: x1 - z_lo must lie strictly inside (fold_lo, fold_hi)
+    float cell_span;  // smallest offset b <= span with (int)(b/dz) > n_points-2: offsets below it index a real cell
     int last_cell;   // n_points - 2
     bool fast_div;   // the 3-operation quotient is safe for this dz (normal exponent range)
 };
@@ -52,6 +53,14 @@ __device__ __forceinline__ Geom make_geom(const float* __restrict__ grid, int n_
     g.fold_lo = -0.99f * g.span;
     g.fold_hi = fminf(1.99f * g.span, (g.live_thr - g.z_lo) - 1e-3f * g.span);
     g.last_cell = n_points - 2;
+    // dz is a rounded quotient, so the last float(s) below span can already divide to n_cells
+    // (e.g. 37 cells on [-3, 3]); the reference then takes cell 0 (periodic) or reports a bad index
+    g.cell_span = g.span;
+    for (int k = 0; k < 4; ++k) {
+        const float below = __uint_as_float(__float_as_uint(g.cell_span) - 1u);
+        if (!(below > 0.f) || __float2int_rz(__fdiv_rn(below, g.dz)) <= g.last_cell) break;
+        g.cell_span = below;
+    }
     // exponent window in which neither dz, 1/dz, the quotient nor the residual can leave the
     // normal range for |x - z_lo| <= span
     g.fast_div = (g.dz > 1e-18f) && (g.dz < 1e18f) && (g.span < 1e18f) &&

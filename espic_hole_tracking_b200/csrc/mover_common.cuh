@@ -110,11 +110,17 @@ __device__ __forceinline__ void smem_add_carry(unsigned* lo, unsigned* hi, unsig
     if (old > ~w) atomicAdd(hi, 1u);
 }
 
-template <bool SMEM>
+template <bool SMEM, bool RESEED = false>
 __device__ __forceinline__ void deposit_one(const Geom& g, float x, int cell, unsigned* s_lo,
                                             unsigned* s_hi, unsigned long long* acc) {
+    // The weights depend on x alone (fmodf(x,dz)/dz, ref :219-223); the cell only seeds the quotient
+    // estimate, which must be within 127 cells of x/dz.  The generic path (RESEED) also sees slots
+    // whose deposit cell is not their position's cell -- the periodic overflow to cell 0 just below
+    // z_max (ref :186-187) -- so it seeds from the position itself; same bits whenever the two agree.
+    int seed = cell;
+    if (RESEED) seed = min(max(__float2int_rz(quotient_dz<false>(g, __fsub_rn(x, g.z_lo))), 0), g.last_cell + 1);
     unsigned w0, w1;
-    node_weights_fixed(g, x, cell, w0, w1);
+    node_weights_fixed(g, x, seed, w0, w1);
     if (SMEM) {
         smem_add_carry(s_lo + cell, s_hi + cell, w0);
         smem_add_carry(s_lo + cell + 1, s_hi + cell + 1, w1);
@@ -177,7 +183,7 @@ __device__ __noinline__ unsigned quad_generic(const MoveArgs& a, int q, int n_sl
         const int act = push_generic<PERIODIC>(g, x, v, dv, a.dt, upd, has_obj, a.grid, a.mask, cell, bad_any);
         a.px[s] = x;
         a.pv[s] = v;
-        if (act == ACT_DEPOSIT) deposit_one<SMEM>(g, x, cell, s_lo, s_hi, a.acc);
+        if (act == ACT_DEPOSIT) deposit_one<SMEM, true>(g, x, cell, s_lo, s_hi, a.acc);
         rem |= (act == ACT_REMOVE) ? (1u << c) : 0u;
     }
     if (bad_any) atomicOr(a.status, ESPIC_ST_BAD_LEFT_INDEX);
@@ -206,7 +212,8 @@ __device__ __forceinline__ void push_fast_periodic(const Geom& g, float& x_io, f
     const float x0 = __fadd_rn(a0, g.z_lo);
     const float b0 = __fsub_rn(x0, g.z_lo);                                 // ref :161 (x - z_min)
     rare |= !(a0 >= 0.f);                 // would wrap from below (or NaN)
-    rare |= !(b0 < g.span);               // would wrap from above, folded onto z_max, or a parked slot
+    rare |= !(b0 < g.cell_span);          // would wrap from above, folded onto z_max (or so close that the cell
+                                          // index overflows: the reference takes cell 0 then), or a parked slot
     const int c0 = (int)min((unsigned)__float2int_rz(quotient_dz<true>(g, b0)), last);
     const float v1 = __fadd_rn(v_io, kick(c0));                              // ref :166-168
     const float x1 = __fadd_rn(x0, __fmul_rn(v1, dt));                      // ref :170
@@ -217,7 +224,7 @@ __device__ __forceinline__ void push_fast_periodic(const Geom& g, float& x_io, f
     const float off = __fsub_rn(a1, (a1 >= g.span) ? g.span : 0.f);
     const float x2 = __fadd_rn(off, (off >= 0.f) ? g.z_lo : g.z_hi);
     const float b2 = __fsub_rn(x2, g.z_lo);                                 // ref :185
-    rare |= !(b2 < g.span);               // folded exactly onto z_max: the reference maps that cell to 0
+    rare |= !(b2 < g.cell_span);          // folded onto z_max or within rounding of it: the reference takes cell 0
     cell_out = (int)min((unsigned)__float2int_rz(quotient_dz<true>(g, b2)), last);
     x_io = x2;
     v_io = v1;

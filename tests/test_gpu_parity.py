@@ -173,6 +173,39 @@ def test_mover_large_grid_path(ops, cpu, periodic):
     check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, periodic)
 
 
+@pytest.mark.parametrize("n_cells", [19, 37, 137])
+def test_mover_cell_index_overflow_just_below_zmax(ops, cpu, n_cells):
+    """dz = fl(span/n_cells) is rounded, so on some grids the last float below z_max already divides
+    to n_cells; the reference's periodic branch then takes cell 0 (ref infMagSim_c.c:161-165,
+    185-189).  Particles parked on those floats, before and after the push, must follow it."""
+    grid = wl.make_grid(n_cells)
+    assert int(np.float32(np.nextafter(np.float32(6), np.float32(0))) / np.float32(np.float32(6) / np.float32(n_cells))) == n_cells
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid, amplitude=0.5)
+    n, S = 4096, 4096
+    rng = np.random.default_rng(n_cells)
+    sp = wl.make_species(n, S, rng, 1.0, 1.0)
+    top_ulps = np.float32(3.0) - np.arange(1, 9, dtype=np.float32) * np.float32(2.0 ** -22)   # the 8 floats below z_max
+    sp.particles[0, :1024] = np.resize(top_ulps, 1024)
+    sp.particles[1, :1024] = np.resize(np.array([0.0, 1e-9, -1e-9, 1e-4, -1e-4], np.float32), 1024)
+    sp.particles[0, 1024:2048] = np.float32(-3.0) + rng.random(1024).astype(np.float32) * np.float32(1e-3)
+    sp.particles[1, 1024:2048] = np.float32(-1.0)            # cross the seam downwards: land just below z_max
+    bg, dt = 3.0, np.float32(1e-3)
+    c = sp.copy()
+    g = to_dev(sp, torch)
+    top_g, last_g = list(sp.current_empty_slot), list(sp.largest_index)
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    for _ in range(3):
+        cpu.move_particles(grid, mask, phi, dt, 0.01, bg, c.largest_index, c.particles, d_ref, c.empty_slots,
+                           c.current_empty_slot, a_b=0.0, periodic_particles=True)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), dt, 0.01, bg, last_g, g["particles"], g_den,
+                           g["empty_slots"], top_g, 0.0, periodic_particles=True)
+        assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+        np.testing.assert_allclose(g_den.cpu().numpy(), d_ref, rtol=0, atol=3e-6 * d_ref.max())
+    assert top_g == c.current_empty_slot
+
+
 @pytest.mark.parametrize("periodic", [False, True])
 def test_mover_window_on_sorted_store(ops, cpu, periodic):
     """65537 grid points, store coarse-sorted first: the large-grid mover then serves nearly every
