@@ -173,6 +173,45 @@ def test_mover_large_grid_path(ops, cpu, periodic):
     check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, periodic)
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("domain", [(-7.3, 11.9, 1000), (0.25, 50.25, 777), (-40.0, -1.5, 4096)])
+def test_mover_other_domains(ops, cpu, domain, periodic):
+    """Nothing in the kernels assumes the script's [-3, 3] box: z_min not a multiple of dz (the
+    reference's fmodf(x, dz) weights are then offset against the cells), one-signed domains."""
+    z_lo, z_hi, n_cells = domain
+    grid = np.linspace(z_lo, z_hi, n_cells + 1).astype(np.float32)
+    mask = np.zeros_like(grid)
+    rng = np.random.default_rng(n_cells)
+    phi = (0.7 * np.sin(2 * np.pi * (grid - grid[0]) / (grid[-1] - grid[0]) * 3)).astype(np.float32)
+    n, S = 50_000, 60_000
+    L = float(grid[-1]) - float(grid[0])
+    p = np.empty((2, S), np.float32)
+    p[0, :n] = (float(grid[0]) + rng.random(n) * L).astype(np.float32)
+    p[1, :n] = (rng.standard_normal(n) * 30.0).astype(np.float32)
+    p[0, n:], p[1, n:] = np.float32(2 * grid[-1]), 0.0
+    if grid[-1] <= 0:       # the reference's parked marker 2*z_max lies inside a negative domain: no dead slots then
+        S = n
+        p = np.ascontiguousarray(p[:, :n])
+    stack = -np.ones(S, np.int32)
+    stack[:S - n] = np.arange(S - 1, n - 1, -1, dtype=np.int32)
+    sp = wl.Species(p, np.zeros((1, S), np.int32), stack, [S - n - 1], [n - 1], -1836.0, 30.0)
+    bg, dt = 5.0, np.float32(2e-3)
+    c = sp.copy()
+    g = to_dev(sp, torch)
+    top_g, last_g = list(sp.current_empty_slot), list(sp.largest_index)
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    for _ in range(3):
+        cpu.move_particles(grid, mask, phi, dt, sp.charge_to_mass, bg, c.largest_index, c.particles, d_ref,
+                           c.empty_slots, c.current_empty_slot, a_b=0.0, periodic_particles=periodic)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), dt, sp.charge_to_mass, bg, last_g, g["particles"], g_den,
+                           g["empty_slots"], top_g, 0.0, periodic_particles=periodic)
+        assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles")
+        assert top_g == c.current_empty_slot
+        assert_bits_equal(g["empty_slots"].cpu().numpy()[:top_g[0] + 1], c.empty_slots[:top_g[0] + 1], "stack")
+        np.testing.assert_allclose(g_den.cpu().numpy(), d_ref, rtol=0, atol=5e-6 * d_ref.max())
+
+
 @pytest.mark.parametrize("n_cells", [19, 37, 137])
 def test_mover_cell_index_overflow_just_below_zmax(ops, cpu, n_cells):
     """dz = fl(span/n_cells) is rounded, so on some grids the last float below z_max already divides
