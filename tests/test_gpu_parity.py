@@ -317,9 +317,15 @@ def test_accumulate_density_and_initialize_mover(ops, cpu):
     assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles after initialize_mover")
 
 
-@pytest.mark.parametrize("n_points", [9, 513, 4097, 65537])
+# 9 .. 1024 points: one CTA; 1500: cluster of 2; 3000: 4; 4097 and up: 8 (1, 3 and 9 rows per thread)
+@pytest.mark.parametrize("n_points", [9, 513, 1024, 1025, 1501, 3000, 3001, 4097, 8193, 20001, 65537])
 @pytest.mark.parametrize("periodic", [False, True])
 def test_poisson(ops, cpu, n_points, periodic):
+    if periodic and n_points % 2 == 0:
+        # the reference reads v[n_points] past its malloc'd arrays in this branch;
+        # with an even point count that lands in allocator slack holding stale heap bytes, not in the
+        # next chunk's size field (a denormal, i.e. 0 in the product): its output is not reproducible
+        pytest.skip("reference result depends on uninitialised heap bytes for even n_points")
     grid = wl.make_grid(n_points - 1)
     rng = np.random.default_rng(n_points)
     charge = (0.05 * rng.standard_normal(n_points)).astype(np.float32)
@@ -331,19 +337,31 @@ def test_poisson(ops, cpu, n_points, periodic):
                       use_pure_c_version=True)
     scale = np.abs(p_ref).max()
     assert scale > 0
-    err = np.abs(p_gpu.cpu().numpy().astype(np.float64) - p_ref).max() / scale
+    first = p_gpu.cpu().numpy().copy()
+    err = np.abs(first.astype(np.float64) - p_ref).max() / scale
+    assert err <= REL, err
+    # the second call finds the factorisation in the workspace: same bits
+    p_gpu.zero_()
+    ops.poisson_solve(dev(grid), dev(mask), dev(charge), wl.DEBYE_LENGTH, p_gpu, periodic_potential=periodic)
+    assert_bits_equal(p_gpu.cpu().numpy(), first, "cached vs uncached solve")
+    # and a different right-hand side on the cached factorisation is still right
+    charge2 = (0.05 * rng.standard_normal(n_points)).astype(np.float32)
+    cpu.poisson_solve(grid, mask, charge2, wl.DEBYE_LENGTH, p_ref, periodic_potential=periodic)
+    ops.poisson_solve(dev(grid), dev(mask), dev(charge2), wl.DEBYE_LENGTH, p_gpu, periodic_potential=periodic)
+    err = np.abs(p_gpu.cpu().numpy().astype(np.float64) - p_ref).max() / np.abs(p_ref).max()
     assert err <= REL, err
 
 
-def test_poisson_object_and_boltzmann(ops, cpu):
-    n_points = 513
+@pytest.mark.parametrize("n_points", [513, 3001, 9001])
+def test_poisson_object_and_boltzmann(ops, cpu, n_points):
     grid = wl.make_grid(n_points - 1)
     rng = np.random.default_rng(3)
     charge = (1.0 + 0.05 * rng.standard_normal(n_points)).astype(np.float32)
     mask = np.zeros_like(grid)
-    mask[200:240] = 1.0
-    mask[199], mask[240] = 0.3, 0.6
-    mask[300] = 0.5
+    k = n_points // 513      # the object straddles run and CTA boundaries on the larger grids
+    mask[200 * k:240 * k] = 1.0
+    mask[200 * k - 1], mask[240 * k] = 0.3, 0.6
+    mask[300 * k] = 0.5
     for transparency in (0.0, 0.35, 1.0):
         for boltz in (False, True):
             p_ref = (0.1 * np.sin(grid)).astype(np.float32)
