@@ -140,6 +140,7 @@ void espic_destroy(espic_ctx* ctx) {
     if (ctx->dev_int2) cudaFree(ctx->dev_int2);
     free_scratch(ctx->staging);
     free_scratch(ctx->chunk_counts);
+    free_scratch(ctx->range_offsets);
     free_scratch(ctx->dv_table);
     free_scratch(ctx->solve_ws);
     free_scratch(ctx->inject_ws);
@@ -486,18 +487,34 @@ struct PinnedRange {
 static PinnedRange g_pinned[32];
 static int g_n_pinned = 0;
 
-static void pin_host_range(const void* ptr, size_t bytes) {
+// Page-locks [ptr, ptr + bytes) of a caller's array once so that the copies run at full PCIe speed
+// (a pageable cudaMemcpyAsync is staged through a driver buffer).  `capacity` is the size of the
+// caller's row: when the used part grows (injection raises largest_index) the registration is
+// replaced by a larger one with headroom, never extended piecemeal -- a copy must not straddle
+// registered and unregistered pages.
+static void pin_host_range(const void* ptr, size_t bytes, size_t capacity) {
     if (!ptr || bytes < (8u << 20)) return;  // small arrays are not worth a registration
-    for (int i = 0; i < g_n_pinned; ++i)
-        if (g_pinned[i].ptr == ptr && g_pinned[i].bytes >= bytes) return;
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("ESPIC_PIN_HOST");
         enabled = e ? atoi(e) : 1;
     }
-    if (!enabled || g_n_pinned >= 32) return;
-    if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) {
-        g_pinned[g_n_pinned++] = PinnedRange{ptr, bytes};
+    if (!enabled) return;
+    int slot = -1;
+    for (int i = 0; i < g_n_pinned; ++i)
+        if (g_pinned[i].ptr == ptr) slot = i;
+    if (slot >= 0 && g_pinned[slot].bytes >= bytes) return;
+    if (slot >= 0) {  // grown past the registered part
+        cudaHostUnregister(const_cast<void*>(ptr));
+        cudaGetLastError();
+        g_pinned[slot] = g_pinned[--g_n_pinned];
+    }
+    if (g_n_pinned >= 32) return;
+    size_t want = bytes + bytes / 4;
+    if (want > capacity) want = capacity;
+    if (want < bytes) want = bytes;
+    if (cudaHostRegister(const_cast<void*>(ptr), want, cudaHostRegisterDefault) == cudaSuccess) {
+        g_pinned[g_n_pinned++] = PinnedRange{ptr, want};
     } else {
         cudaGetLastError();  // leave it pageable
     }
@@ -542,8 +559,8 @@ void move_particles_c(float* grid, float* object_mask, float* potential, float d
     int* d_top = ctx->dev_int2;
     const size_t used = (size_t)(largest_index + 1);
     if (used) {
-        pin_host_range(particles, used * sizeof(float));
-        pin_host_range(particles + S, used * sizeof(float));
+        pin_host_range(particles, used * sizeof(float), S * sizeof(float));
+        pin_host_range(particles + S, used * sizeof(float), S * sizeof(float));
     }
     H2D(d_grid, grid, n, float);
     H2D(d_mask, object_mask, n, float);

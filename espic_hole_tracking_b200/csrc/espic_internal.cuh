@@ -159,7 +159,8 @@ struct espic_ctx {
     int* status = nullptr;              // ESPIC_ST_* bits
     unsigned int* ticket = nullptr;     // last-block-done counters
     espic::Scratch staging;             // removed slot ids, one region per chunk
-    espic::Scratch chunk_counts;        // removed count per chunk (+ scanned offsets)
+    espic::Scratch chunk_counts;        // removed count per range
+    espic::Scratch range_offsets;       // their exclusive scan
     espic::Scratch dv_table;            // per-cell velocity kick for grids too large for smem
     espic::Scratch solve_ws;            // fp64 rows of the field solve
     espic::Scratch inject_ws;

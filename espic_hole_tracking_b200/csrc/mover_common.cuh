@@ -36,6 +36,7 @@ struct MoveArgs {
     int prefetch_units;  // L2 prefetch distance along a warp's stream, in 256-slot units
     int staged;          // 1: units are staged through shared memory with cp.async, one unit ahead
     int tile_bytes;      // size of the grid tables in shared memory (the staging ring follows them)
+    int strided;         // experiment: units dealt round-robin to the warps instead of in contiguous ranges
     int* seg_counter;    // windowed kernel: next segment to hand out (reset by k_finish)
     int n_segments;      // windowed kernel: segments of 32 ranges each
 };

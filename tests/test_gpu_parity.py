@@ -95,6 +95,52 @@ def test_mover_multi_step(ops, cpu, n_cells, periodic):
         assert top_g[0] > sp.current_empty_slot[0]
 
 
+def test_mover_periodic_removal_order(ops, cpu):
+    """Periodic runs remove a particle only when a step carries it past 0.99 * (2 z_max) (ref
+    infMagSim_c.c:172): rare, but the freed slots must still reach the stack in ascending slot order.
+    The periodic mover deals its 256-slot units round-robin to the warps and stages removals per
+    unit; here ~2 % of the particles, spread over all units and over both the fast and the
+    generic path, are flung out over three steps."""
+    n_cells = 4096
+    grid = wl.make_grid(n_cells)
+    mask = np.zeros_like(grid)
+    phi = wl.smooth_potential(grid, amplitude=1.0)
+    dt = wl.timestep()
+    n = 1_500_000      # 5859 units: more units than mover warps (4736), so some warps own two
+    _, sp = wl.make_plasma(n, n_cells, seed=21, holes=0.01)
+    rng = np.random.default_rng(5)
+    flung = rng.choice(n, size=n // 50, replace=False)
+    sp.particles[1, flung] = (rng.random(len(flung)) * 8000.0 + 2000.0).astype(np.float32)   # 1.7 .. 8.7 per step
+    bg = wl.background_density(n, 1, n_cells)
+    c = sp.copy()
+    g = to_dev(sp, torch)
+    top_g, last_g = list(sp.current_empty_slot), list(sp.largest_index)
+    g_den = torch.zeros(len(grid), device="cuda")
+    d_ref = np.zeros_like(grid)
+    tops = [top_g[0]]
+    for step in range(3):
+        cpu.move_particles(grid, mask, phi, dt, sp.charge_to_mass, bg, c.largest_index, c.particles, d_ref,
+                           c.empty_slots, c.current_empty_slot, a_b=0.0, periodic_particles=True)
+        ops.move_particles(dev(grid), dev(mask), dev(phi), dt, sp.charge_to_mass, bg, last_g, g["particles"], g_den,
+                           g["empty_slots"], top_g, 0.0, periodic_particles=True)
+        assert top_g == c.current_empty_slot
+        tops.append(top_g[0])
+        assert_bits_equal(g["particles"].cpu().numpy(), c.particles, f"particles step {step}")
+        assert_bits_equal(g["empty_slots"].cpu().numpy()[:top_g[0] + 1], c.empty_slots[:top_g[0] + 1], "stack")
+        check_density(g_den.cpu().numpy(), d_ref, grid, c.particles[0, :n], bg, True)
+    assert tops[1] > tops[0] + 1000 and tops[3] > tops[1]
+    # a removal-free launch afterwards: the per-unit counters were left clean
+    phi0 = np.zeros_like(grid)
+    g["particles"][1].clamp_(-50.0, 50.0)
+    c.particles[1] = np.clip(c.particles[1], -50.0, 50.0)
+    cpu.move_particles(grid, mask, phi0, dt, sp.charge_to_mass, bg, c.largest_index, c.particles, d_ref,
+                       c.empty_slots, c.current_empty_slot, a_b=0.0, periodic_particles=True)
+    ops.move_particles(dev(grid), dev(mask), dev(phi0), dt, sp.charge_to_mass, bg, last_g, g["particles"], g_den,
+                       g["empty_slots"], top_g, 0.0, periodic_particles=True)
+    assert top_g == c.current_empty_slot and top_g[0] == tops[3]
+    assert_bits_equal(g["particles"].cpu().numpy(), c.particles, "particles, quiet step")
+
+
 @pytest.mark.parametrize("periodic", [False, True])
 def test_mover_scalar_path_and_device_scalars(ops, cpu, periodic):
     """Storage length not a multiple of 4 (no float4 path) + DeviceInt stack top / largest index."""
