@@ -200,6 +200,7 @@ struct TeamShared {
     Aff aff_warp[32];
     Mat2 mat_tot[2][kMaxTeam];
     Aff aff_tot[2][kMaxTeam];
+    Aff aff_warps[2][32];           // the CTA's warp composites, in scan order (team_scan_aff)
     double bcast[2][2];
     double sum[2][kMaxTeam];
     double red[32];
@@ -240,6 +241,51 @@ __device__ __forceinline__ T team_exclusive_scan(const Team& tm, TeamShared& sh,
         for (int r = tm.size - 1; r > tm.rank; --r) pre = compose(tot[r], pre);
     }
     return compose(res, pre);
+}
+
+// Exclusive scan of affine maps over the team with one CTA barrier and one cluster barrier: every
+// warp scans its lanes with shuffles and posts its composite; after the CTA barrier every warp
+// scans the 32 posted composites for itself (no second barrier), one warp writes the CTA's total
+// into every CTA's table (8 DSMEM stores per CTA -- remote stores are slow, ~50 ns each: posting all
+// 256 warp composites to every CTA instead cost 7 us per scan), and after the cluster barrier the
+// totals of the CTAs before this one are folded in.  reverse: the same in descending team-thread
+// order (lanes, warps and CTAs mirrored), for the back substitution.  Advances `phase`.
+__device__ __forceinline__ Aff team_scan_aff(const Team& tm, TeamShared& sh, Aff mine, int& phase, bool reverse) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int vlane = reverse ? 31 - lane : lane;  // positions in scan order
+    const int vwarp = reverse ? 31 - w : w;
+    const int vrank = reverse ? tm.size - 1 - tm.rank : tm.rank;
+    const int par = phase & 1;
+    ++phase;
+    Aff incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int src = reverse ? lane + d : lane - d;
+        const Aff other{__shfl_sync(0xffffffffu, incl.A, src & 31), __shfl_sync(0xffffffffu, incl.B, src & 31)};
+        if (vlane >= d) incl = compose(incl, other);
+    }
+    if (vlane == 31) sh.aff_warps[par][vwarp] = incl;
+    __syncthreads();
+    Aff warps = sh.aff_warps[par][lane];  // inclusive scan of the 32 warp composites, redundantly per warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Aff other{__shfl_up_sync(0xffffffffu, warps.A, d), __shfl_up_sync(0xffffffffu, warps.B, d)};
+        if (lane >= d) warps = compose(warps, other);
+    }
+    Aff before{__shfl_sync(0xffffffffu, warps.A, (vwarp - 1) & 31), __shfl_sync(0xffffffffu, warps.B, (vwarp - 1) & 31)};
+    if (vwarp == 0) before = aff_identity();
+    if (tm.size > 1) {
+        const Aff cta{__shfl_sync(0xffffffffu, warps.A, 31), __shfl_sync(0xffffffffu, warps.B, 31)};
+        if (w == 0 && lane < tm.size) remote(&sh.aff_tot[par][0], lane)[vrank] = cta;
+        cg::this_cluster().sync();
+        Aff ctas = aff_identity();  // the CTAs before this one, earliest applied first
+        for (int r = 0; r < vrank; ++r) ctas = compose(sh.aff_tot[par][r], ctas);
+        before = compose(before, ctas);
+    }
+    const int prev = reverse ? lane + 1 : lane - 1;
+    Aff excl{__shfl_sync(0xffffffffu, incl.A, prev & 31), __shfl_sync(0xffffffffu, incl.B, prev & 31)};
+    if (vlane == 0) excl = aff_identity();
+    return compose(excl, before);
 }
 
 // Sum over the team, CTAs added in rank order (deterministic).  Advances `phase`.
@@ -465,7 +511,7 @@ __device__ __forceinline__ void forward_sweep(const Team& tm, TeamShared& sh, in
     }
     if (tm.T == 0) team_publish(tm, sh, phase, 0, y(0));
     const int par = phase & 1;
-    const Aff pre = team_exclusive_scan(tm, sh, comp, aff_identity(), phase, false);
+    const Aff pre = team_scan_aff(tm, sh, comp, phase, false);
     double prev = pre.A * sh.bcast[par][0] + pre.B;
 #pragma unroll 8
     for (int i = 0; i < m; ++i) {
@@ -477,13 +523,12 @@ __device__ __forceinline__ void forward_sweep(const Team& tm, TeamShared& sh, in
             y(i) = r;
         }
     }
-    __syncthreads();
 }
 
 // in place: z[j] -= z[j+1]*bwd[j], j = n-2..0.  The scan runs in REVERSE team-thread order.
 __device__ __forceinline__ void backward_sweep(const Team& tm, TeamShared& sh, int& phase, const Plane& z,
-                                               const Plane& bwd, int n, int m, double* s_edge) {
-    const int t = threadIdx.x, j0 = tm.T * m;
+                                               const Plane& bwd, int n, int m) {
+    const int j0 = tm.T * m;
     Aff comp = aff_identity();
 #pragma unroll 8
     for (int i = m - 1; i >= 0; --i) {
@@ -494,22 +539,12 @@ __device__ __forceinline__ void backward_sweep(const Team& tm, TeamShared& sh, i
         comp.A = on ? next.A : comp.A;
         comp.B = on ? next.B : comp.B;
     }
-    // reverse-order exclusive scan: hand the composite to the mirrored thread, scan, hand back
-    Aff* s_rev = reinterpret_cast<Aff*>(s_edge);
-    __syncthreads();
-    s_rev[kSolveThreads - 1 - t] = comp;
-    __syncthreads();
-    const Aff mine_rev = s_rev[t];
-    __syncthreads();
     {
         const int Tl = (n - 1) / m, il = (n - 1) - Tl * m;  // owner of row n-1
         if (tm.T == Tl) team_publish(tm, sh, phase, 0, z(il));
     }
     const int par = phase & 1;
-    const Aff pre_rev = team_exclusive_scan(tm, sh, mine_rev, aff_identity(), phase, true);
-    s_rev[kSolveThreads - 1 - t] = pre_rev;
-    __syncthreads();
-    const Aff pre = s_rev[t];
+    const Aff pre = team_scan_aff(tm, sh, comp, phase, true);
     double next = pre.A * sh.bcast[par][0] + pre.B;
 #pragma unroll 8
     for (int i = m - 1; i >= 0; --i) {
@@ -521,7 +556,6 @@ __device__ __forceinline__ void backward_sweep(const Team& tm, TeamShared& sh, i
             z(i) = r;
         }
     }
-    __syncthreads();
 }
 
 // Workspace (doubles): [header 16] then planes of m*Tn: low, dg, sup, D, D2 (scratch of the
@@ -531,6 +565,90 @@ __device__ __forceinline__ void backward_sweep(const Team& tm, TeamShared& sh, i
 // driver step of every configuration -- so it is computed on the first call, recorded under that
 // key in the header, and later calls go straight to the two sweeps.  Both routes end in the
 // same sweeps over the same planes, so a cached and an uncached call return identical bits.
+struct FactorPlanes {
+    Plane low, dg, sup, D, D2, fwd, bwd, inv, wq;
+};
+
+// First call for a matrix (and every call whose matrix is not cacheable): rows, eliminated diagonal,
+// multiplier planes, periodic correction vector.  Kept out of line so that the per-step path of
+// k_poisson stays short and contiguous in the instruction cache.
+__device__ __noinline__ void factorise(const SolveArgs& a, const RowConsts& k, const Team& tm, TeamShared& sh,
+                                       int& phase, const float* charge, const FactorPlanes& P, double* hdr, int m,
+                                       bool cacheable, double* s_edge, int& bad_mask) {
+    const int n = a.n, tid = threadIdx.x;
+    const Plane &low = P.low, &dg = P.dg, &sup = P.sup, &D = P.D, &D2 = P.D2, &fwd = P.fwd, &bwd = P.bwd, &inv = P.inv,
+                &wq = P.wq;
+    // ---- factorisation: rows (ref :385-503), eliminated diagonal (ref :343-349), multipliers
+    for (int i = 0; i < m; ++i) {
+        const int j = tm.T * m + i;
+        if (j >= n) break;
+        double r_low, r_dg, r_sup, r_rhs;
+        build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
+        low(i) = r_low;
+        dg(i) = r_dg;
+        sup(i) = r_sup;
+    }
+    __syncthreads();
+    eliminate_diagonal(tm, sh, phase, dg, low, sup, D, n, m, s_edge);
+    make_multipliers(tm, low, sup, D, fwd, bwd, inv, n, m, s_edge);
+    if (a.periodic) {  // ref :504-507: the second solve re-eliminates the eliminated diagonal (quirk 1)
+        eliminate_diagonal(tm, sh, phase, D, low, sup, D2, n, m, s_edge);
+        // w = "solve" of u = e_{n-1} on that matrix: the forward sweep leaves u unchanged, the
+        // backward sweep and the final division act.  dg / low are free now: scratch for them.
+        const Plane bwd2 = dg, wz = low;
+        {
+            const int j0 = tm.T * m;
+            s_edge[kSolveThreads + tid] = (j0 < n) ? D2(0) : 1.;
+            team_sync(tm);
+            const double D_after = next_thread_value(tm, s_edge + kSolveThreads, 1.);
+            for (int i = 0; i < m; ++i) {
+                const int j = j0 + i;
+                if (j >= n) break;
+                const double Dn = (i == m - 1) ? D_after : D2(i + 1);
+                const double sp = sup(i);
+                bwd2(i) = (j <= n - 2) ? sp / Dn : 0.;
+            }
+            for (int i = 0; i < m; ++i) {
+                const int j = j0 + i;
+                if (j < n) wz(i) = (j == n - 1) ? 1. : 0.;
+            }
+            team_sync(tm);
+        }
+        backward_sweep(tm, sh, phase, wz, bwd2, n, m);
+        for (int i = 0; i < m; ++i)
+            if (tm.T * m + i < n) wq(i) = wz(i) / D2(i);
+        __syncthreads();
+    }
+    if (tm.T == 0 && cacheable) {
+        hdr[1] = (double)__ldg(a.grid);
+        hdr[2] = (double)__ldg(a.grid + n - 1);
+        hdr[3] = (double)a.debye;
+        hdr[4] = (double)n;
+        hdr[5] = (double)a.periodic;
+        hdr[6] = (double)tm.size;
+        __threadfence();
+        reinterpret_cast<unsigned long long*>(hdr)[0] = kFactorMagic;
+    } else if (tm.T == 0) {
+        reinterpret_cast<unsigned long long*>(hdr)[0] = 0ull;  // the planes no longer match any key
+    }
+}
+
+// Right-hand side through the full row builder (object rows blended in, Boltzmann electrons).
+__device__ __noinline__ void rhs_general(const SolveArgs& a, const RowConsts& k, const Team& tm, const float* charge,
+                                         const Plane& y, int m, int& bad_mask) {
+    for (int i = 0; i < m; ++i) {
+        const int j = min(tm.T * m + i, a.n - 1);
+        double r_low, r_dg, r_sup, r_rhs;
+        build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
+        y(i) = r_rhs;
+    }
+}
+
+// ONE_ROW: every team thread owns exactly one row (n <= Tn; the 4097-point grid on 8 CTAs).  The
+// run loops collapse at compile time, which keeps the executed path short: the kernel starts with a
+// cold instruction cache every step (the movers in between evict it), and the general variant,
+// whose sweeps are unrolled for long runs, spent 40 % of its 23 us waiting for instructions.
+template <bool ONE_ROW>
 __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];  // y plane when it fits (m <= kSolveSmemRows)
     __shared__ TeamShared sh;
@@ -540,7 +658,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     const Team tm = make_team();
     int phase = 0;
     const int n = a.n, tid = threadIdx.x;
-    const int m = (n + tm.Tn - 1) / tm.Tn;
+    const int m = ONE_ROW ? 1 : (n + tm.Tn - 1) / tm.Tn;
     const size_t plane = (size_t)m * tm.Tn;
     double* hdr = a.ws;
     double* base = a.ws + kHeaderDoubles;
@@ -549,6 +667,18 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         bwd{base + 6 * plane, tm.Tn, tm.T}, inv{base + 7 * plane, tm.Tn, tm.T}, wq{base + 8 * plane, tm.Tn, tm.T};
     const Plane y = (m <= kSolveSmemRows) ? Plane{reinterpret_cast<double*>(smem_raw), kSolveThreads, tid}
                                           : Plane{base + 9 * plane, tm.Tn, tm.T};
+
+    // The factorisation planes were last touched a whole step ago and the movers have streamed
+    // gigabytes through L2 since: start pulling this thread's elements back in now, so that the
+    // sweeps below meet L2 hits instead of one DRAM round trip per dependent load.
+    if ((tid & 15) == 0) {  // one request per 128-byte line
+        for (int i = 0; i < m; ++i) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&fwd(i)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&bwd(i)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&inv(i)));
+            if (a.periodic) asm volatile("prefetch.global.L2 [%0];" ::"l"(&wq(i)));
+        }
+    }
 
     // ---- multi-GPU: the all-reduce of the two density grids (ref infMagSim_script.py:763, 773),
     // done by every rank for itself over NVLink peer memory.  Ranks are summed in rank order,
@@ -580,14 +710,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             a.ion[j] = si;
             a.ele[j] = se;
         }
-        __threadfence();
-        team_sync(tm);
+        team_sync(tm);  // the cluster barrier releases / acquires the global writes above
     }
 
     // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
-    const float* charge = a.charge;
-    if (a.ion) {
-        if (tid == 0) {  // every CTA works the fixed end values out for itself; CTA 0 stores them
+    const RowConsts k = row_consts(a);
+    const bool cacheable = (a.transparency == 1.f) && !a.boltzmann;
+    if (tid == 0) {
+        if (a.ion) {  // every CTA works the fixed end values out for itself; CTA 0 stores them
             float i0 = a.ion[0], i1 = a.ion[n - 1], e0 = a.ele[0], e1 = a.ele[n - 1];
             if (a.fold_ends) {
                 if (a.fix_i) { i0 = __fadd_rn(i0, i1); i1 = i0; }
@@ -598,98 +728,49 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             }
             s_end[0] = i0; s_end[1] = i1; s_end[2] = e0; s_end[3] = e1;
         }
-        team_sync(tm);  // every CTA has read the raw end values
-        if (tm.T == 0) {
-            a.ion[0] = s_end[0]; a.ion[n - 1] = s_end[1]; a.ele[0] = s_end[2]; a.ele[n - 1] = s_end[3];
-        }
-        for (int j = tm.T; j < n; j += tm.Tn) {
-            const float x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : a.ion[j];
-            const float yv = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
-            a.charge_out[j] = __fsub_rn(x, yv);
-        }
-        charge = a.charge_out;
-        __threadfence();
-    }
-
-    const RowConsts k = row_consts(a);
-    const bool cacheable = (a.transparency == 1.f) && !a.boltzmann;
-    if (tid == 0) {
         const unsigned long long* h = reinterpret_cast<const unsigned long long*>(hdr);
         s_cached = cacheable && h[0] == kFactorMagic && hdr[1] == (double)__ldg(a.grid) &&
                    hdr[2] == (double)__ldg(a.grid + n - 1) && hdr[3] == (double)a.debye && hdr[4] == (double)n &&
                    hdr[5] == (double)a.periodic && hdr[6] == (double)tm.size;
     }
-    team_sync(tm);  // also orders the prologue's charge_out writes before the reads below
-    int bad_mask = 0;
-
-    if (!s_cached) {
-        // ---- factorisation: rows (ref :385-503), eliminated diagonal (ref :343-349), multipliers
+    team_sync(tm);  // every CTA has read the raw end values and the workspace key
+    const float* charge = a.charge;
+    if (a.ion) {
+        if (tm.T == 0) {
+            a.ion[0] = s_end[0]; a.ion[n - 1] = s_end[1]; a.ele[0] = s_end[2]; a.ele[n - 1] = s_end[3];
+        }
+        // each thread makes the charge of its own rows: nobody else reads them in this kernel
         for (int i = 0; i < m; ++i) {
             const int j = tm.T * m + i;
             if (j >= n) break;
-            double r_low, r_dg, r_sup, r_rhs;
-            build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
-            low(i) = r_low;
-            dg(i) = r_dg;
-            sup(i) = r_sup;
+            const float x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : a.ion[j];
+            const float yv = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
+            a.charge_out[j] = __fsub_rn(x, yv);
         }
-        __syncthreads();
-        eliminate_diagonal(tm, sh, phase, dg, low, sup, D, n, m, s_edge);
-        make_multipliers(tm, low, sup, D, fwd, bwd, inv, n, m, s_edge);
-        if (a.periodic) {  // ref :504-507: the second solve re-eliminates the eliminated diagonal (quirk 1)
-            eliminate_diagonal(tm, sh, phase, D, low, sup, D2, n, m, s_edge);
-            // w = "solve" of u = e_{n-1} on that matrix: the forward sweep leaves u unchanged, the
-            // backward sweep and the final division act.  dg / low are free now: scratch for them.
-            const Plane bwd2 = dg, wz = low;
-            {
-                const int j0 = tm.T * m;
-                s_edge[kSolveThreads + tid] = (j0 < n) ? D2(0) : 1.;
-                team_sync(tm);
-                const double D_after = next_thread_value(tm, s_edge + kSolveThreads, 1.);
-                for (int i = 0; i < m; ++i) {
-                    const int j = j0 + i;
-                    if (j >= n) break;
-                    const double Dn = (i == m - 1) ? D_after : D2(i + 1);
-                    const double sp = sup(i);
-                    bwd2(i) = (j <= n - 2) ? sp / Dn : 0.;
-                }
-                for (int i = 0; i < m; ++i) {
-                    const int j = j0 + i;
-                    if (j < n) wz(i) = (j == n - 1) ? 1. : 0.;
-                }
-                team_sync(tm);
-            }
-            backward_sweep(tm, sh, phase, wz, bwd2, n, m, s_edge);
-            for (int i = 0; i < m; ++i)
-                if (tm.T * m + i < n) wq(i) = wz(i) / D2(i);
-            __syncthreads();
-        }
-        if (tm.T == 0 && cacheable) {
-            hdr[1] = (double)__ldg(a.grid);
-            hdr[2] = (double)__ldg(a.grid + n - 1);
-            hdr[3] = (double)a.debye;
-            hdr[4] = (double)n;
-            hdr[5] = (double)a.periodic;
-            hdr[6] = (double)tm.size;
-            __threadfence();
-            reinterpret_cast<unsigned long long*>(hdr)[0] = kFactorMagic;
-        } else if (tm.T == 0) {
-            reinterpret_cast<unsigned long long*>(hdr)[0] = 0ull;  // the planes no longer match any key
-        }
+        charge = a.charge_out;
     }
+    int bad_mask = 0;
+
+    if (!s_cached)
+        factorise(a, k, tm, sh, phase, charge, FactorPlanes{low, dg, sup, D, D2, fwd, bwd, inv, wq}, hdr, m, cacheable,
+                  s_edge, bad_mask);
 
     // ---- solve: right-hand side, forward and backward sweeps (ref :350-353), output (ref :518-525)
+    if (cacheable) {
+        // transparency 1, no Boltzmann term: the blend rhs*1 + rhs*0 of build_row is the plain row's
+        // right-hand side bit for bit (ref :392-395, :409, :428)
 #pragma unroll 4
-    for (int i = 0; i < m; ++i) {
-        const int j = min(tm.T * m + i, n - 1);  // rows past n: a copy of the last row, never used
-        double r_low, r_dg, r_sup, r_rhs;
-        build_row(a, k, charge, j, r_low, r_dg, r_sup, r_rhs, bad_mask);
-        y(i) = r_rhs;
+        for (int i = 0; i < m; ++i) {
+            const int j = min(tm.T * m + i, n - 1);  // rows past n: a copy of the last row, never used
+            y(i) = (j == 0 || j == n - 1) ? 0. : (double)charge[j] * (double)k.rhs_scale;
+        }
+    } else {
+        rhs_general(a, k, tm, charge, y, m, bad_mask);
     }
     if (bad_mask) atomicOr(a.status, ESPIC_ST_BAD_OBJECT_MASK);
     __syncthreads();
     forward_sweep(tm, sh, phase, y, fwd, n, m);
-    backward_sweep(tm, sh, phase, y, bwd, n, m, s_edge);
+    backward_sweep(tm, sh, phase, y, bwd, n, m);
     if (a.periodic) {  // ref :508-514, :518-523
         if (tm.T == 0) team_publish(tm, sh, phase, 1, y(0) * inv(0));
         const int par = phase & 1;
@@ -758,7 +839,9 @@ static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
     static bool configured = false;
     static int max_team = kMaxTeam;
     if (!configured) {  // static (19 KB) + dynamic (up to 128 KB) exceeds the 48 KB default
-        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSolveSmemRows * kSolveThreads * 8));
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kSolveSmemRows * kSolveThreads * 8));
         if (const char* e = getenv("ESPIC_SOLVE_TEAM")) {  // tuning knob: largest cluster to use
             const int t = atoi(e);
@@ -778,7 +861,7 @@ static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
             probe.attrs = pa;
             probe.numAttrs = 1;
             int clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&clusters, k_poisson, &probe) == cudaSuccess && clusters >= 1) break;
+            if (cudaOccupancyMaxActiveClusters(&clusters, k_poisson<false>, &probe) == cudaSuccess && clusters >= 1) break;
             cudaGetLastError();
             max_team /= 2;
         }
@@ -805,7 +888,8 @@ static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ESPIC_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_poisson, a));
+    if (m == 1) ESPIC_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_poisson<true>, a));
+    else ESPIC_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_poisson<false>, a));
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_poisson launch");
 }
