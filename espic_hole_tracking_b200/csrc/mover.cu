@@ -19,15 +19,21 @@
 // The tile is flushed once per CTA with 64-bit global reductions into ctx->acc; k_finish
 // converts to the float density the reference's callers expect.
 //
-// Removal (non-periodic walls, absorbing object) must reproduce the reference's sequential
-// stack pushes: slots appear on the stack in ascending slot order.  Each warp owns whole
-// chunks of 4096 consecutive slots, compacts the removed slot ids of a chunk in order with
-// ballots into that chunk's staging region, and records the count; k_finish scans the counts
-// (one CTA) and k_scatter copies the staged ids to their final stack positions.
+// Work split: the store is cut into units of 256 consecutive slots.  The wall variant gives every
+// warp of the persistent grid (148 CTAs x 32 warps) one contiguous, ascending range of units;
+// the periodic variant deals the units round-robin (warp w: units w, w+4736, ...), which keeps
+// the whole grid on one contiguous stretch of the store at any moment (DRAM page locality).
 //
-// Grids too large for the shared-memory tables (more than ~19k points) use the same kernel
-// with the kick table in global memory (L1/L2-resident) and 64-bit global reductions for
-// the deposit.
+// Removal (walls, absorbing object; in periodic runs only a particle flung past 0.99*2*z_max)
+// must reproduce the reference's sequential stack pushes: slots appear on the stack in
+// ascending slot order.  A range -- a warp's range of units, or a single unit in the
+// round-robin split -- compacts its removed slot ids in order with ballots into the staging
+// region behind its first slot and records the count; k_finish scans the counts (skipped when
+// nothing was removed) and k_scatter copies the staged ids to their final stack positions.
+//
+// Grids too large for the shared-memory tables (more than ~19k points) are moved by
+// k_move_win (mover_win.cu); start-up calls on such grids use this kernel with the kick table
+// in global memory (k_build_dv) and 64-bit global reductions for the deposit.
 #include <cstdio>
 #include <cstdlib>
 
@@ -36,8 +42,8 @@
 namespace espic {
 
 
-// FAST: interior chunks run the register fast path on float4 quads; everything else (the last
-// chunk of the store, unaligned stores, start-up calls with update_position=0, an absorbing
+// FAST: complete units run the register fast path on float4 quads; everything else (the slots behind the last
+// complete unit, unaligned stores, start-up calls with update_position=0, an absorbing
 // object, exotic dz) goes quad by quad through quad_generic.
 template <bool PERIODIC, bool SMEM, bool STRIDED>
 __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
