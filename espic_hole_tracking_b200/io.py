@@ -68,9 +68,13 @@ class Recorder:
         centers = lambda lo, hi: np.float32(np.linspace(lo + (hi - lo) / 200., hi - (hi - lo) / 200., 100))
         vi, ve = 20. * sim.v_th_i, 4. * sim.v_th_e
         hole = sim.hole_relative_positions.cpu().numpy()
-        box = np.full(c.n_steps + 1, sim.v_b, np.float32)
-        hole_vel = np.zeros_like(hole)
-        hole_vel[1:] = (hole[1:] - hole[:-1]) / np.float32(sim.dt) + box[1:len(hole)]          # :917
+        ctrl = sim.ctrl
+        pad = lambda a, n: np.concatenate([a, np.zeros(a.shape[:-1] + (max(0, n - a.shape[-1]),), a.dtype)], axis=-1)[..., :n]
+        box = pad(ctrl.box[0], c.n_steps + 1)
+        if c.moving_box_simulation:
+            hole_vel = pad(ctrl.hole_velocities, len(hole))                                     # :917, kept by the controller
+        else:   # the same formula from the stored positions (no per-step host read-back in this mode)
+            hole_vel = ((hole - np.roll(hole, 1)).astype(np.float64) / sim.dt + box[:len(hole)]).astype(np.float32)
         path = os.path.join(directory, self.filename_base())
         np.savez(path, grid=sim.grid.cpu().numpy(), times=f32(self.times), object_masks=zeros_grid,
                  potentials=f32(self.potentials), potentials_electrons=f32(self.potentials), electric_fields=zeros_grid,
@@ -83,7 +87,7 @@ class Recorder:
                  trapped_electron_distribution_functions=f32(self.histograms["electrons_inject0"]),
                  background_ion_density=sim.background_density, background_electron_density=sim.background_density,
                  box_velocities=box, hole_relative_positions=hole, hole_velocities=hole_vel,
-                 ions_vel=np.zeros((2, c.n_steps + 1), np.float32))
+                 ions_vel=pad(ctrl.ions_extra, c.n_steps + 1))
         return path + ".npz"
 
 
@@ -94,7 +98,10 @@ def save_checkpoint(sim, path: str) -> None:
     state = {"k": sim.k, "t": sim.t, "cfg": dict(sim.cfg.__dict__), "rank": sim.rank, "world": sim.world,
              "potential": sim.potential.cpu(), "densities": sim.densities.cpu(), "charge": sim.charge_density.cpu(),
              "hole": sim.hole_relative_positions.cpu(), "host_rng": sim.host_rng.get_state(),
-             "rng": (sim.ctx_rng_state() if hasattr(sim, "ctx_rng_state") else None)}
+             "rng": (sim.ctx_rng_state() if hasattr(sim, "ctx_rng_state") else None),
+             "ctrl": {"box": sim.ctrl.box.copy(), "ions_extra": sim.ctrl.ions_extra.copy(),
+                      "hole_velocities": sim.ctrl.hole_velocities.copy(),
+                      "filter_z": None if sim.ctrl.filter.z is None else sim.ctrl.filter.z.copy()}}
     den_i, den_e = sim._deposit_rows(sim.k)
     state["pending_densities"] = torch.stack([den_i, den_e]).cpu()
     for name, s in (("ions", sim.ions), ("electrons", sim.electrons)):
@@ -123,5 +130,10 @@ def load_checkpoint(sim, path: str) -> None:
             getattr(s, f).copy_(state[name][f])
         s.current_empty_slot[0] = state[name]["top"]
         s.largest_index[0] = state[name]["last"]
+    if "ctrl" in state:
+        sim.ctrl.box, sim.ctrl.ions_extra = state["ctrl"]["box"].copy(), state["ctrl"]["ions_extra"].copy()
+        sim.ctrl.hole_velocities = state["ctrl"]["hole_velocities"].copy()
+        sim.ctrl.filter.z = None if state["ctrl"]["filter_z"] is None else state["ctrl"]["filter_z"].copy()
+    sim._plan_sorting()   # sort intervals are derived from the configuration, not stored
     if sim.xch is not None:
         sim.xch.publish(sim.k, sim.k)

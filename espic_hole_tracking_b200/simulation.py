@@ -13,9 +13,12 @@ background_density = n*P*dz/(z_max-z_min) (:402, :510) and the only per-step exc
 sum all-reduce of the density grids (:763, :773), here ONE collective over the concatenated
 [2, n_points] ion+electron buffer.
 
-Out of scope: the moving-box controller and its filtfilt (:917-928; the
-reference default is moving_box_simulation=False, so the box velocity stays v_b_0 and a_b=0),
-the absorbing-object geometry helper (:192-246; object_mask stays zero as in every config),
+The moving-box controller (:917-928, off by default as in the reference) and the ion velocity
+offset of the background acceleration (:852-862) are host scalar bookkeeping, kept in
+``controller.BoxController``; with the controller on, a step reads the tracked hole position back
+(4 bytes) between the field solve and the pushes.
+
+Out of scope: the absorbing-object geometry helper (:192-246; object_mask stays zero as in every config),
 counter-streaming beams, Boltzmann/quasineutral/prescribed-potential modes, plotting and .npz
 output.
 """
@@ -29,6 +32,7 @@ import torch
 
 from . import distributed as dd
 from . import operators as ops
+from .controller import BoxController, PHASE2_POTENTIAL
 from ._lib import Context, Species, StepArgs
 
 
@@ -65,6 +69,7 @@ class SimConfig:
     time_steps_immobile_ions: int = 30000
     time_steps_immobile_electrons: int = 0
     create_electron_dimple: bool = True
+    moving_box_simulation: bool = False   # :141: a frame that follows the hole (controller.BoxController)
     debye_length: float = 0.125
     z_min: float = -3.0
     z_max: float = 3.0
@@ -198,8 +203,16 @@ class Simulation:
         self.t = 0.0
         self.sort_intervals = {"ions": 0, "electrons": 0}   # set by initialize() (_plan_sorting)
         self.sort_key_shift = 0
-        self.v_b = c.v_b_0     # box velocity (moving box disabled: constant), :730-736
+        self.v_b = c.v_b_0     # initial box velocity (:736); per step: self.ctrl.box
         self.a_b = 0.0
+        self.ctrl = BoxController(c.n_steps, self.dt, self.dz, c.step_size, self.v_th_e, c.debye_length,
+                                  v_b_0=c.v_b_0, moving_box=c.moving_box_simulation,
+                                  hole_tracking_end_step=c.hole_tracking_end_step,
+                                  background_acceleration=c.background_acceleration,
+                                  hole_pushing_start_step=c.hole_pushing_start_step,
+                                  hole_pushing_end_step=c.hole_pushing_end_step, n_points=self.n_points)
+        self.background_potential_phase2 = torch.linspace(PHASE2_POTENTIAL, 0., self.n_points, dtype=torch.float64
+                                                          ).to(torch.float32).to(self.device)         # :673
         self.hist = {}
 
     def _deposit_rows(self, k: int):
@@ -301,14 +314,15 @@ class Simulation:
         L = c.z_max - c.z_min
         growth = math.exp(max(0, k - c.density_growth_start_step) * c.density_growth_rate * c.step_size)
         w_ion = c.w_ion_perturbation * self.v_th_e / c.debye_length * math.sqrt(1. / c.mass_ratio)   # :663
-        e_i = expected_particle_injection(c.n_particles / L, self.v_th_i / math.sqrt(c.sigma), self.v_b - c.v_d_i,
-                                          self.dt)
+        v_flux = self.ctrl.injection_flux_velocity(k)                                             # box[0,k+1]
+        e_i = expected_particle_injection(c.n_particles / L, self.v_th_i / math.sqrt(c.sigma),
+                                          v_flux + float(self.ctrl.ions_extra[0, k]) - c.v_d_i, self.dt)
         e_i *= (1 - c.amplitude_perturbation * math.sin(max(0, k - c.hole_tracking_end_step) * self.dt * w_ion))
         e_i *= growth
         n_i = int(e_i)
         if (e_i - n_i) > self.host_rng.rand():
             n_i += 1
-        e_e = expected_particle_injection(c.n_particles / L, self.v_th_e, self.v_b, self.dt) * growth
+        e_e = expected_particle_injection(c.n_particles / L, self.v_th_e, v_flux, self.dt) * growth
         n_e = int(e_e)
         if (e_e - n_e) > self.host_rng.rand():
             n_e += 1
@@ -348,8 +362,14 @@ class Simulation:
         periodic = c.periodic_particles
         self.reduce_densities()
         ions_mobile = k <= c.time_steps_immobile_ions                                            # :929-939
-        ramp = self.set_background_acceleration and c.hole_pushing_start_step <= k < c.hole_pushing_end_step
-        if not ramp and not c.phase_space_histograms:
+        ramp = self.ctrl.background_phase(k)          # 0, 1 (input-file ramp) or 2 (:852-862); advances ions_extra
+        moving = c.moving_box_simulation
+        if not moving:
+            self.ctrl.update_frozen(k)                # box[0,k+1] = box[0,k], box[1,k] = 0 (:926-928)
+        a_b = self.ctrl.a_b(k)
+        v_inj = self.ctrl.injection_velocity(k)       # (box[0,k] + box[0,k+1]) / 2 (:998, :1017)
+        v_inj_ions = v_inj + float(self.ctrl.ions_extra[0, k]) - c.v_d_i
+        if not ramp and not moving and not c.phase_space_histograms:
             # field solve + both pushes as one host call (espic_pic_step); same kernels, same order
             a = self._step_args()
             if self.xch is not None:   # densities entering step k: slot k&1 of every rank; pushes fill slot (k+1)&1
@@ -360,7 +380,7 @@ class Simulation:
                 a.reduced_electron_density = self.electron_density.data_ptr()
             else:
                 a.exchange_parity = -1
-            a.a_b = self.a_b
+            a.a_b = a_b
             a.fix_ions = int(periodic or k <= c.time_steps_immobile_ions)
             a.fix_electrons = 1
             a.ions.dt = self.dt if ions_mobile else 0.
@@ -370,7 +390,7 @@ class Simulation:
             device_inject = (not periodic) and isinstance(self.sampler, DeviceUniformSampler) and ions_mobile
             if device_inject:   # counts on the host (:965-975, 1005-1009), everything else in the same host call
                 a.n_inject_ions, a.n_inject_electrons = self.injection_counts(k)
-                a.v_d_ions, a.v_d_electrons = self.v_b - c.v_d_i, self.v_b
+                a.v_d_ions, a.v_d_electrons = v_inj_ions, v_inj
                 a.step_index, a.inject_dt = k, self.dt
             else:
                 a.n_inject_ions = a.n_inject_electrons = 0
@@ -378,8 +398,12 @@ class Simulation:
             self.ctx.check(self.ctx._lib.espic_pic_step(self.ctx.handle, a), "espic_pic_step")
             done_tracking, done_inject = True, device_inject
         else:
-            self._step_operator_by_operator(k, ions_mobile, ramp)
-            done_tracking = done_inject = False
+            done_tracking = self._step_operator_by_operator(k, ions_mobile, ramp)
+            done_inject = False
+            if moving:   # the control law ran inside: these are the values of step k now
+                a_b = self.ctrl.a_b(k)
+                v_inj = self.ctrl.injection_velocity(k)
+                v_inj_ions = v_inj + float(self.ctrl.ions_extra[0, k]) - c.v_d_i
         den_i, den_e = self._deposit_rows(k + 1)
         if not ions_mobile:
             den_i.fill_(1.0)   # :934 (every rank sets ones; the next all-reduce sums them, as in the reference)
@@ -392,13 +416,14 @@ class Simulation:
             if n_i > 0 and ions_mobile:                                                          # :986-1000
                 s = self.ions
                 ops.inject_particles(n_i, self.grid, self.dt, self.v_th_i / math.sqrt(c.sigma),
-                                     self.background_density, self.sampler, self.v_b - c.v_d_i, self.a_b, k,
+                                     self.background_density, self.sampler, v_inj_ions,
+                                     a_b + float(self.ctrl.ions_extra[1, k]), k,
                                      s.tags, s.particles, s.empty_slots, s.current_empty_slot, s.largest_index,
                                      den_i, ctx=self.ctx)
             if n_e > 0:                                                                          # :1015-1019
                 s = self.electrons
                 ops.inject_particles(n_e, self.grid, self.dt, self.v_th_e, self.background_density, self.sampler,
-                                     self.v_b, self.a_b, k, s.tags, s.particles, s.empty_slots,
+                                     v_inj, a_b, k, s.tags, s.particles, s.empty_slots,
                                      s.current_empty_slot, s.largest_index, den_e, ctx=self.ctx)
         if self.xch is not None:
             self.xch.publish(k + 1, k + 1)
@@ -408,9 +433,10 @@ class Simulation:
             if every and self.k % every == 0:
                 self.sort_particles((n,), key_shift=self.sort_key_shift, lookahead_steps=0.5 * every)
 
-    def _step_operator_by_operator(self, k: int, ions_mobile: bool, ramp: bool) -> None:
+    def _step_operator_by_operator(self, k: int, ions_mobile: bool, ramp: int) -> bool:
         """The same step through the individual operators, in the reference's order (used when the
-        ion potential carries the background ramp or the per-step histograms are on)."""
+        ion potential carries a background ramp, the moving-box controller is on or the per-step
+        histograms are wanted).  Returns whether the hole position of this step has been tracked."""
         c = self.cfg
         periodic = c.periodic_particles
         fix_ions = periodic or k <= c.time_steps_immobile_ions
@@ -427,21 +453,39 @@ class Simulation:
                             object_transparency=1., boltzmann_electrons=False, periodic_particles=periodic,
                             periodic_potential=self.periodic_potential, fix_ions=fix_ions, fix_electrons=True,
                             ctx=self.ctx)                                                      # :763-779, 807, 831-836
+        tracked = False
+        if c.moving_box_simulation:
+            # the control law needs this step's hole position before the pushes (:896-897, 917-928): track
+            # now and read the two floats back -- the one host synchronisation per step of this mode
+            n_hist = self.hole_relative_positions.shape[0]
+            if c.track_hole and c.initial_transient_steps < k < n_hist:
+                ops.hole_position_tracking(self.potential, self.dz, c.debye_length * 4., self.grid, self.fine_mesh,
+                                           out=self.hole_relative_positions[k:k + 1], ctx=self.ctx)
+                tracked = True
+            pos = float(self.hole_relative_positions[k]) if k < n_hist else 0.0
+            prev = float(self.hole_relative_positions[k - 1]) if (k - 1) < n_hist else 0.0   # k = 0 reads the last (zero) entry
+            self.ctrl.update(k, pos, prev)
+        a_b = self.ctrl.a_b(k)
         den_i, den_e = self._deposit_rows(k + 1)
-        potential_ions = self.potential + self.background_potential if ramp else self.potential  # :852-864
+        potential_ions = self.potential                                                          # :852-864
+        if ramp == 1:
+            potential_ions = self.potential + self.background_potential
+        elif ramp == 2:
+            potential_ions = self.potential + self.background_potential_phase2
         if c.phase_space_histograms:
             self.phase_space()
         s = self.ions
         ops.move_particles(self.grid, self.object_mask, potential_ions, self.dt if ions_mobile else 0.,
                            s.charge_to_mass, self.background_density, s.largest_index, s.particles,
-                           den_i, s.empty_slots, s.current_empty_slot, self.a_b,
+                           den_i, s.empty_slots, s.current_empty_slot, a_b,
                            periodic_particles=periodic, use_pure_c_version=True, ctx=self.ctx)
         s = self.electrons
         ops.move_particles(self.grid, self.object_mask, self.potential,
                            0. if k < c.time_steps_immobile_electrons else self.dt, s.charge_to_mass,
                            self.background_density, s.largest_index, s.particles, den_e,
-                           s.empty_slots, s.current_empty_slot, self.a_b, periodic_particles=periodic,
+                           s.empty_slots, s.current_empty_slot, a_b, periodic_particles=periodic,
                            use_pure_c_version=True, ctx=self.ctx)                                # :940-950
+        return tracked
 
     def phase_space(self) -> None:
         """The three per-step 100x100 histograms (:865-895); results stay on the device."""

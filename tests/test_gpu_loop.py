@@ -267,3 +267,39 @@ def test_large_grid_auto_sort_is_physically_invisible(pkg, periodic):
         assert_bits_equal(a[i], b[i], what)
     for x, y in zip(a[3], b[3]):
         np.testing.assert_array_equal(x, y)
+
+
+def test_moving_box_controller_in_the_loop(pkg):
+    """moving_box_simulation=True (off in the reference's defaults, infMagSim_script.py:141): the
+    control law runs on the host between the field solve and the pushes of every step.  Fed the hole
+    positions the run itself tracked, the reference's own loop (:917-928, scipy filtfilt over the
+    whole history each step) must reproduce the box velocities and accelerations the run used."""
+    from espic_hole_tracking_b200.simulation import SimConfig, Simulation
+    from tests.test_host_logic import _reference_box_loop
+    n_steps, end = 160, 150
+    cfg = SimConfig(n_steps=n_steps, n_particles=100_000, n_cells=512, periodic_particles=False, track_hole=True,
+                    moving_box_simulation=True, hole_tracking_end_step=end, v_b_0=0.25)
+    sim = Simulation(cfg)
+    sim.init_synthetic()
+    sim.initialize()
+    sim.run(n_steps)
+    # a synthetic start has no settled hole yet: the tracked position jumps about, the law answers with
+    # large accelerations, and a few injected particles can land outside the box ("bad left_index",
+    # infMagSim_cython.py:272-273) exactly as they would in the reference; nothing else may be flagged
+    assert sim.ctx.status() & ~8 == 0
+    pos = sim.hole_relative_positions.cpu().numpy()
+    assert np.all(pos[:81] == 0) and np.abs(pos[81:]).max() > 0
+    want_box, want_hv = _reference_box_loop(pos, sim.dt, 0.25, cfg.step_size, sim.v_th_e, cfg.debye_length, end)
+    np.testing.assert_allclose(sim.ctrl.hole_velocities[:n_steps], want_hv, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(sim.ctrl.box[:, :n_steps + 1], want_box, rtol=2e-6, atol=1e-5 * np.abs(want_box).max())
+    assert np.abs(sim.ctrl.box[1, 101:end]).max() > 0          # the frame did accelerate ...
+    assert np.all(sim.ctrl.box[1, :101] == 0) and np.all(sim.ctrl.box[1, end:] == 0)   # ... only while tracking
+    act = sim.n_active()
+    assert abs(act["electrons"] - 100_000) < 20_000 and abs(act["ions"] - 100_000) < 20_000
+    # same configuration with the controller off: frame at rest, and no host read-back was needed
+    cfg2 = SimConfig(n_steps=40, n_particles=100_000, n_cells=512, periodic_particles=False, track_hole=True, v_b_0=0.25)
+    sim2 = Simulation(cfg2)
+    sim2.init_synthetic()
+    sim2.initialize()
+    sim2.run(40)
+    assert np.all(sim2.ctrl.box[0] == np.float32(0.25)) and not sim2.ctrl.box[1].any()
