@@ -7,26 +7,45 @@
 namespace espic {
 
 // tanh(s)/cosh(s) with one exponential: with e = exp(-|s|),
-// tanh = (1-e^2)/(1+e^2), 1/cosh = 2e/(1+e^2).
-__device__ __forceinline__ double tanh_over_cosh(double s) {
-    const double e = exp(-fabs(s));
-    const double e2 = e * e;
-    const double den = 1. + e2;
-    const double r = 2. * e * (1. - e2) / (den * den);
-    return s < 0. ? -r : r;
+// tanh = (1-e^2)/(1+e^2), 1/cosh = 2e/(1+e^2).  Single precision with the hardware exponential
+// and reciprocal: ~3e-7 relative, two orders below the rounding noise of the reference's own
+// float accumulation over n_points terms (ref infMagSim_c.c:676-680), so the maximum it feeds
+// lands on the same fine-mesh point.
+__device__ __forceinline__ float tanh_over_cosh(float s) {
+    const float e = __expf(-fabsf(s));
+    const float e2 = e * e;
+    const float den = 1.f + e2;
+    const float r = __fdividef(2.f * e * (1.f - e2), den * den);
+    return copysignf(r, s);
 }
 
-// GRADIENT=false: data is used as given.  GRADIENT=true: data is a potential and the signal
-// is numpy's gradient of it in float32 (central differences, one-sided ends).
+constexpr int kFilterFine = 7;       // fine-mesh points per CTA: the 1001-point mesh makes 143 CTAs, one wave
+constexpr int kFilterThreads = 1024;
+
+// Res[i] = sum_j tanh((fine[i]-grid[j])/L) / cosh((fine[i]-grid[j])/L) * signal[j].
+// GRADIENT=false: data is the signal.  GRADIENT=true: data is a potential and the signal is
+// numpy's gradient of it in float32 (central differences, one-sided ends).
+// n_fine x n_points kernel evaluations (6.6e7 on the 65537-point grid, every step) bound by the
+// two special-function operations each costs: a CTA takes kFilterFine mesh points at once so that
+// grid and signal are loaded (and the gradient formed) once for all of them.  A thread sums its
+// n_points/1024 products in float (64 terms on the largest grid), the partial sums are reduced in
+// double.
 template <bool GRADIENT>
-__global__ void __launch_bounds__(256) k_field_filter(int n, const float* __restrict__ grid,
-                                                      const float* __restrict__ data, float div_mid,
-                                                      float div_end, float L, int n_fine,
-                                                      const float* __restrict__ fine, float* __restrict__ res) {
-    __shared__ double s_red[8];
-    for (int i = blockIdx.x; i < n_fine; i += gridDim.x) {
-        const float xf = fine[i];
-        double part = 0.;
+__global__ void __launch_bounds__(kFilterThreads) k_field_filter(int n, const float* __restrict__ grid,
+                                                                 const float* __restrict__ data, float div_mid,
+                                                                 float div_end, float L, int n_fine,
+                                                                 const float* __restrict__ fine,
+                                                                 float* __restrict__ res) {
+    __shared__ double s_red[kFilterFine][kFilterThreads / 32];
+    const float inv_L = 1.f / L;
+    const bool exact_inv = (inv_L * L == 1.f) && (__float_as_uint(L) & 0x007fffffu) == 0u;  // L a power of two
+    for (int i0 = blockIdx.x * kFilterFine; i0 < n_fine; i0 += gridDim.x * kFilterFine) {
+        float xf[kFilterFine], part[kFilterFine];
+#pragma unroll
+        for (int f = 0; f < kFilterFine; ++f) {
+            xf[f] = fine[min(i0 + f, n_fine - 1)];
+            part[f] = 0.f;
+        }
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             float sig;
             if (GRADIENT) {
@@ -36,17 +55,26 @@ __global__ void __launch_bounds__(256) k_field_filter(int n, const float* __rest
             } else {
                 sig = data[j];
             }
-            const double s = (double)__fdiv_rn(__fsub_rn(xf, grid[j]), L);
-            part += tanh_over_cosh(s) * (double)sig;
+            const float g = grid[j];
+#pragma unroll
+            for (int f = 0; f < kFilterFine; ++f) {
+                const float d = __fsub_rn(xf[f], g);
+                const float s = exact_inv ? d * inv_L : __fdiv_rn(d, L);   // ref :679, a float quotient
+                part[f] = fmaf(tanh_over_cosh(s), sig, part[f]);
+            }
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+        for (int f = 0; f < kFilterFine; ++f) {
+            double p = (double)part[f];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) p += __shfl_xor_sync(0xffffffffu, p, d);
+            if ((threadIdx.x & 31) == 0) s_red[f][threadIdx.x >> 5] = p;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < kFilterFine && i0 + (int)threadIdx.x < n_fine) {
             double t = 0.;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-            res[i] = (float)t;
+            for (int w = 0; w < kFilterThreads / 32; ++w) t += s_red[threadIdx.x][w];
+            res[i0 + threadIdx.x] = (float)t;
         }
         __syncthreads();
     }
@@ -120,7 +148,8 @@ __global__ void __launch_bounds__(256) k_histogram(const float* __restrict__ xs,
 int launch_field_filter(espic_ctx* ctx, int n_points, const float* grid, const float* data, float L,
                         int n_fine, const float* fine, float* res) {
     if (n_points < 1 || n_fine < 1) return 0;
-    k_field_filter<false><<<n_fine < 4 * ctx->sm_count ? n_fine : 4 * ctx->sm_count, 256, 0, ctx->stream>>>(
+    const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
+    k_field_filter<false><<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
         n_points, grid, data, 1.f, 1.f, L, n_fine, fine, res);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_field_filter launch");
@@ -129,7 +158,8 @@ int launch_field_filter(espic_ctx* ctx, int n_points, const float* grid, const f
 int launch_hole_position(espic_ctx* ctx, int n_points, const float* grid, const float* potential, double dz,
                          float L, int n_fine, const float* fine, float* scratch_res, float* pos_out) {
     if (n_points < 2 || n_fine < 1) return fail(ctx, ESPIC_E_ARG, "hole_position needs n_points>=2, n_fine>=1");
-    k_field_filter<true><<<n_fine < 4 * ctx->sm_count ? n_fine : 4 * ctx->sm_count, 256, 0, ctx->stream>>>(
+    const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
+    k_field_filter<true><<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
         n_points, grid, potential, (float)(2. * dz), (float)dz, L, n_fine, fine, scratch_res);
     k_argmax_position<<<1, 1024, 0, ctx->stream>>>(n_fine, scratch_res, fine, pos_out);
     ctx->launches += 2;
