@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
         const int per = (n_chunks + (int)blockDim.x - 1) / (int)blockDim.x;
         const int i0 = min(tid * per, n_chunks), i1 = min(i0 + per, n_chunks);
         int sum = 0;
+#pragma unroll 8
         for (int i = i0; i < i1; ++i) sum += a.counts[i];
         int incl = sum;
 #pragma unroll
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
         }
         __syncthreads();
         int run = (w ? s_warp[w - 1] : 0) + incl - sum;
+#pragma unroll 8
         for (int i = i0; i < i1; ++i) {
             a.offsets[i] = run;
             run += a.counts[i];
@@ -538,7 +540,10 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     k_finish<<<n_points <= 8192 ? 1 : (n_points + 4095) / 4096, 1024, 0, ctx->stream>>>(f);
     ctx->launches++;
     ESPIC_CUDA(ctx, cudaGetLastError());
-    k_scatter<<<ctx->sm_count, 256, 0, ctx->stream>>>(a.staging, offsets, f.scatter_hdr, empty_slots,
+    // one warp per range where possible: a range costs two dependent round trips (offsets, then the
+    // staged ids), so a warp walking 16 ranges in turn made this kernel 50-120 us at 18945 ranges
+    const int scatter_ctas = (mover_warps + 1 + 7) / 8 < 16 * ctx->sm_count ? (mover_warps + 1 + 7) / 8 : 16 * ctx->sm_count;
+    k_scatter<<<scatter_ctas, 256, 0, ctx->stream>>>(a.staging, offsets, f.scatter_hdr, empty_slots,
                                                       largest_allowed_slot, largest_index_dev, largest_index,
                                                       mover_warps, a.strided ? a.counts : nullptr);
     ctx->launches++;

@@ -131,7 +131,10 @@ __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom&
         if (__any_sync(0xffffffffu, rare))
             return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
         store_quad(a, q, p);
-        deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, s_hi, a.acc);
+        if (__all_sync(0xffffffffu, dep == 0xFu))  // uniform: the whole warp deposits (no per-slot predicates)
+            deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, s_hi, a.acc);
+        else
+            deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, s_hi, a.acc);
         return rem;
     }
 }
