@@ -18,9 +18,12 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for periodic in (True, False):
-    cfg = SimConfig(n_steps=40, n_particles=400_000, n_cells=1024, periodic_particles=periodic,
-                    periodic_potential=False, track_hole=False)
+# 1024 cells: field solve as a 2-CTA cluster; 65536 cells: 8 CTAs with 9 rows per thread, the windowed mover and
+# its automatic re-sorting (local to each rank) under the exchange
+cells_list = [int(c) for c in os.environ.get("ESPIC_CHECK_CELLS", "1024,65536").split(",")]
+for n_cells, periodic in [(c, p) for c in cells_list for p in (True, False)]:
+    cfg = SimConfig(n_steps=40, n_particles=400_000, n_cells=n_cells, periodic_particles=periodic,
+                    periodic_potential=False, track_hole=False, sort_interval_electrons=5 if n_cells > 20000 else None)
     sims = {}
     for mode in ("nccl", "p2p"):
         sim = Simulation(cfg, rank=rank, world_size=world, device=dev, exchange=mode)
@@ -46,7 +49,7 @@ for periodic in (True, False):
     good = worst <= tol and st == [0, 0] and (periodic is False or act[0] == act[1])
     ok &= good
     if rank == 0:
-        print(f"periodic={periodic}: max |phi_p2p - phi_nccl| / max|phi| over 12 steps = {worst:.3e} (tol {tol}); "
+        print(f"cells={n_cells} periodic={periodic}: max |phi_p2p - phi_nccl| / max|phi| over 12 steps = {worst:.3e} (tol {tol}); "
               f"ranks bit-identical: {same}; status {st}; active {act}", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
