@@ -18,6 +18,8 @@
 // (ref :101) and the same acceptance test in double (ref :614, :654).  Parity of the
 // injection body itself is exact when both sides are fed the same velocities and fractions
 // (tests/test_inject_gpu.py); parity of the sampler is statistical.
+#include <cmath>
+
 #include "espic_internal.cuh"
 
 namespace espic {
@@ -65,8 +67,16 @@ __global__ void k_uniforms(int n, float* __restrict__ out, unsigned long long se
 // test log(u) <= log(|v|/|v_max|) + ((v_max+v_d)^2 - (v+v_d)^2)/(2 v_th^2) in double; the stream of
 // uniforms differs from the reference's anyway (see the header), so the test is evaluated in
 // float with the fast log: the accepted distribution changes by O(1e-6) relative.
-__global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restrict__ out,
-                                  unsigned long long seed, unsigned long long call, int* status) {
+// The constants of one draw_velocities call (ref infMagSim_c.c:576-578, 608-610, 648-650), worked
+// out once on the host in double as the reference does: in the kernel they cost every thread a
+// thousand double-precision instructions (pow, exp, two erf) -- 20 us of fixed latency per call.
+struct SamplerConsts {
+    float v_d, inv_two_vt2, side_split;
+    float lo[2], width[2], mode_term[2], log_abs_mode[2];
+};
+
+static SamplerConsts sampler_consts(float v_th, float v_d) {
+    SamplerConsts c;
     const float half_window = 5.f;
     const float beta = (float)((double)v_d / (sqrt(2.) * (double)v_th));
     const double b = (double)beta;
@@ -74,27 +84,35 @@ __global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restric
     const float ratio = (float)((gauss - b * (1. - erf(b))) / (gauss + b * (1. + erf(b))));
     const double vd = (double)v_d, vt = (double)v_th;
     const double disc = sqrt(pow(vd, 2.) + 4. * pow(vt, 2.));
-    const float inv_two_vt2 = (float)(1. / (2. * pow(vt, 2.)));
-    const float side_split = 1.f / (1.f + ratio);
-    // both walls' constants, computed once per thread
-    float mode[2], lo[2], width[2], mode_term[2], log_abs_mode[2];
+    c.v_d = v_d;
+    c.inv_two_vt2 = (float)(1. / (2. * pow(vt, 2.)));
+    c.side_split = 1.f / (1.f + ratio);
+    float mode[2];
     mode[0] = (float)((-vd + disc) / 2.);   // enters at z_min moving right (ref :608-610)
-    lo[0] = (float)fmax((double)(mode[0] - half_window * v_th), 0.);
-    width[0] = (mode[0] + half_window * v_th) - lo[0];
+    c.lo[0] = (float)fmax((double)(mode[0] - half_window * v_th), 0.);
+    c.width[0] = (mode[0] + half_window * v_th) - c.lo[0];
     mode[1] = (float)((-vd - disc) / 2.);   // enters at z_max moving left (ref :648-650)
-    lo[1] = mode[1] - half_window * v_th;
-    width[1] = (float)fmin((double)(mode[1] + half_window * v_th), 0.) - lo[1];
-#pragma unroll
+    c.lo[1] = mode[1] - half_window * v_th;
+    c.width[1] = (float)fmin((double)(mode[1] + half_window * v_th), 0.) - c.lo[1];
     for (int s = 0; s < 2; ++s) {
-        mode_term[s] = (mode[s] + v_d) * (mode[s] + v_d);
-        log_abs_mode[s] = __logf(fabsf(mode[s]));
+        c.mode_term[s] = (mode[s] + v_d) * (mode[s] + v_d);
+        c.log_abs_mode[s] = logf(fabsf(mode[s]));
     }
+    return c;
+}
+
+__global__ void k_draw_velocities(int n, const SamplerConsts k, float* __restrict__ out, unsigned long long seed,
+                                  unsigned long long call, int* status) {
+    const float v_d = k.v_d, inv_two_vt2 = k.inv_two_vt2, side_split = k.side_split;
     Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t r[4];
         uint32_t block = 0;
         ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
         const int s = (u32_to_unit_float(r[0]) - side_split >= 0.f) ? 0 : 1;   // ref :584-585
+        const float lo_s = s ? k.lo[1] : k.lo[0], width_s = s ? k.width[1] : k.width[0];
+        const float mode_term_s = s ? k.mode_term[1] : k.mode_term[0];
+        const float log_abs_mode_s = s ? k.log_abs_mode[1] : k.log_abs_mode[0];
         int next = 2;  // first trial uses r[2], r[3] of block 0; later blocks give two trials each
         float v = 0.f;
         for (int tries = 1;; ++tries) {
@@ -105,9 +123,9 @@ __global__ void k_draw_velocities(int n, float v_th, float v_d, float* __restric
             const float u_v = u32_to_unit_float(r[next]);
             const float u_a = u32_to_unit_float(r[next + 1]);
             next += 2;
-            v = __fadd_rn(__fmul_rn(u_v, width[s]), lo[s]);  // ref :611-612 / :651-652
+            v = __fadd_rn(__fmul_rn(u_v, width_s), lo_s);  // ref :611-612 / :651-652
             const float vs = v + v_d;
-            const float bound = (__logf(fabsf(v)) - log_abs_mode[s]) + (mode_term[s] - vs * vs) * inv_two_vt2;
+            const float bound = (__logf(fabsf(v)) - log_abs_mode_s) + (mode_term_s - vs * vs) * inv_two_vt2;
             if (__logf(u_a) <= bound) break;                 // ref :614 / :654
             // ref :589-607: after 1000 rejections the reference prints a warning and keeps
             // looping; we raise a status bit, and give up after 1e6 so a NaN parameter cannot
@@ -343,7 +361,8 @@ int rng_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_o
     const unsigned long long key = rng_key(ctx);
     int grid_dim = (n + 127) / 128;
     if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
-    k_draw_velocities<<<grid_dim, 128, 0, ctx->stream>>>(n, v_th, v_d, v_out, key, ctx->rng_consumed++, ctx->status);
+    k_draw_velocities<<<grid_dim, 128, 0, ctx->stream>>>(n, sampler_consts(v_th, v_d), v_out, key, ctx->rng_consumed++,
+                                                         ctx->status);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_draw_velocities launch");
 }
