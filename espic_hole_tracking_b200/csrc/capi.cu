@@ -393,13 +393,15 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         if (rc) return rc;
         float* uni = (float*)ctx->rng_ws.ptr;
         float* vel = uni + ((n_inj[i] + 63) & ~63);
-        // same draw order as the reference wrapper: fractions first, then velocities (ref infMagSim_cython.py:245-248)
-        if ((rc = rng_uniforms(ctx, n_inj[i], uni))) return rc;
-        if ((rc = rng_draw_velocities(ctx, n_inj[i], v_th[i], v_d[i], vel))) return rc;
+        // same draw order as the reference wrapper: fractions first, then velocities (ref infMagSim_cython.py:245-248);
+        // both draws and the bad-index classification in one launch, placement + deposit + stack pop in a second
+        if ((rc = rng_sample_for_injection(ctx, n_inj[i], v_th[i], v_d[i], vel, uni, a->grid, a->n_points, a->inject_dt,
+                                           a->background_density, a->a_b)))
+            return rc;
         const espic_species* s = sp[i];
         rc = launch_inject(ctx, n_inj[i], a->grid, a->n_points, a->inject_dt, a->background_density, vel, uni, a->a_b,
                            a->step_index, tags[i], s->particles, s->particle_storage_length, s->empty_slots,
-                           s->current_empty_slot, s->largest_index, s->density);
+                           s->current_empty_slot, s->largest_index, s->density, true);
         if (rc) return rc;
     }
     return ESPIC_OK;

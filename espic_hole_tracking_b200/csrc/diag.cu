@@ -19,6 +19,42 @@ __device__ __forceinline__ float tanh_over_cosh(float s) {
     return copysignf(r, s);
 }
 
+// fine[argmax(res)] with numpy's first-maximum tie rule, by one CTA (any width that is a multiple of 32)
+__device__ __forceinline__ void argmax_position(int n_fine, const float* res, const float* __restrict__ fine,
+                                                float* __restrict__ out) {
+    __shared__ float s_val[32];
+    __shared__ int s_idx[32];
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_fine; i += blockDim.x) {
+        const float v = __ldcg(res + i);   // written by other CTAs of the same launch
+        if (v > best || (v == best && i < idx) || idx == 0x7fffffff) {
+            best = v;
+            idx = i;
+        }
+    }
+    auto better = [](float va, int ia, float vb, int ib) { return (vb > va) || (vb == va && ib < ia); };
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
+        if (better(best, idx, ov, oi)) { best = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = (threadIdx.x < (blockDim.x >> 5)) ? s_val[threadIdx.x] : -INFINITY;
+        idx = (threadIdx.x < (blockDim.x >> 5)) ? s_idx[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
+            if (better(best, idx, ov, oi)) { best = ov; idx = oi; }
+        }
+        if (threadIdx.x == 0) out[0] = (idx < n_fine) ? fine[idx] : fine[0];
+    }
+}
+
 constexpr int kFilterFine = 7;       // fine-mesh points per CTA: the 1001-point mesh makes 143 CTAs, one wave
 constexpr int kFilterThreads = 1024;
 
@@ -34,9 +70,10 @@ template <bool GRADIENT>
 __global__ void __launch_bounds__(kFilterThreads) k_field_filter(int n, const float* __restrict__ grid,
                                                                  const float* __restrict__ data, float div_mid,
                                                                  float div_end, float L, int n_fine,
-                                                                 const float* __restrict__ fine,
-                                                                 float* __restrict__ res) {
+                                                                 const float* __restrict__ fine, float* res,
+                                                                 float* __restrict__ pos_out, unsigned* ticket) {
     __shared__ double s_red[kFilterFine][kFilterThreads / 32];
+    __shared__ int s_last;
     const float inv_L = 1.f / L;
     const bool exact_inv = (inv_L * L == 1.f) && (__float_as_uint(L) & 0x007fffffu) == 0u;  // L a power of two
     for (int i0 = blockIdx.x * kFilterFine; i0 < n_fine; i0 += gridDim.x * kFilterFine) {
@@ -78,41 +115,16 @@ __global__ void __launch_bounds__(kFilterThreads) k_field_filter(int n, const fl
         }
         __syncthreads();
     }
-}
-
-// fine[argmax(res)] with numpy's first-maximum tie rule
-__global__ void __launch_bounds__(1024) k_argmax_position(int n_fine, const float* __restrict__ res,
-                                                          const float* __restrict__ fine, float* __restrict__ out) {
-    __shared__ float s_val[32];
-    __shared__ int s_idx[32];
-    float best = -INFINITY;
-    int idx = 0x7fffffff;
-    for (int i = threadIdx.x; i < n_fine; i += blockDim.x) {
-        const float v = res[i];
-        if (v > best || (v == best && i < idx) || idx == 0x7fffffff) {
-            best = v;
-            idx = i;
+    if (pos_out) {  // hole position = fine[argmax(Res)] (ref infMagSim_script.py:746-753), by the last CTA to finish
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            argmax_position(n_fine, res, fine, pos_out);
+            if (threadIdx.x == 0) *ticket = 0u;
         }
-    }
-    auto better = [](float va, int ia, float vb, int ib) { return (vb > va) || (vb == va && ib < ia); };
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, d);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
-        if (better(best, idx, ov, oi)) { best = ov; idx = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = idx; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        best = (threadIdx.x < (blockDim.x >> 5)) ? s_val[threadIdx.x] : -INFINITY;
-        idx = (threadIdx.x < (blockDim.x >> 5)) ? s_idx[threadIdx.x] : 0x7fffffff;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, d);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
-            if (better(best, idx, ov, oi)) { best = ov; idx = oi; }
-        }
-        if (threadIdx.x == 0) out[0] = (idx < n_fine) ? fine[idx] : fine[0];
     }
 }
 
@@ -150,7 +162,7 @@ int launch_field_filter(espic_ctx* ctx, int n_points, const float* grid, const f
     if (n_points < 1 || n_fine < 1) return 0;
     const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
     k_field_filter<false><<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
-        n_points, grid, data, 1.f, 1.f, L, n_fine, fine, res);
+        n_points, grid, data, 1.f, 1.f, L, n_fine, fine, res, nullptr, nullptr);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_field_filter launch");
 }
@@ -160,9 +172,9 @@ int launch_hole_position(espic_ctx* ctx, int n_points, const float* grid, const 
     if (n_points < 2 || n_fine < 1) return fail(ctx, ESPIC_E_ARG, "hole_position needs n_points>=2, n_fine>=1");
     const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
     k_field_filter<true><<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
-        n_points, grid, potential, (float)(2. * dz), (float)dz, L, n_fine, fine, scratch_res);
-    k_argmax_position<<<1, 1024, 0, ctx->stream>>>(n_fine, scratch_res, fine, pos_out);
-    ctx->launches += 2;
+        n_points, grid, potential, (float)(2. * dz), (float)dz, L, n_fine, fine, scratch_res, pos_out,
+        (unsigned*)(ctx->status + 9));
+    ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "hole position launch");
 }
 

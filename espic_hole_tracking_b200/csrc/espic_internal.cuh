@@ -237,7 +237,9 @@ int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge,
                           int fix_i, int fix_e);
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
-                  int storage, int* empty_slots, int* top, int* largest, float* density);
+                  int storage, int* empty_slots, int* top, int* largest, float* density, bool classified = false);
+int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
+                             const float* grid, int n_points, float dt, float bg, float a_b);
 int rng_seed(espic_ctx* ctx, unsigned long seed);
 int rng_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out);
 int rng_uniforms(espic_ctx* ctx, int n, float* out);

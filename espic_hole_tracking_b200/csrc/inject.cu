@@ -101,40 +101,52 @@ static SamplerConsts sampler_consts(float v_th, float v_d) {
     return c;
 }
 
+// One velocity (element i of sampler call `call`).
+__device__ __forceinline__ float draw_velocity(const Philox& ph, int i, unsigned long long call, const SamplerConsts& k,
+                                               int* status) {
+    const float v_d = k.v_d, inv_two_vt2 = k.inv_two_vt2, side_split = k.side_split;
+    uint32_t r[4];
+    uint32_t block = 0;
+    ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
+    const int s = (u32_to_unit_float(r[0]) - side_split >= 0.f) ? 0 : 1;   // ref :584-585
+    const float lo_s = s ? k.lo[1] : k.lo[0], width_s = s ? k.width[1] : k.width[0];
+    const float mode_term_s = s ? k.mode_term[1] : k.mode_term[0];
+    const float log_abs_mode_s = s ? k.log_abs_mode[1] : k.log_abs_mode[0];
+    int next = 2;  // first trial uses r[2], r[3] of block 0; later blocks give two trials each
+    float v = 0.f;
+    for (int tries = 1;; ++tries) {
+        if (next >= 4) {
+            ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
+            next = 0;
+        }
+        const float u_v = u32_to_unit_float(r[next]);
+        const float u_a = u32_to_unit_float(r[next + 1]);
+        next += 2;
+        v = __fadd_rn(__fmul_rn(u_v, width_s), lo_s);  // ref :611-612 / :651-652
+        const float vs = v + v_d;
+        const float bound = (__logf(fabsf(v)) - log_abs_mode_s) + (mode_term_s - vs * vs) * inv_two_vt2;
+        if (__logf(u_a) <= bound) break;                 // ref :614 / :654
+        // ref :589-607: after 1000 rejections the reference prints a warning and keeps
+        // looping; we raise a status bit, and give up after 1e6 so a NaN parameter cannot
+        // hang the GPU
+        if (tries == 1000) atomicOr(status, ESPIC_ST_SAMPLER_STALL);
+        if (tries >= 1000000) break;
+    }
+    return v;
+}
+
+// Element i of uniform call `call`: the same value k_uniforms writes to out[i].
+__device__ __forceinline__ float uniform_at(const Philox& ph, int i, unsigned long long call) {
+    uint32_t r[4];
+    ph((uint32_t)(i >> 2), 0u, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x554e4946u, r);
+    return u32_to_unit_float(r[i & 3]);
+}
+
 __global__ void k_draw_velocities(int n, const SamplerConsts k, float* __restrict__ out, unsigned long long seed,
                                   unsigned long long call, int* status) {
-    const float v_d = k.v_d, inv_two_vt2 = k.inv_two_vt2, side_split = k.side_split;
     Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t r[4];
-        uint32_t block = 0;
-        ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
-        const int s = (u32_to_unit_float(r[0]) - side_split >= 0.f) ? 0 : 1;   // ref :584-585
-        const float lo_s = s ? k.lo[1] : k.lo[0], width_s = s ? k.width[1] : k.width[0];
-        const float mode_term_s = s ? k.mode_term[1] : k.mode_term[0];
-        const float log_abs_mode_s = s ? k.log_abs_mode[1] : k.log_abs_mode[0];
-        int next = 2;  // first trial uses r[2], r[3] of block 0; later blocks give two trials each
-        float v = 0.f;
-        for (int tries = 1;; ++tries) {
-            if (next >= 4) {
-                ph((uint32_t)i, block++, (uint32_t)call, (uint32_t)(call >> 32) ^ 0x56454c4fu, r);
-                next = 0;
-            }
-            const float u_v = u32_to_unit_float(r[next]);
-            const float u_a = u32_to_unit_float(r[next + 1]);
-            next += 2;
-            v = __fadd_rn(__fmul_rn(u_v, width_s), lo_s);  // ref :611-612 / :651-652
-            const float vs = v + v_d;
-            const float bound = (__logf(fabsf(v)) - log_abs_mode_s) + (mode_term_s - vs * vs) * inv_two_vt2;
-            if (__logf(u_a) <= bound) break;                 // ref :614 / :654
-            // ref :589-607: after 1000 rejections the reference prints a warning and keeps
-            // looping; we raise a status bit, and give up after 1e6 so a NaN parameter cannot
-            // hang the GPU
-            if (tries == 1000) atomicOr(status, ESPIC_ST_SAMPLER_STALL);
-            if (tries >= 1000000) break;
-        }
-        out[i] = v;
-    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = draw_velocity(ph, i, call, k, status);
 }
 
 // ---- injection body --------------------------------------------------------------------------
@@ -151,7 +163,8 @@ struct InjectArgs {
     unsigned long long* acc;
     float* density;
     int* status;
-    int* ws;  // [0] bad count
+    int* ws;  // [0] bad count, [1] stack top after a sequential replay, [2] a deposit went past the wall tiles
+    unsigned* ticket;  // last-CTA-done counter of the commit kernel
     int n_inject, n_points, k;
     float dt, a_b;
     double inv_scale;
@@ -185,6 +198,25 @@ __global__ void k_inject_classify(const InjectArgs a) {
     if (threadIdx.x == 0 && bad) atomicAdd(a.ws, bad);
 }
 
+// The device sampler's two draws and the classification above in one launch: fractions and
+// velocities are written out for the commit kernel, the bad-index count goes to ws[0].
+__global__ void __launch_bounds__(128) k_sample_classify(const InjectArgs a, const SamplerConsts k, float* __restrict__ uni_out,
+                                                         float* __restrict__ vel_out, unsigned long long seed,
+                                                         unsigned long long call_uni, unsigned long long call_vel) {
+    const Geom g = make_geom(a.grid, a.n_points);
+    Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
+    int bad = 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x) {
+        const float u = uniform_at(ph, l, call_uni);
+        const float v = draw_velocity(ph, l, call_vel, k, a.status);
+        uni_out[l] = u;
+        vel_out[l] = v;
+        bad += place_injected(g, v, u, a.dt, a.a_b).bad ? 1 : 0;
+    }
+    bad = __syncthreads_count(bad);
+    if (threadIdx.x == 0 && bad) atomicAdd(a.ws, bad);
+}
+
 __device__ __forceinline__ void deposit_injected(const Geom& g, const Injected& p, unsigned long long* acc) {
     const unsigned w0 = left_share_fixed(g, p.x, p.cell);
     atomicAdd(acc + p.cell, (unsigned long long)w0);
@@ -198,7 +230,7 @@ __device__ __forceinline__ void deposit_injected(const Geom& g, const Injected& 
 constexpr int kWallNodes = 2048;  // nodes kept per wall; anything farther in goes to global memory
 
 __device__ __forceinline__ void deposit_injected_tiled(const Geom& g, const Injected& p, unsigned* s_wall,
-                                                       unsigned long long* acc, int n_points) {
+                                                       unsigned long long* acc, int n_points, bool& interior) {
     const unsigned w0 = left_share_fixed(g, p.x, p.cell);
     const unsigned w[2] = {w0, kWeightOne - w0};
 #pragma unroll
@@ -212,12 +244,44 @@ __device__ __forceinline__ void deposit_injected_tiled(const Geom& g, const Inje
             if (old > ~w[k]) atomicAdd(acc + node, 1ull << 32);  // the word wrapped: credit 2^32 globally
         } else {
             atomicAdd(acc + node, (unsigned long long)w[k]);
+            interior = true;
         }
+    }
+}
+
+// Density of the injected particles added to the caller's float density, accumulators re-zeroed,
+// stack top updated: run by the last CTA of the commit kernel to finish (ref infMagSim_cython.py:281-285).
+__device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhere) {
+    const int n = a.n_points;
+    // injected particles sit within |v| dt of a wall: unless a deposit went further in, only the
+    // two wall regions can hold anything
+    const int span = everywhere ? n : 2 * kWallNodes;
+    for (int jj = threadIdx.x; jj < span; jj += blockDim.x) {
+        const int j = everywhere ? jj : (jj < kWallNodes ? jj : (n - kWallNodes) + (jj - kWallNodes));
+        const unsigned long long v = __ldcg(a.acc + j);
+        if (v) {
+            a.density[j] = __fadd_rn(a.density[j], (float)((double)v * a.inv_scale));
+            a.acc[j] = 0ull;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int top0 = *a.top;
+        if (a.ws[0] == 0) {
+            const int n_ok = min(a.n_inject, top0 + 1);
+            *a.top = top0 - (n_ok > 0 ? n_ok : 0);
+        } else {
+            *a.top = a.ws[1];
+        }
+        a.ws[0] = 0;
+        a.ws[1] = 0;
+        a.ws[2] = 0;
+        *a.ticket = 0u;
     }
 }
 
 __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
     __shared__ unsigned s_wall[2 * kWallNodes];
+    __shared__ int s_last;
     const Geom g = make_geom(a.grid, a.n_points);
     const int top0 = *a.top;
     const int n_bad = a.ws[0];
@@ -225,6 +289,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
         for (int j = threadIdx.x; j < 2 * kWallNodes; j += blockDim.x) s_wall[j] = 0u;
         __syncthreads();
         int my_max = -1;
+        bool interior = false;
         for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x) {
             const int sp = top0 - l;
             if (sp < 0) {  // ref :255-256 "no empty slots" (the reference then reads empty_slots[-1])
@@ -237,9 +302,10 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
             a.pv[slot] = p.v;
             a.px[slot] = p.x;
             my_max = max(my_max, slot);
-            deposit_injected_tiled(g, p, s_wall, a.acc, a.n_points);
+            deposit_injected_tiled(g, p, s_wall, a.acc, a.n_points, interior);
             a.empty_slots[sp] = -1;
         }
+        if (interior) a.ws[2] = 1;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, d));
         if ((threadIdx.x & 31) == 0 && my_max >= 0) atomicMax(a.largest, my_max);
@@ -274,42 +340,51 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
             }
         }
         *a.largest = last;
-        a.ws[1] = top;  // final stack top for k_inject_finish
+        a.ws[1] = top;  // final stack top for inject_finish
+        a.ws[2] = 1;
+    }
+    // the last CTA to get here finishes for all of them (the stack top may only change once every
+    // CTA has read it, the accumulators only once every CTA has flushed)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const bool everywhere = n_bad != 0 || a.n_points < 2 * kWallNodes || *(volatile int*)(a.ws + 2) != 0;
+        inject_finish(a, everywhere);
     }
 }
 
-__global__ void __launch_bounds__(1024) k_inject_finish(const InjectArgs a) {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.n_points; j += gridDim.x * blockDim.x) {
-        const unsigned long long v = a.acc[j];
-        if (v) {
-            a.density[j] = __fadd_rn(a.density[j], (float)((double)v * a.inv_scale));
-            a.acc[j] = 0ull;
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const int top0 = *a.top;
-        if (a.ws[0] == 0) {
-            const int n_ok = min(a.n_inject, top0 + 1);
-            *a.top = top0 - (n_ok > 0 ? n_ok : 0);
-        } else {
-            *a.top = a.ws[1];
-        }
-        a.ws[0] = 0;
-        a.ws[1] = 0;
-    }
-}
+static unsigned long long rng_key(espic_ctx* ctx);
 
-int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
-                  const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
-                  int storage, int* empty_slots, int* top, int* largest, float* density) {
-    if (n_inject <= 0) return 0;
+static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const float* grid, int n_points, float dt,
+                            float bg, float a_b) {
     if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
     int rc = ensure_acc(ctx, n_points);
     if (rc) return rc;
     rc = ensure(ctx, ctx->inject_ws, 64, "inject workspace");
     if (rc) return rc;
-    InjectArgs a{};
     a.grid = grid;
+    a.acc = ctx->acc;
+    a.status = ctx->status;
+    a.ws = (int*)ctx->inject_ws.ptr;
+    a.ticket = (unsigned*)(ctx->status + 8);
+    a.n_inject = n_inject;
+    a.n_points = n_points;
+    a.dt = dt;
+    a.a_b = a_b;
+    a.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
+    return 0;
+}
+
+int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
+                  const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
+                  int storage, int* empty_slots, int* top, int* largest, float* density, bool classified) {
+    if (n_inject <= 0) return 0;
+    InjectArgs a{};
+    int rc = fill_inject_args(ctx, a, n_inject, grid, n_points, dt, bg, a_b);
+    if (rc) return rc;
     a.vel = vel;
     a.uni = uni;
     a.px = particles;
@@ -318,24 +393,37 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
     a.empty_slots = empty_slots;
     a.top = top;
     a.largest = largest;
-    a.acc = ctx->acc;
     a.density = density;
-    a.status = ctx->status;
-    a.ws = (int*)ctx->inject_ws.ptr;
-    a.n_inject = n_inject;
-    a.n_points = n_points;
     a.k = k;
-    a.dt = dt;
-    a.a_b = a_b;
-    a.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
     int grid_dim = (n_inject + 255) / 256;
     if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
-    k_inject_classify<<<grid_dim, 256, 0, ctx->stream>>>(a);
-    // one CTA per SM at most: every CTA zeroes and flushes its own 16 KB wall tile
+    if (!classified) {
+        k_inject_classify<<<grid_dim, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    // one CTA per SM at most: every CTA zeroes and flushes its own 16 KB wall tile; the last one to
+    // finish adds the injected density to the caller's and pops the stack
     k_inject_commit<<<grid_dim < ctx->sm_count ? grid_dim : ctx->sm_count, 256, 0, ctx->stream>>>(a);
-    k_inject_finish<<<n_points <= 8192 ? 1 : (n_points + 4095) / 4096, 1024, 0, ctx->stream>>>(a);
-    ctx->launches += 3;
+    ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "inject launch");
+}
+
+// Fractions + velocities for n_inject particles from the device sampler and their classification, one
+// launch; follow with launch_inject(..., classified = true).  Same streams as rng_uniforms followed by
+// rng_draw_velocities (ref infMagSim_cython.py:245-248: fractions first).
+int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
+                             const float* grid, int n_points, float dt, float bg, float a_b) {
+    if (n_inject <= 0) return 0;
+    InjectArgs a{};
+    int rc = fill_inject_args(ctx, a, n_inject, grid, n_points, dt, bg, a_b);
+    if (rc) return rc;
+    const unsigned long long key = rng_key(ctx);
+    const unsigned long long call_uni = ctx->rng_consumed++, call_vel = ctx->rng_consumed++;
+    int grid_dim = (n_inject + 127) / 128;
+    if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
+    k_sample_classify<<<grid_dim, 128, 0, ctx->stream>>>(a, sampler_consts(v_th, v_d), uni, vel, key, call_uni, call_vel);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_sample_classify launch");
 }
 
 // ---- sampler front ends -----------------------------------------------------------------------
