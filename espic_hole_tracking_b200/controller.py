@@ -89,6 +89,8 @@ class BoxController:
         bp = np.linspace(background_acceleration, 0., num=n_points, endpoint=True).astype(np.float32)
         bp2 = np.linspace(PHASE2_POTENTIAL, 0., num=n_points, endpoint=True).astype(np.float32)
         self._slopes = (float(bp[1] - bp[0]) / self.dz, float(bp2[1] - bp2[0]) / self.dz)
+        # nothing ever changes: box[0] stays v_b_0, box[1] and ions_extra stay zero; the step skips the bookkeeping
+        self.is_static = not self.moving_box and not self.set_background_acceleration
 
     def _ensure(self, k: int) -> None:
         """Runs longer than cfg.n_steps keep going: the histories grow."""

@@ -314,9 +314,12 @@ class Simulation:
         L = c.z_max - c.z_min
         growth = math.exp(max(0, k - c.density_growth_start_step) * c.density_growth_rate * c.step_size)
         w_ion = c.w_ion_perturbation * self.v_th_e / c.debye_length * math.sqrt(1. / c.mass_ratio)   # :663
-        v_flux = self.ctrl.injection_flux_velocity(k)                                             # box[0,k+1]
+        if self.ctrl.is_static:
+            v_flux, v_extra = float(self.ctrl.box[0, 0]), 0.0
+        else:
+            v_flux, v_extra = self.ctrl.injection_flux_velocity(k), float(self.ctrl.ions_extra[0, k])   # box[0,k+1]
         e_i = expected_particle_injection(c.n_particles / L, self.v_th_i / math.sqrt(c.sigma),
-                                          v_flux + float(self.ctrl.ions_extra[0, k]) - c.v_d_i, self.dt)
+                                          v_flux + v_extra - c.v_d_i, self.dt)
         e_i *= (1 - c.amplitude_perturbation * math.sin(max(0, k - c.hole_tracking_end_step) * self.dt * w_ion))
         e_i *= growth
         n_i = int(e_i)
@@ -362,13 +365,17 @@ class Simulation:
         periodic = c.periodic_particles
         self.reduce_densities()
         ions_mobile = k <= c.time_steps_immobile_ions                                            # :929-939
-        ramp = self.ctrl.background_phase(k)          # 0, 1 (input-file ramp) or 2 (:852-862); advances ions_extra
         moving = c.moving_box_simulation
-        if not moving:
-            self.ctrl.update_frozen(k)                # box[0,k+1] = box[0,k], box[1,k] = 0 (:926-928)
-        a_b = self.ctrl.a_b(k)
-        v_inj = self.ctrl.injection_velocity(k)       # (box[0,k] + box[0,k+1]) / 2 (:998, :1017)
-        v_inj_ions = v_inj + float(self.ctrl.ions_extra[0, k]) - c.v_d_i
+        if self.ctrl.is_static:                       # frame at rest, no background ramp (the reference's defaults)
+            ramp, a_b, v_inj = 0, 0.0, float(self.ctrl.box[0, 0])
+            v_inj_ions = v_inj - c.v_d_i
+        else:
+            ramp = self.ctrl.background_phase(k)      # 0, 1 (input-file ramp) or 2 (:852-862); advances ions_extra
+            if not moving:
+                self.ctrl.update_frozen(k)            # box[0,k+1] = box[0,k], box[1,k] = 0 (:926-928)
+            a_b = self.ctrl.a_b(k)
+            v_inj = self.ctrl.injection_velocity(k)   # (box[0,k] + box[0,k+1]) / 2 (:998, :1017)
+            v_inj_ions = v_inj + float(self.ctrl.ions_extra[0, k]) - c.v_d_i
         if not ramp and not moving and not c.phase_space_histograms:
             # field solve + both pushes as one host call (espic_pic_step); same kernels, same order
             a = self._step_args()
@@ -417,7 +424,7 @@ class Simulation:
                 s = self.ions
                 ops.inject_particles(n_i, self.grid, self.dt, self.v_th_i / math.sqrt(c.sigma),
                                      self.background_density, self.sampler, v_inj_ions,
-                                     a_b + float(self.ctrl.ions_extra[1, k]), k,
+                                     a_b + (0.0 if self.ctrl.is_static else float(self.ctrl.ions_extra[1, k])), k,
                                      s.tags, s.particles, s.empty_slots, s.current_empty_slot, s.largest_index,
                                      den_i, ctx=self.ctx)
             if n_e > 0:                                                                          # :1015-1019
