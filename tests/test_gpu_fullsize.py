@@ -113,3 +113,66 @@ def test_full_size_properties(setup, periodic):
         cells = torch.where(cells > N_CELLS - 1, torch.zeros_like(cells), cells)   # infMagSim_c.c:162-163
     assert bool((cells[1:] >= cells[:-1]).all())             # sorted by the mover's cell index
     assert ops.default_context().status() == 0
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_full_size_large_grid(setup, periodic):
+    """The same store on the 65536-cell grid of BASELINE configs[3]: the mover keeps a window of the grid
+    in shared memory per segment of the store (mover_win.cu).  On the random store most slots take
+    its global fallback, on the coarse-sorted copy nearly all take the window; both must give the
+    same density bit for bit (integer deposit), conserve charge exactly, leave the same multiset of
+    particle states, and agree bit for bit with the oracle on a 2e5-slot sample of the SORTED store."""
+    ops, s = setup
+    S = s["S"]
+    n_cells = 65536
+    grid = torch.from_numpy(wl.make_grid(n_cells)).cuda()
+    phi = torch.from_numpy(wl.smooth_potential(wl.make_grid(n_cells), amplitude=1.0)).cuda()
+    mask = torch.zeros_like(grid)
+    bg = wl.background_density(N, 1, n_cells)
+    dt = wl.timestep()
+    stores = {}
+    for name in ("random", "sorted"):
+        p, stack = s["p"].clone(), s["stack"].clone()
+        top, last = ops.DeviceInt(4095), ops.DeviceInt(N - 1)
+        if name == "sorted":
+            ops.sort_particles_by_cell(grid, p, None, stack, top, last, periodic_particles=periodic, key_shift=8,
+                                       lookahead=2.0 * dt)
+        stores[name] = dict(p=p, stack=stack, top=top, last=last)
+    st = stores["sorted"]
+    sample = torch.arange(0, N, 500, device="cuda")
+    x0, v0 = st["p"][0, sample].cpu().numpy(), st["p"][1, sample].cpu().numpy()
+    dens = {}
+    for name, d in stores.items():
+        den = torch.zeros(n_cells + 1, device="cuda")
+        for _ in range(2):
+            ops.move_particles(grid, mask, phi, dt, -1836.0, bg, d["last"], d["p"], den, d["stack"], d["top"], 0.0,
+                               periodic_particles=periodic)
+        dens[name] = den
+    assert torch.equal(dens["random"], dens["sorted"])
+    # --- oracle on the sample of the sorted store, two steps, bit for bit
+    from oracle import cpu as ocpu
+    k = ocpu.load("reference" if ocpu.have("reference") else "port")
+    ps = np.stack([x0, v0]).astype(np.float32)
+    n_s = ps.shape[1]
+    stk, tp = -np.ones(n_s, np.int32), [-1]
+    for _ in range(2):
+        k.move_particles(grid.cpu().numpy(), np.zeros(n_cells + 1, np.float32), phi.cpu().numpy(), dt, -1836.0, bg,
+                         [n_s - 1], ps, np.zeros(n_cells + 1, np.float32), stk, tp, a_b=0.0, periodic_particles=periodic)
+    got = torch.stack([st["p"][0, sample], st["p"][1, sample]]).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ps.view(np.uint32))
+    # --- conservation, bookkeeping, same multiset of states in both stores
+    counts = {}
+    for name, d in stores.items():
+        live = d["p"][0] < 5.9
+        counts[name] = int(live.sum().item())
+        assert counts[name] + (d["top"][0] + 1) == S
+    assert counts["random"] == counts["sorted"]
+    total = float(dens["sorted"].double().sum().item()) * bg
+    assert abs(total - counts["sorted"]) <= 2e-7 * counts["sorted"]
+    keys = []
+    for d in stores.values():
+        live = d["p"][0] < 5.9
+        packed = (d["p"][0][live].view(torch.int32).long() << 32) | (d["p"][1][live].view(torch.int32).long() & 0xffffffff)
+        keys.append(torch.sort(packed).values)
+    assert torch.equal(keys[0], keys[1])
+    assert ops.default_context().status() == 0
