@@ -8,7 +8,9 @@
 //      the circular window of kWinCells cells (start on a bucket boundary) that holds the most
 //      samples, centre-weighted;
 //   2. builds the window's tables in shared memory: kick per cell (copied from the global kick
-//      table k_build_dv made) and the two u32 planes of the fixed-point deposit;
+//      table k_build_dv made) and ONE u32 plane of the fixed-point deposit -- a word that wraps
+//      (every 256 full-weight deposits on a node) credits 2^32 to the global accumulator directly,
+//      which buys a window half as wide again as two planes would allow (8 instead of 12 B/cell);
 //   3. runs the fast slot update on its ranges.  A slot whose gather cell or deposit cell is
 //      outside the window is served per lane from global memory (kick table load, 64-bit
 //      reductions into ctx->acc) -- the warp keeps going, nothing is re-done;
@@ -18,7 +20,7 @@
 // the seam still fits one window.
 //
 // After espic_sort_particles() a segment's particles sit within a few hundred cells of each
-// other and drift apart by |v| dt per step; the window leaves ~9000 cells of margin either side,
+// other and drift apart by |v| dt per step; the window leaves ~13700 cells of margin either side,
 // so nearly all slots stay on the shared-memory path for many steps.  On an unsorted store about
 // kWinCells/n_cells of the slots do, the rest behave like the all-global kernel.  Because the
 // deposit accumulates integers the density does not depend on which path a slot took, nor on the
@@ -30,7 +32,7 @@
 
 namespace espic {
 
-constexpr int kWinCells = 18432;
+constexpr int kWinCells = 27648;
 constexpr int kWinNodes = kWinCells + 2;  // both nodes of every cell, plus one when the window wraps past the seam
 constexpr int kWinBuckets = 64;
 constexpr int kWinThreads = 1024;
@@ -69,8 +71,7 @@ struct KickWindow {
 // Deposit of the slots of a quad named by `dep`: window cells through the shared-memory planes,
 // the others straight into the global accumulators.
 __device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, const int* cell, unsigned dep,
-                                                 const WinMap& map, unsigned* s_lo, unsigned* s_hi,
-                                                 unsigned long long* acc) {
+                                                 const WinMap& map, unsigned* s_lo, unsigned long long* acc) {
     unsigned carries = 0, outside = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -93,8 +94,9 @@ __device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, 
             if (carries & (3u << (2 * c))) {
                 bool inside;
                 const int j = map(cell[c], inside);
-                if (carries & (1u << (2 * c))) atomicAdd(s_hi + j, 1u);
-                if (carries & (2u << (2 * c))) atomicAdd(s_hi + j + 1, 1u);
+                // the word wrapped: its 2^32 goes straight to the global accumulator of that node
+                if (carries & (1u << (2 * c))) atomicAdd(acc + map.node_of(j), 1ull << 32);
+                if (carries & (2u << (2 * c))) atomicAdd(acc + map.node_of(j + 1), 1ull << 32);
             }
             if (outside & (1u << c)) {
                 unsigned w0, w1;
@@ -108,7 +110,7 @@ __device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, 
 
 template <bool PERIODIC>
 __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
-                                                  const KickWindow& kick, unsigned* s_lo, unsigned* s_hi) {
+                                                  const KickWindow& kick, unsigned* s_lo) {
     int cell[4];
     bool rare = false;
     if (PERIODIC) {
@@ -117,7 +119,7 @@ __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom&
         if (__any_sync(0xffffffffu, rare))
             return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
         store_quad(a, q, p);
-        deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, s_hi, a.acc);
+        deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
         return 0u;
     } else {
         unsigned dep = 0, rem = 0;
@@ -132,9 +134,9 @@ __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom&
             return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
         store_quad(a, q, p);
         if (__all_sync(0xffffffffu, dep == 0xFu))  // uniform: the whole warp deposits (no per-slot predicates)
-            deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, s_hi, a.acc);
+            deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
         else
-            deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, s_hi, a.acc);
+            deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, a.acc);
         return rem;
     }
 }
@@ -144,7 +146,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_dv = reinterpret_cast<float*>(smem_raw);
     unsigned* s_lo = reinterpret_cast<unsigned*>(s_dv + kWinNodes);
-    unsigned* s_hi = s_lo + kWinNodes;
     __shared__ int s_bucket[kWinBuckets];
     __shared__ int s_score[kWinBuckets];
     __shared__ int s_seg, s_w_lo;
@@ -209,7 +210,6 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
             const int node = map.node_of(j);
             s_dv[j] = (node >= 0 && node < n_cells) ? __ldg(a.dv_global + node) : 0.f;
             s_lo[j] = 0u;
-            s_hi[j] = 0u;
         }
         __syncthreads();
 
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
                     Quad p0, p1;
                     load_quad(a, q0, p0);
                     load_quad(a, q1, p1);
-                    const unsigned rem0 = quad_fast_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, s_hi);
-                    const unsigned rem1 = quad_fast_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, s_hi);
+                    const unsigned rem0 = quad_fast_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo);
+                    const unsigned rem1 = quad_fast_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo);
                     if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
                         stage_removed(rem0, q0, lane, stage_ids, removed);
                         stage_removed(rem1, q1, lane, stage_ids, removed);
@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
 
         // 4. flush
         for (int j = tid; j < kWinNodes; j += blockDim.x) {
-            const unsigned lo = s_lo[j], hi = s_hi[j];
-            if (lo | hi) atomicAdd(a.acc + map.node_of(j), ((unsigned long long)hi << 32) | lo);
+            const unsigned lo = s_lo[j];
+            if (lo) atomicAdd(a.acc + map.node_of(j), (unsigned long long)lo);
         }
         __syncthreads();
     }
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
 int move_window_size(int n_points) { return n_points - 1 > kWinCells ? kWinCells : 0; }
 
 int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic) {
-    const size_t smem = (size_t)kWinNodes * 12;
+    const size_t smem = (size_t)kWinNodes * 8;
     static bool configured = false;
     static int segs_per_cta = 4;
     if (!configured) {
