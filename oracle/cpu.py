@@ -5,8 +5,12 @@ Two interchangeable CPU arms with the reference's Python operator signatures
 
 * ``load("reference")``  -> oracle/_ref/libref.so, the UNMODIFIED infMagSim_c.c compiled by
   oracle/Makefile with the reference's flags.  Wall injection has no C symbol in the
-  reference (its body is Cython, infMagSim_cython.py:230-285) so that one operator runs the
-  Python restatement below on top of the reference's own ``draw_velocities_c``.
+  reference (its body is Cython, infMagSim_cython.py:230-285): that operator runs the
+  reference's own function, cut unchanged out of the reference file and cythonized by
+  oracle/build_inject_ref.py into oracle/_ref/inject_ref*.so (``reference_inject_particles``;
+  ``inject_given`` uses the twin built against oracle/inject_shim.c so that the velocities can
+  be supplied).  Only where those extensions are missing does it fall back to the scalar
+  Python restatement below.
 * ``load("port")``       -> oracle/libespic_oracle.so, our C restatement (espic_oracle.c).
 
 Nothing under espic_hole_tracking_b200/ may import this module; only tests/,
@@ -15,6 +19,9 @@ __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
 from __future__ import annotations
 
 import ctypes as C
+import glob
+import importlib.machinery
+import importlib.util
 import os
 import subprocess
 
@@ -30,12 +37,76 @@ _f64p = C.POINTER(C.c_double)
 
 
 def build(verbose: bool = False) -> None:
-    """Compile the C restatement and, when /root/reference is present, oracle/_ref."""
+    """Compile the C restatement and, when /root/reference is present, oracle/_ref (libref.so and
+    the cythonized injection routine)."""
     out = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
     if verbose:
         print(out.stdout)
+
+
+_ext_cache: dict = {}
+
+
+def _load_ext(name: str):
+    """An extension module built by oracle/build_inject_ref.py, or None when it is not there."""
+    if name not in _ext_cache:
+        hits = sorted(glob.glob(os.path.join(HERE, "_ref", name + ".*.so")))
+        mod = None
+        if hits:
+            loader = importlib.machinery.ExtensionFileLoader(name, hits[0])
+            spec = importlib.util.spec_from_loader(name, loader)
+            mod = importlib.util.module_from_spec(spec)
+            loader.exec_module(mod)
+        _ext_cache[name] = mod
+    return _ext_cache[name]
+
+
+def have_inject_reference() -> bool:
+    return _load_ext("inject_ref") is not None and _load_ext("inject_ref_given") is not None
+
+
+class _GivenUniforms:
+    """uniform_2d_sampler stand-in: get(n) returns [n, 2] whose column 0 is the supplied fractions."""
+
+    def __init__(self, uniforms):
+        self.u = np.asarray(uniforms, dtype=np.float32)
+
+    def get(self, n):
+        out = np.zeros((int(n), 2), dtype=np.float32)
+        out[:, 0] = self.u[:int(n)]
+        return out
+
+
+def reference_inject_particles(n_inject, grid, dt, v_th, background_density, uniform_2d_sampler, v_d, a_b, k,
+                               particles_hist, particles, empty_slots, current_empty_slot_list, largest_index_list,
+                               density, seed=None):
+    """THE reference's inject_particles (infMagSim_cython.py:230-285, compiled unchanged) with the
+    reference's own draw_velocities_c; ``seed`` re-seeds its MT19937 first (seedgenrand_c)."""
+    ext = _load_ext("inject_ref")
+    if ext is None:
+        raise FileNotFoundError("oracle/_ref/inject_ref*.so missing: run `python oracle/build_inject_ref.py`")
+    if seed is not None:
+        ext.seedgenrand_c(int(seed))
+    ext.inject_particles(int(n_inject), grid, dt, v_th, background_density, uniform_2d_sampler, v_d, a_b, int(k),
+                         particles_hist, particles, empty_slots, current_empty_slot_list, largest_index_list, density)
+
+
+def reference_inject_given(n_inject, grid, dt, background_density, velocities, uniforms, a_b, k, particles_hist,
+                           particles, empty_slots, current_empty_slot_list, largest_index_list, density):
+    """The same compiled reference body with caller-supplied velocities (oracle/inject_shim.c)."""
+    ext = _load_ext("inject_ref_given")
+    if ext is None:
+        raise FileNotFoundError("oracle/_ref/inject_ref_given*.so missing: run `python oracle/build_inject_ref.py`")
+    if int(n_inject) <= 0:
+        return
+    vel = np.ascontiguousarray(velocities[:int(n_inject)], dtype=np.float32)
+    shim = C.CDLL(ext.__file__)
+    shim.inject_shim_set_velocities.argtypes = [_f32p, C.c_int]
+    shim.inject_shim_set_velocities(vel.ctypes.data_as(_f32p), len(vel))
+    ext.inject_particles(int(n_inject), grid, dt, 1.0, background_density, _GivenUniforms(uniforms), 0.0, a_b, int(k),
+                         particles_hist, particles, empty_slots, current_empty_slot_list, largest_index_list, density)
 
 
 def _fp(a: np.ndarray):
@@ -175,9 +246,9 @@ class CpuKernels:
                          current_empty_slot_list, largest_index_list, density):
         """Draw order as in the reference: host uniforms first (:245), then velocities (:248)."""
         n_inject = int(n_inject)
-        uniforms = np.ascontiguousarray(
-            uniform_2d_sampler.get(n_inject).astype(np.float32).T[0]) if n_inject > 0 \
-            else np.zeros(0, np.float32)
+        if n_inject <= 0:   # the reference's &velocities[0] needs at least one element
+            return
+        uniforms = np.ascontiguousarray(uniform_2d_sampler.get(n_inject).astype(np.float32).T[0])
         velocities = self.draw_velocities(n_inject, v_th, v_d)
         self.inject_given(n_inject, grid, dt, background_density, velocities, uniforms, a_b, k,
                           particles_hist, particles, empty_slots, current_empty_slot_list,
@@ -198,6 +269,10 @@ class CpuKernels:
                          _ip(empty_slots), C.byref(top), C.byref(last), _fp(density))
             current_empty_slot_list[0] = top.value
             largest_index_list[0] = last.value
+        elif _load_ext("inject_ref_given") is not None:
+            reference_inject_given(n_inject, grid, dt, background_density, velocities, uniforms, a_b, k,
+                                   particles_hist, particles, empty_slots, current_empty_slot_list,
+                                   largest_index_list, density)
         else:
             inject_python(n_inject, grid, dt, background_density, velocities, uniforms, a_b, k,
                           particles_hist, particles, empty_slots, current_empty_slot_list,

@@ -5,9 +5,10 @@
 
 The fixtures pin the oracle (tests/test_golden.py, CPU) and the CUDA path (-m gpu) to outputs of
 the reference itself; they travel with the repository, /root/reference does not.
-The injection fixture comes from the scalar float32 Python restatement of the Cython body
-(oracle/cpu.py:inject_python, infMagSim_cython.py:230-285) on top of the reference's own
-draw_velocities_c, because the reference has no compiled injection routine.
+The injection fixture comes from the reference's own inject_particles
+(infMagSim_cython.py:230-285), cut unchanged out of the reference file and cythonized by
+oracle/build_inject_ref.py (oracle/_ref/inject_ref*.so), drawing its velocities with the
+reference's own draw_velocities_c.
 """
 import os
 import sys
@@ -71,8 +72,10 @@ def main():
     den0 = np.random.default_rng(1).random(len(grid)).astype(np.float32)
     den = den0.copy()
     uni = np.random.default_rng(2).random(400).astype(np.float32)
-    cpu.inject_python(400, grid, np.float32(0.01), np.float32(4.0), vel_drift, uni, np.float32(0.2), 17, ions.tags,
-                      ions.particles, ions.empty_slots, ions.current_empty_slot, ions.largest_index, den)
+    # the reference's own routine: re-seeded with 385 it draws vel_drift again (v_th 1, v_d 0.8) before placing
+    cpu.reference_inject_particles(400, grid, np.float32(0.01), np.float32(1.0), np.float32(4.0), cpu._GivenUniforms(uni),
+                                   np.float32(0.8), np.float32(0.2), 17, ions.tags, ions.particles, ions.empty_slots,
+                                   ions.current_empty_slot, ions.largest_index, den, seed=385)
     np.savez_compressed(os.path.join(HERE, "sampler_and_injection.npz"), vel_384_4285_0=vel, vel_385_1_08=vel_drift,
                         grid=grid, uniforms=uni, density_in=den0, density_out=den, particles_in=before.particles,
                         stack_in=before.empty_slots, top_in=before.current_empty_slot[0], last_in=before.largest_index[0],

@@ -162,20 +162,75 @@ def test_known_answers(ref, port):
             assert abs(d.sum() - 1.0) < 1e-6
 
 
-def test_injection_port_vs_python_restatement(port):
-    """The injection body is Cython-only in the reference (no compiled arm exists); the C
-    restatement is pinned against a scalar float32 Python restatement of the same lines."""
-    n_cells = 500  # dz not exactly representable: exercises fmod vs index disagreement
+@pytest.fixture(scope="module")
+def inject_ref():
+    """The reference's own Cython inject_particles (infMagSim_cython.py:230-285), cut unchanged out of the
+    reference file and compiled by oracle/build_inject_ref.py."""
+    if not cpu.have_inject_reference():
+        if os.path.exists("/root/reference/infMagSim_cython.py"):
+            cpu.build()
+        if not cpu.have_inject_reference():
+            pytest.skip("oracle/_ref/inject_ref*.so not built and /root/reference absent")
+    return cpu
+
+
+@pytest.mark.parametrize("n_cells,dt,v_th,v_d,a_b", [
+    (500, 0.01, 1.0, 0.3, 0.2),          # dz not exactly representable: fmod vs index disagreement
+    (4096, wl.timestep(), 42.85, 0.0, 0.0),   # the bench grid, electron parameters
+    (4096, wl.timestep(), 1.0, 0.8, 0.37),
+    (500, 0.2, 42.85, 0.0, 0.2),         # "bad left_index": |partial_dt*v| exceeds the domain for a third of the particles
+])
+def test_injection_port_vs_compiled_reference(port, inject_ref, capfd, n_cells, dt, v_th, v_d, a_b):
+    """oracle_inject_particles == the reference's inject_particles bit for bit (state, tags, stack,
+    density), the reference drawing its own velocities from its own MT19937 (same seed on both sides)."""
+    grid = wl.make_grid(n_cells)
+    ions, _ = wl.make_plasma(2000, n_cells, seed=9)
+    a, b, c = ions.copy(), ions.copy(), ions.copy()
+    da = np.random.default_rng(1).random(len(grid)).astype(np.float32)
+    db, dc = da.copy(), da.copy()
+    n, bg, k = 300, np.float32(4.0), 17
+    dt, v_th, v_d, a_b = np.float32(dt), np.float32(v_th), np.float32(v_d), np.float32(a_b)
+    inject_ref.reference_inject_particles(n, grid, dt, v_th, bg, wl.HostUniformSampler(5), v_d, a_b, k, a.tags,
+                                          a.particles, a.empty_slots, a.current_empty_slot, a.largest_index, da,
+                                          seed=384)
+    port.seedgenrand_c(384)
+    vel = port.draw_velocities(n, v_th, v_d)
+    uni = np.ascontiguousarray(wl.HostUniformSampler(5).get(n).astype(np.float32).T[0])
+    port.inject_given(n, grid, dt, bg, vel, uni, a_b, k, b.tags, b.particles, b.empty_slots, b.current_empty_slot,
+                      b.largest_index, db)
+    # and the reference body fed the same velocities through the shim build
+    inject_ref.reference_inject_given(n, grid, dt, bg, vel, uni, a_b, k, c.tags, c.particles, c.empty_slots,
+                                      c.current_empty_slot, c.largest_index, dc)
+    capfd.readouterr()  # the reference prints one line per bad particle
+    bad = dt > 0.1
+    for r, dr in ((a, da), (c, dc)):
+        assert r.current_empty_slot == b.current_empty_slot
+        assert r.largest_index == b.largest_index
+        np.testing.assert_array_equal(r.particles.view(np.uint32), b.particles.view(np.uint32))
+        np.testing.assert_array_equal(r.empty_slots, b.empty_slots)
+        np.testing.assert_array_equal(r.tags, b.tags)
+        np.testing.assert_array_equal(dr.view(np.uint32), db.view(np.uint32))
+    if bad:   # bad particles keep their slot on the stack (ref :272-274)
+        assert ions.current_empty_slot[0] - n < b.current_empty_slot[0] < ions.current_empty_slot[0]
+    else:
+        assert b.current_empty_slot == [ions.current_empty_slot[0] - n]
+
+
+def test_injection_python_restatement_vs_compiled_reference(inject_ref):
+    """The scalar Python restatement (the fallback of the "reference" arm where the compiled extension is
+    absent) against the compiled reference function."""
+    n_cells = 500
     grid = wl.make_grid(n_cells)
     ions, _ = wl.make_plasma(2000, n_cells, seed=9)
     a, b = ions.copy(), ions.copy()
     da = np.random.default_rng(1).random(len(grid)).astype(np.float32)
     db = da.copy()
-    port.seedgenrand_c(384)
-    vel = port.draw_velocities(300, np.float32(1.0), np.float32(0.3))
+    ref_k = cpu.load("reference")
+    ref_k.seedgenrand_c(384)
+    vel = ref_k.draw_velocities(300, np.float32(1.0), np.float32(0.3))
     uni = np.random.default_rng(2).random(300).astype(np.float32)
-    port.inject_given(300, grid, np.float32(0.01), np.float32(4.0), vel, uni, np.float32(0.2), 17,
-                      a.tags, a.particles, a.empty_slots, a.current_empty_slot, a.largest_index, da)
+    inject_ref.reference_inject_given(300, grid, np.float32(0.01), np.float32(4.0), vel, uni, np.float32(0.2), 17,
+                                      a.tags, a.particles, a.empty_slots, a.current_empty_slot, a.largest_index, da)
     cpu.inject_python(300, grid, np.float32(0.01), np.float32(4.0), vel, uni, np.float32(0.2), 17,
                       b.tags, b.particles, b.empty_slots, b.current_empty_slot, b.largest_index, db)
     assert a.current_empty_slot == b.current_empty_slot == [ions.current_empty_slot[0] - 300]
