@@ -21,6 +21,13 @@ Keys of the JSON line beyond the base contract:
                 reference.
   e2e_host_arrays  the literal drop-in: move_particles_c/poisson_solve_c called with HOST arrays
                 (particles cross PCIe in both directions every call).
+  checks        self-validation after every timed loop, outside it (Simulation.validate): device status
+                word, finite potential, charge conservation of the deposit against the live particle
+                count, and -- N>1 -- an all-gathered hash of the potential equal on all ranks.  A failed
+                check makes the process exit non-zero: no number without a valid run.
+  configs3      (N=1) BASELINE configs[3] in front of the driver: 65536 cells, absorbing walls + injection,
+                electron dimple, hole tracking every step, 1e8+1e8 particles, at least two electron sort
+                intervals inside the timed region, with its own roofline for k_move_win<walls>.
 """
 import argparse
 import json
@@ -151,6 +158,7 @@ def main():
                          "instead of periodic particles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-arrays", action="store_true")
+    ap.add_argument("--no-configs3", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -212,6 +220,7 @@ def main():
     ctx.timing_enable(False)
     launches = ctx.launch_count() - launches0
     clk = clocks.stop(t0, t1) if rank == 0 else None
+    checks = {"after_device_timed_loop": sim.validate()}
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -285,6 +294,8 @@ def main():
     barrier()
     e_ms = (time.perf_counter() - e0) * 1e3
     assert len(max_phi) == args.steps
+    checks["after_e2e_loop"] = sim.validate()
+    checks["ok"] = all(c["ok"] for c in checks.values())
     if world > 1:
         t = torch.tensor([e_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -312,7 +323,7 @@ def main():
                                            f"[2,{args.cells + 1}] slots over NVLink peer memory, no collective launch)",
                                     "nccl": f"one NCCL fp32 all-reduce of [2,{args.cells + 1}] per step",
                                     "none": "none (single rank)"}[sim.exchange_mode])},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checks": checks,
     }
 
     # ---------------- the literal host-array drop-in (rank 0, N=1 only) ----------------
@@ -322,10 +333,21 @@ def main():
         except Exception as exc:  # reported, never hidden
             line["e2e_host_arrays"] = {"error": repr(exc)}
 
+    # ---------------- BASELINE configs[3] (rank 0, N=1 only) ----------------
+    del sim
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_configs3 and not args.walls and args.cells == N_CELLS:
+        try:
+            line["configs3"] = configs3_leg(n, device, peak, peak_src)
+            checks["configs3"] = line["configs3"]["checks"]
+            checks["ok"] = checks["ok"] and line["configs3"]["checks"]["ok"]
+        except Exception as exc:  # reported, never hidden
+            line["configs3"] = {"error": repr(exc)}
+            checks["ok"] = False
+        torch.cuda.empty_cache()
+
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del sim
-        torch.cuda.empty_cache()
         from oracle import cpu, loop
         kind = "reference" if cpu.have("reference") else "port"
         if kind == "port" and not cpu.have("port"):
@@ -342,6 +364,74 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not checks["ok"]:
+        sys.stderr.write("bench.py: self-checks FAILED: " + json.dumps(checks) + "\n")
+        sys.exit(1)
+
+
+def configs3_leg(n, device, peak, peak_src):
+    """BASELINE configs[3] as the reference would run it: 65536 cells, absorbing walls with injection (the
+    reference's default boundary), the electron phase-space dimple, hole tracking every step; 1e8+1e8
+    particles.  Timed over (at least) two electron sort intervals, sorts inside the timed region."""
+    import torch
+
+    from espic_hole_tracking_b200.simulation import SimConfig, Simulation
+    cells = 65536
+    cfg = SimConfig(n_steps=400, n_particles=n, n_cells=cells, periodic_particles=False, extra_storage_factor=1.1,
+                    track_hole=True, initial_transient_steps=0, create_electron_dimple=True)
+    sim = Simulation(cfg, device=device)
+    sim.init_synthetic()
+    sim.initialize()
+    k_e = max(int(sim.sort_intervals["electrons"]), 1)
+    warm = 8
+    steps = max(2 * k_e, 40)
+    # start the timed region right after an electron sort so that it holds whole intervals
+    while (sim.k + warm) % k_e != 0:
+        warm += 1
+    for _ in range(warm):
+        sim.step()
+    torch.cuda.synchronize()
+    live0 = sim.n_active()
+    ctx = sim.ctx
+    launches0 = ctx.launch_count()
+    ctx.timing_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        sim.step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    timing = ctx.timing_read()
+    ctx.timing_enable(False)
+    launches = ctx.launch_count() - launches0
+    live1 = sim.n_active()
+    live_mean = 0.5 * (live0["ions"] + live0["electrons"] + live1["ions"] + live1["electrons"])
+    per_launch = 0.5 * live_mean                       # live particles one mover launch advances
+    mover_ms = timing["mean_ms"]
+    achieved = ALGO_BYTES_PER_PARTICLE_STEP * per_launch / (mover_ms * 1e-3) / 1e9 if mover_ms > 0 else 0.0
+    window = ctx._lib.espic_mover_window_cells(ctx.handle, sim.n_points)
+    chk = sim.validate()
+    pos = sim.hole_relative_positions[warm:warm + steps].cpu().numpy()
+    return {
+        "metric": METRIC, "value": live_mean * steps / (ms * 1e-3), "unit": "particle-steps/s", "steps": steps,
+        "warmup": warm, "ms_per_step": ms / steps,
+        "config": {"workload": f"{n:.3g} ions + {n:.3g} electrons, {cells}-cell wall-bounded grid with injection, electron "
+                               "dimple, hole tracking every step (BASELINE configs[3])",
+                   "cells": cells, "periodic": False, "sort_interval_steps": dict(sim.sort_intervals),
+                   "electron_sort_intervals_timed": steps / k_e,
+                   "live_particles": {"start": live0, "end": live1}},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": f"espic::k_move_win<walls> ({window}-cell shared-memory window per store segment)",
+                     "launch_ms_mean": mover_ms, "launches_timed": timing["launches"],
+                     "mover_share_of_step": timing["total_ms"] / ms if ms > 0 else None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * per_launch,
+                     "note": "mean over every mover launch of the timed region (both species, all steps of the sort "
+                             "intervals); algorithmic bytes count LIVE particles only, the kernel also scans dead slots"},
+        "gpu_launches": int(launches), "checks": chk,
+        "hole_position_last": float(pos[-1]) if len(pos) else None,
+    }
 
 
 def host_array_leg(sim, n, cells):

@@ -80,6 +80,9 @@ SIGNATURES = {
     "espic_seed": (c_int, [c_void_p, C.c_ulong]),
     "espic_draw_velocities": (c_int, [c_void_p, c_int, c_float, c_float, P]),
     "espic_genrand": (c_int, [c_void_p, c_int, P]),
+    "espic_rng_get_state": (c_int, [c_void_p, C.POINTER(C.c_ulonglong)]),
+    "espic_rng_set_state": (c_int, [c_void_p, C.POINTER(C.c_ulonglong)]),
+    "espic_exchange_set_timeout": (c_int, [c_void_p, c_double]),
     "espic_selftest_quotient": (c_int, [c_void_p, P, c_int, C.POINTER(C.c_ulonglong)]),
     "espic_field_filter": (c_int, [c_void_p, c_int, P, P, c_float, c_int, P, P]),
     "espic_hole_position": (c_int, [c_void_p, c_int, P, P, c_double, c_float, c_int, P, P, P]),
@@ -88,6 +91,9 @@ SIGNATURES = {
     # reference-named host-pointer drop-ins
     "move_particles_c": (None, [P, P, P, c_float, c_float, c_float, c_int, P, P, P, P, c_float, c_int,
                                 c_int, c_int, c_int, c_int]),
+    "move_particles_c_minimal": (None, [P, P, P, c_float, c_float, c_float, c_int, P, P, P, P, c_int,
+                                        c_int, c_int, c_int, c_int]),
+    "tridiagonal_solve_c": (None, [P, P, P, P, P, c_int]),
     "poisson_solve_c": (None, [P, P, P, c_float, P, c_float, c_float, c_int, c_int, c_int]),
     "draw_velocities_c": (None, [c_int, c_float, c_float, P]),
     "sgenrand": (None, [C.c_ulong]),
@@ -169,6 +175,19 @@ class Context:
         st = c_int(0)
         self.check(self._lib.espic_status(self.handle, C.byref(st)), "espic_status")
         return st.value
+
+    def rng_state(self):
+        """(key, calls consumed, seeded) of the device sampler (checkpoints)."""
+        st = (C.c_ulonglong * 3)()
+        self.check(self._lib.espic_rng_get_state(self.handle, st), "espic_rng_get_state")
+        return [int(v) for v in st]
+
+    def set_rng_state(self, state) -> None:
+        st = (C.c_ulonglong * 3)(*[int(v) for v in state])
+        self.check(self._lib.espic_rng_set_state(self.handle, st), "espic_rng_set_state")
+
+    def set_exchange_timeout(self, seconds: float) -> None:
+        self.check(self._lib.espic_exchange_set_timeout(self.handle, float(seconds)), "espic_exchange_set_timeout")
 
     def launch_count(self) -> int:
         return int(self._lib.espic_launch_count(self.handle))

@@ -111,6 +111,13 @@ int espic_create(espic_ctx** out, int device) {
         return ESPIC_E_NODEVICE;
     }
     if (device < 0 || device >= count) return ESPIC_E_ARG;
+    // the context's device is made current only while an entry point runs (DeviceGuard); the
+    // caller's current device is left as it was
+    struct Restore {
+        int prev = -1;
+        Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+        ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
     if (cudaSetDevice(device) != cudaSuccess) return ESPIC_E_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ESPIC_E_CUDA;
@@ -132,6 +139,7 @@ int espic_create(espic_ctx** out, int device) {
 }
 
 void espic_destroy(espic_ctx* ctx) {
+    DeviceGuard guard(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -166,6 +174,7 @@ int espic_set_stream(espic_ctx* ctx, void* cuda_stream) {
 const char* espic_last_error(espic_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
 int espic_status(espic_ctx* ctx, int* status_out) {
+    DeviceGuard guard(ctx);
     if (!ctx || !status_out) return ESPIC_E_ARG;
     int st = 0;
     ESPIC_CUDA(ctx, cudaMemcpyAsync(&st, ctx->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -184,6 +193,7 @@ int espic_device_info(espic_ctx* ctx, int* sm_count, int* mover_grid, int* mover
 }
 
 int espic_mover_window_cells(espic_ctx* ctx, int n_points) {
+    DeviceGuard guard(ctx);
     if (!ctx || n_points < 2) return 0;
     return move_window_cells(ctx, n_points);
 }
@@ -191,6 +201,7 @@ int espic_mover_window_cells(espic_ctx* ctx, int n_points) {
 long long espic_launch_count(espic_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 int espic_timing_enable(espic_ctx* ctx, int on) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (on && !ctx->ev) {
         ctx->ev_cap = 8192;
@@ -204,6 +215,7 @@ int espic_timing_enable(espic_ctx* ctx, int on) {
 }
 
 int espic_timing_read(espic_ctx* ctx, double* mean_ms, int* launches, double* total_ms) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     ESPIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double tot = 0.;
@@ -227,6 +239,7 @@ int espic_move_particles(espic_ctx* ctx, const float* grid, const float* object_
                          float* particles, float* density, int* empty_slots, int* current_empty_slot,
                          float a_b, int update_position, int periodic_particles, int largest_allowed_slot,
                          int n_points, int particle_storage_length) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !object_mask || !potential || !particles || !density || !empty_slots || !current_empty_slot)
         return fail(ctx, ESPIC_E_ARG, "espic_move_particles: null pointer argument");
@@ -240,6 +253,7 @@ int espic_move_particles_dev(espic_ctx* ctx, const float* grid, const float* obj
                              const int* largest_index_dev, float* particles, float* density, int* empty_slots,
                              int* current_empty_slot, float a_b, int update_position, int periodic_particles,
                              int largest_allowed_slot, int n_points, int particle_storage_length) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !object_mask || !potential || !particles || !density || !empty_slots || !current_empty_slot ||
         !largest_index_dev)
@@ -251,6 +265,7 @@ int espic_move_particles_dev(espic_ctx* ctx, const float* grid, const float* obj
 }
 
 int espic_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out) {
+    DeviceGuard guard(ctx);
     if (!ctx || !grid || !counts_out || n_points < 2) return ESPIC_E_ARG;
     return launch_selftest_quotient(ctx, grid, n_points, counts_out);
 }
@@ -258,6 +273,7 @@ int espic_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, uns
 int espic_sort_particles(espic_ctx* ctx, const float* grid, int n_points, float* particles,
                          int particle_storage_length, int* particles_hist, int* empty_slots, int n_stack,
                          int* current_empty_slot, int* largest_index_dev, int largest_index, int periodic_particles) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !particles || !particles_hist || !empty_slots || !current_empty_slot || !largest_index_dev)
         return fail(ctx, ESPIC_E_ARG, "espic_sort_particles: null pointer argument");
@@ -269,6 +285,7 @@ int espic_sort_particles_coarse(espic_ctx* ctx, const float* grid, int n_points,
                                 int particle_storage_length, int* particles_hist, int* empty_slots, int n_stack,
                                 int* current_empty_slot, int* largest_index_dev, int largest_index,
                                 int periodic_particles, int key_shift, float lookahead) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !particles || !empty_slots || !current_empty_slot || !largest_index_dev)
         return fail(ctx, ESPIC_E_ARG, "espic_sort_particles_coarse: null pointer argument");
@@ -278,6 +295,7 @@ int espic_sort_particles_coarse(espic_ctx* ctx, const float* grid, int n_points,
 
 int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storage_length, int largest_index,
                            double v_b) {
+    DeviceGuard guard(ctx);
     if (!ctx || !particles) return ESPIC_E_ARG;
     return launch_shift_velocities(ctx, particles, particle_storage_length, largest_index, v_b);
 }
@@ -285,6 +303,7 @@ int espic_shift_velocities(espic_ctx* ctx, float* particles, int particle_storag
 int espic_poisson_solve(espic_ctx* ctx, const float* grid, const float* object_mask, const float* charge,
                         float debye_length, float* potential, float object_potential, float object_transparency,
                         int boltzmann_electrons, int periodic_potential, int n_points) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !object_mask || !charge || !potential)
         return fail(ctx, ESPIC_E_ARG, "espic_poisson_solve: null pointer argument");
@@ -294,6 +313,7 @@ int espic_poisson_solve(espic_ctx* ctx, const float* grid, const float* object_m
 
 int espic_prepare_charge(espic_ctx* ctx, float* ion_density, float* electron_density, float* charge, int n_points,
                          int periodic, int fix_ions, int fix_electrons) {
+    DeviceGuard guard(ctx);
     if (!ctx || !ion_density || !electron_density || !charge) return ESPIC_E_ARG;
     return launch_prepare_charge(ctx, ion_density, electron_density, charge, n_points, periodic, fix_ions,
                                  fix_electrons);
@@ -303,6 +323,7 @@ int espic_field_solve(espic_ctx* ctx, const float* grid, const float* object_mas
                       float* electron_density, float* charge, int periodic_particles, int fix_ions,
                       int fix_electrons, float debye_length, float* potential, float object_potential,
                       float object_transparency, int boltzmann_electrons, int periodic_potential, int n_points) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !object_mask || !ion_density || !electron_density || !charge || !potential)
         return fail(ctx, ESPIC_E_ARG, "espic_field_solve: null pointer argument");
@@ -312,22 +333,26 @@ int espic_field_solve(espic_ctx* ctx, const float* grid, const float* object_mas
 }
 
 int espic_exchange_create(espic_ctx* ctx, int n_points, int world, int rank, void* handle_out) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     return exchange_create(ctx, n_points, world, rank, handle_out);
 }
 
 int espic_exchange_open(espic_ctx* ctx, const void* handles) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     return exchange_open(ctx, handles);
 }
 
 int espic_exchange_slot(espic_ctx* ctx, int parity, float** slot_out) {
+    DeviceGuard guard(ctx);
     if (!ctx || !slot_out || !ctx->xch.local) return ESPIC_E_ARG;
     *slot_out = static_cast<float*>(ctx->xch.local) + (size_t)(parity & 1) * ctx->xch.slot_floats;
     return ESPIC_OK;
 }
 
 int espic_exchange_publish(espic_ctx* ctx, int parity, int step) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     return exchange_publish(ctx, parity, step);
 }
@@ -337,6 +362,7 @@ int espic_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float
                                int fix_ions, int fix_electrons, float debye_length, float* potential,
                                float object_potential, float object_transparency, int boltzmann_electrons,
                                int periodic_potential, int n_points) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (!grid || !object_mask || !ion_density || !electron_density || !charge || !potential)
         return fail(ctx, ESPIC_E_ARG, "espic_field_solve_exchange: null pointer argument");
@@ -347,6 +373,7 @@ int espic_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float
 }
 
 int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
+    DeviceGuard guard(ctx);
     if (!ctx || !a) return ESPIC_E_ARG;
     if (!a->grid || !a->object_mask || !a->potential || !a->charge) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null grid pointer");
     const espic_species* sp[2] = {&a->ions, &a->electrons};
@@ -411,6 +438,7 @@ int espic_inject_particles(espic_ctx* ctx, int n_inject, const float* grid, int 
                            float background_density, const float* velocities, const float* uniform01, float a_b,
                            int k, int* particles_hist, float* particles, int particle_storage_length,
                            int* empty_slots, int* current_empty_slot, int* largest_index, float* density) {
+    DeviceGuard guard(ctx);
     if (!ctx) return ESPIC_E_ARG;
     if (n_inject > 0 && (!grid || !velocities || !uniform01 || !particles_hist || !particles || !empty_slots ||
                          !current_empty_slot || !largest_index || !density))
@@ -420,26 +448,55 @@ int espic_inject_particles(espic_ctx* ctx, int n_inject, const float* grid, int 
                          largest_index, density);
 }
 
-int espic_seed(espic_ctx* ctx, unsigned long seed) { return ctx ? rng_seed(ctx, seed) : ESPIC_E_ARG; }
+int espic_seed(espic_ctx* ctx, unsigned long seed) {
+    DeviceGuard guard(ctx);
+    return ctx ? rng_seed(ctx, seed) : ESPIC_E_ARG;
+}
 
 int espic_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out) {
+    DeviceGuard guard(ctx);
     if (!ctx || (n > 0 && !v_out)) return ESPIC_E_ARG;
     return rng_draw_velocities(ctx, n, v_th, v_d, v_out);
 }
 
 int espic_genrand(espic_ctx* ctx, int n, float* out) {
+    DeviceGuard guard(ctx);
     if (!ctx || (n > 0 && !out)) return ESPIC_E_ARG;
     return rng_uniforms(ctx, n, out);
 }
 
+int espic_rng_get_state(espic_ctx* ctx, unsigned long long* state3) {
+    if (!ctx || !state3) return ESPIC_E_ARG;
+    state3[0] = ctx->rng_key;
+    state3[1] = ctx->rng_consumed;
+    state3[2] = (unsigned long long)ctx->rng_seeded;
+    return ESPIC_OK;
+}
+
+int espic_rng_set_state(espic_ctx* ctx, const unsigned long long* state3) {
+    if (!ctx || !state3) return ESPIC_E_ARG;
+    ctx->rng_key = state3[0];
+    ctx->rng_consumed = state3[1];
+    ctx->rng_seeded = state3[2] != 0ull;
+    return ESPIC_OK;
+}
+
+int espic_exchange_set_timeout(espic_ctx* ctx, double seconds) {
+    if (!ctx || !(seconds > 0.)) return ESPIC_E_ARG;
+    ctx->exchange_timeout_s = seconds;
+    return ESPIC_OK;
+}
+
 int espic_field_filter(espic_ctx* ctx, int n_points, const float* grid, const float* data, float L, int n_fine,
                        const float* fine_mesh, float* res) {
+    DeviceGuard guard(ctx);
     if (!ctx || !grid || !data || !fine_mesh || !res) return ESPIC_E_ARG;
     return launch_field_filter(ctx, n_points, grid, data, L, n_fine, fine_mesh, res);
 }
 
 int espic_hole_position(espic_ctx* ctx, int n_points, const float* grid, const float* potential, double dz,
                         float L, int n_fine, const float* fine_mesh, float* scratch_res, float* position_out) {
+    DeviceGuard guard(ctx);
     if (!ctx || !grid || !potential || !fine_mesh || !scratch_res || !position_out) return ESPIC_E_ARG;
     return launch_hole_position(ctx, n_points, grid, potential, dz, L, n_fine, fine_mesh, scratch_res,
                                 position_out);
@@ -448,6 +505,7 @@ int espic_hole_position(espic_ctx* ctx, int n_points, const float* grid, const f
 int espic_phase_space_histogram(espic_ctx* ctx, const float* xs, const float* ys, int n_data, const int* tags,
                                 int tag_value, float x_min, float step_x, float y_min, float step_y,
                                 int n_bins_x, int n_bins_y, int* hist) {
+    DeviceGuard guard(ctx);
     if (!ctx || !xs || !ys || !hist) return ESPIC_E_ARG;
     return launch_histogram(ctx, xs, ys, n_data, tags, tag_value, x_min, step_x, y_min, step_y, n_bins_x,
                             n_bins_y, hist);
@@ -539,18 +597,22 @@ static void report_status(espic_ctx* ctx) {
 #define D2H(dst, src, n, T) \
     if ((rc = check_cuda(ctx, cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream), "D2H"))) die(ctx, __func__, rc)
 
-void move_particles_c(float* grid, float* object_mask, float* potential, float dt, float charge_to_mass,
-                      float background_density, int largest_index, float* particles, float* density,
-                      int* empty_slots, int* current_empty_slot, float a_b, int update_position,
-                      int periodic_particles, int largest_allowed_slot, int n_points,
-                      int particle_storage_length) {
+}  // extern "C"
+
+// Host-array mover shared by move_particles_c and move_particles_c_minimal.
+static void move_host_arrays(const char* who, float* grid, float* object_mask, float* potential, float dt,
+                             float charge_to_mass, float background_density, int largest_index, float* particles,
+                             float* density, int* empty_slots, int* current_empty_slot, float a_b,
+                             int update_position, int periodic_particles, int largest_allowed_slot, int n_points,
+                             int particle_storage_length, int minimal) {
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     const size_t S = (size_t)particle_storage_length, n = (size_t)n_points;
     const size_t n_stack = (size_t)largest_allowed_slot + 1;
     const size_t need = 4 * padded(n * 4) + padded(2 * S * 4) + padded(n_stack * 4) + 256;
-    if ((rc = ensure(ctx, ctx->host_stage, need, "host staging"))) die(ctx, __func__, rc);
+    if ((rc = ensure(ctx, ctx->host_stage, need, "host staging"))) die(ctx, who, rc);
     Carver cv{(char*)ctx->host_stage.ptr};
     float* d_grid = cv.take<float>(n);
     float* d_mask = cv.take<float>(n);
@@ -565,7 +627,11 @@ void move_particles_c(float* grid, float* object_mask, float* potential, float d
         pin_host_range(particles + S, used * sizeof(float), S * sizeof(float));
     }
     H2D(d_grid, grid, n, float);
-    H2D(d_mask, object_mask, n, float);
+    if (minimal) {  // move_particles_c_minimal never looks at the mask (ref infMagSim_c.c:321-332, commented out)
+        if ((rc = check_cuda(ctx, cudaMemsetAsync(d_mask, 0, n * sizeof(float), ctx->stream), "memset"))) die(ctx, who, rc);
+    } else {
+        H2D(d_mask, object_mask, n, float);
+    }
     H2D(d_phi, potential, n, float);
     if (used) {
         H2D(d_part, particles, used, float);
@@ -575,25 +641,80 @@ void move_particles_c(float* grid, float* object_mask, float* potential, float d
     // the entries between the old and the new top come back
     const int top_in = *current_empty_slot;
     H2D(d_top, current_empty_slot, 1, int);
-    rc = espic_move_particles(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, largest_index,
-                              d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles,
-                              largest_allowed_slot, n_points, particle_storage_length);
-    if (rc) die(ctx, __func__, rc);
+    rc = launch_move(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, largest_index, nullptr,
+                     d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles, largest_allowed_slot,
+                     n_points, particle_storage_length, minimal);
+    if (rc) die(ctx, who, rc);
     if (used) {
         D2H(particles, d_part, used, float);
         D2H(particles + S, d_part + S, used, float);
     }
     D2H(density, d_den, n, float);
     D2H(current_empty_slot, d_top, 1, int);
-    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, who, rc);
     {
         const long long first = (long long)top_in + 1;
         long long last = *current_empty_slot;
         if (last > largest_allowed_slot) last = largest_allowed_slot;
         if (first >= 0 && last >= first) D2H(empty_slots + first, d_stack + first, last - first + 1, int);
     }
-    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, who, rc);
     report_status(ctx);
+}
+
+extern "C" {
+
+void move_particles_c(float* grid, float* object_mask, float* potential, float dt, float charge_to_mass,
+                      float background_density, int largest_index, float* particles, float* density,
+                      int* empty_slots, int* current_empty_slot, float a_b, int update_position,
+                      int periodic_particles, int largest_allowed_slot, int n_points,
+                      int particle_storage_length) {
+    move_host_arrays("move_particles_c", grid, object_mask, potential, dt, charge_to_mass, background_density,
+                     largest_index, particles, density, empty_slots, current_empty_slot, a_b, update_position,
+                     periodic_particles, largest_allowed_slot, n_points, particle_storage_length, 0);
+}
+
+// ref infMagSim_c.c:231-341: the stripped mover -- never periodic (its periodic branches are commented
+// out, so the flag is ignored), no frame acceleration, no object, and only slots that were inside the
+// domain on entry can be removed (ref :333).
+void move_particles_c_minimal(float* grid, float* object_mask, float* potential, float dt, float charge_to_mass,
+                              float background_density, int largest_index, float* particles, float* density,
+                              int* empty_slots, int* current_empty_slot, int update_position,
+                              int periodic_particles, int largest_allowed_slot, int n_points,
+                              int particle_storage_length) {
+    (void)periodic_particles;
+    move_host_arrays("move_particles_c_minimal", grid, object_mask, potential, dt, charge_to_mass,
+                     background_density, largest_index, particles, density, empty_slots, current_empty_slot, 0.f,
+                     update_position, 0, largest_allowed_slot, n_points, particle_storage_length, 1);
+}
+
+// ref infMagSim_c.c:343-354: Thomas algorithm on host double arrays; b and d are modified in place
+// exactly as the reference modifies them (eliminated diagonal, back-substituted right-hand side).
+void tridiagonal_solve_c(double* a, double* b, double* c, double* d, double* x, int n) {
+    if (n <= 0) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
+    int rc;
+    const size_t m = (size_t)n;
+    if ((rc = ensure(ctx, ctx->host_stage, 5 * padded(m * 8) + 256, "host staging"))) die(ctx, __func__, rc);
+    Carver cv{(char*)ctx->host_stage.ptr};
+    double* d_a = cv.take<double>(m);
+    double* d_b = cv.take<double>(m);
+    double* d_c = cv.take<double>(m);
+    double* d_d = cv.take<double>(m);
+    double* d_x = cv.take<double>(m);
+    if (n > 1) {  // the reference reads a[0..n-2] and c[0..n-2]
+        H2D(d_a, a, n - 1, double);
+        H2D(d_c, c, n - 1, double);
+    }
+    H2D(d_b, b, n, double);
+    H2D(d_d, d, n, double);
+    if ((rc = launch_tridiagonal(ctx, d_a, d_b, d_c, d_d, d_x, n))) die(ctx, __func__, rc);
+    D2H(b, d_b, n, double);
+    D2H(d, d_d, n, double);
+    D2H(x, d_x, n, double);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
 }
 
 void poisson_solve_c(float* grid, float* object_mask, float* charge, float debye_length, float* potential,
@@ -601,6 +722,7 @@ void poisson_solve_c(float* grid, float* object_mask, float* charge, float debye
                      int periodic_potential, int n_points) {
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     const size_t n = (size_t)n_points;
     if ((rc = ensure(ctx, ctx->host_stage, 4 * padded(n * 4) + 256, "host staging"))) die(ctx, __func__, rc);
@@ -630,6 +752,7 @@ void draw_velocities_c(int n, float v_th, float v_d, float* v_array) {
     if (n <= 0) return;
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     if ((rc = ensure(ctx, ctx->host_stage, padded((size_t)n * 4) + 256, "host staging"))) die(ctx, __func__, rc);
     float* d_v = (float*)ctx->host_stage.ptr;
@@ -642,6 +765,7 @@ void draw_velocities_c(int n, float v_th, float v_d, float* v_array) {
 float genrand(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     float out = 0.f;
     float* d = (float*)(ctx->dev_int2 + 8);
@@ -655,6 +779,7 @@ void electric_field_filter_c(int n_points, float* grid, float* data_array, float
                              float* fine_mesh, float* Res) {
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     const size_t n = (size_t)n_points, m = (size_t)n_fine_mesh;
     if ((rc = ensure(ctx, ctx->host_stage, 2 * padded(n * 4) + 2 * padded(m * 4) + 256, "host staging")))
@@ -677,6 +802,7 @@ void histogram2d_uniform_grid_c(float* X, float* Y, float x_min, float step_x, f
     if (n_data <= 0) return;
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     const size_t n = (size_t)n_data, bins = (size_t)n_bins_x * n_bins_y;
     if ((rc = ensure(ctx, ctx->host_stage, 2 * padded(n * 4) + padded(bins * 4) + 256, "host staging")))
@@ -702,6 +828,7 @@ void inject_particles_c(int n_inject, float* grid, int n_points, float dt, float
     if (n_inject <= 0) return;
     std::lock_guard<std::mutex> lock(g_mutex);
     espic_ctx* ctx = default_ctx();
+    DeviceGuard guard(ctx);
     int rc;
     const size_t S = (size_t)particle_storage_length, n = (size_t)n_points, m = (size_t)n_inject;
     const size_t need = 2 * padded(n * 4) + 2 * padded(m * 4) + padded(2 * S * 4) + 2 * padded(S * 4) + 256;

@@ -185,8 +185,10 @@ int launch_histogram(espic_ctx* ctx, const float* xs, const float* ys, int n_dat
     if (nx < 1 || ny < 1) return fail(ctx, ESPIC_E_ARG, "histogram needs positive bin counts");
     const size_t smem = (size_t)nx * ny * sizeof(int);
     const int use_smem = smem <= 96 * 1024;
-    if (use_smem && smem > 48 * 1024)
+    if (use_smem && smem > 48 * 1024 && smem > ctx->hist_smem_set) {
         ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->hist_smem_set = smem;
+    }
     int grid_dim = (n_data + 256 * 16 - 1) / (256 * 16);
     if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
     if (grid_dim < 1) grid_dim = 1;

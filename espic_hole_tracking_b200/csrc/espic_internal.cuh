@@ -182,6 +182,20 @@ struct espic_ctx {
     int mover_grid = 0, mover_block = 0;
     int mover_ranges = 0;  // ranges of the work split of the last mover launch (see Split)
 
+    // Per-context (hence per-device) launch configuration: the >48 KB shared-memory opt-in of a
+    // kernel is a property of the device's copy of the function, so it is set once per context,
+    // never once per process (a second context on another device needs its own).
+    struct MoveCfg {
+        size_t smem = (size_t)-1;  // dynamic shared memory the cached choice was made for
+        int per_sm = 0, threads = 0;
+    } move_cfg[8];                 // one per k_move instantiation
+    bool win_configured = false;
+    bool sort_configured = false;
+    bool solve_configured = false;
+    int solve_max_team = 0;
+    size_t hist_smem_set = 0;
+    double exchange_timeout_s = 30.;  // espic_exchange_set_timeout
+
     // per-launch timing of the mover kernel
     int timing_on = 0;
     cudaEvent_t* ev = nullptr;
@@ -202,6 +216,22 @@ int check_cuda(espic_ctx* ctx, cudaError_t e, const char* what);
 int ensure(espic_ctx* ctx, Scratch& s, size_t bytes, const char* what);
 int ensure_acc(espic_ctx* ctx, int n_points);
 
+// Makes the context's device current for the duration of an entry point and restores the caller's
+// afterwards: a context may live on any device of the process, whatever device is current.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const espic_ctx* ctx) {
+        if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+            switched = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define ESPIC_CUDA(ctx, call)                                      \
     do {                                                           \
         int _rc = ::espic::check_cuda((ctx), (call), #call);       \
@@ -212,7 +242,8 @@ int ensure_acc(espic_ctx* ctx, int n_points);
 int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const float* phi, float dt,
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
-                int periodic, int largest_allowed_slot, int n_points, int storage);
+                int periodic, int largest_allowed_slot, int n_points, int storage, int minimal = 0);
+int launch_tridiagonal(espic_ctx* ctx, double* a, double* b, double* c, double* d, double* x, int n);
 int move_window_cells(espic_ctx* ctx, int n_points);  // 0: whole-grid tables fit in shared memory
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);
 int launch_sort(espic_ctx* ctx, const float* grid, int n_points, float* particles, int storage, int* tags,

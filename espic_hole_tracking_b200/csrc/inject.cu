@@ -17,7 +17,8 @@
 // generator (one independent counter per output element) with the same float conversion
 // (ref :101) and the same acceptance test in double (ref :614, :654).  Parity of the
 // injection body itself is exact when both sides are fed the same velocities and fractions
-// (tests/test_inject_gpu.py); parity of the sampler is statistical.
+// (tests/test_gpu_parity.py::test_injection_given_inputs, tests/test_golden.py); parity of the sampler
+// is statistical.
 #include <cmath>
 
 #include "espic_internal.cuh"

@@ -381,10 +381,13 @@ int move_window_cells(espic_ctx* ctx, int n_points) {
 template <bool PERIODIC, bool SMEM, bool STRIDED = false>
 static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
     auto kern = k_move<PERIODIC, SMEM, STRIDED>;
-    // CTA width and CTAs per SM for this tile size, chosen once (one device per process): as many
-    // 256-thread CTAs as the tile allows, else wider CTAs so that an SM still holds 32 warps
-    static size_t cached_smem = (size_t)-1;
-    static int cached_per_sm = 0, cached_threads = kMoveThreads;
+    // CTA width and CTAs per SM for this tile size, chosen once per context and instantiation (the
+    // shared-memory opt-in belongs to the device's copy of the kernel): as many 256-thread CTAs as
+    // the tile allows, else wider CTAs so that an SM still holds 32 warps
+    espic_ctx::MoveCfg& cfg = ctx->move_cfg[(PERIODIC ? 4 : 0) + (SMEM ? 2 : 0) + (STRIDED ? 1 : 0)];
+    size_t& cached_smem = cfg.smem;
+    int& cached_per_sm = cfg.per_sm;
+    int& cached_threads = cfg.threads;
     if (cached_smem != smem) {
         if (smem > 48 * 1024)
             ESPIC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -422,7 +425,7 @@ static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
 int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const float* phi, float dt,
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
-                int periodic, int largest_allowed_slot, int n_points, int storage) {
+                int periodic, int largest_allowed_slot, int n_points, int storage, int minimal) {
     if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
     if (storage < 1) return fail(ctx, ESPIC_E_ARG, "particle_storage_length must be >= 1");
     if (!largest_index_dev && largest_index >= storage)
@@ -465,7 +468,9 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.qm = qm;
     a.a_b = a_b;
     a.update_position = update_position;
+    a.minimal = minimal;
     a.vec_ok = ((reinterpret_cast<uintptr_t>(particles) & 15u) == 0 && (storage & 3) == 0) ? 1 : 0;
+    if (minimal) a.vec_ok = 0;  // the stripped variant (never on the step path) runs the generic slot update only
     static int prefetch_env = -2;
     if (prefetch_env == -2) {
         const char* e = getenv("ESPIC_PREFETCH_UNITS");  // tuning knob; -1 = measured default, 0 = off
@@ -515,7 +520,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
         const char* e = getenv("ESPIC_WINDOW");  // 0: always the all-global kernel
         window_env = e ? atoi(e) : 1;
     }
-    if (!use_smem && window_env && a.vec_ok && update_position && move_window_size(n_points) > 0) {
+    if (!use_smem && window_env && a.vec_ok && update_position && !minimal && move_window_size(n_points) > 0) {
         rc = launch_move_window(ctx, a, periodic);
     } else if (periodic && a.strided) {
         rc = launch_move_variant<true, true, true>(ctx, a, smem);

@@ -39,6 +39,8 @@ struct MoveArgs {
     int strided;         // experiment: units dealt round-robin to the warps instead of in contiguous ranges
     int* seg_counter;    // windowed kernel: next segment to hand out (reset by k_finish)
     int n_segments;      // windowed kernel: segments of 32 ranges each
+    int minimal;  // move_particles_c_minimal (ref infMagSim_c.c:231-341): no mask, and a slot that is out of
+                  // bounds on entry is left alone even when it does not carry the parked marker (ref :333)
 };
 
 // The velocity kick of a cell, read straight from a table indexed by cell.
@@ -60,7 +62,8 @@ enum { ACT_NONE = 0, ACT_DEPOSIT = 1, ACT_REMOVE = 2 };
 template <bool PERIODIC>
 __device__ __forceinline__ int push_generic(const Geom& g, float& x_io, float& v_io, const float* dv, float dt,
                                             bool update_position, bool has_obj, const float* __restrict__ grid,
-                                            const float* __restrict__ mask, int& cell_out, bool& bad_any) {
+                                            const float* __restrict__ mask, int& cell_out, bool& bad_any,
+                                            bool minimal = false) {
     float x = x_io, v = v_io;
     bool alive;
     if (PERIODIC) {
@@ -98,7 +101,8 @@ __device__ __forceinline__ int push_generic(const Geom& g, float& x_io, float& v
     }
     cell_out = cell;
     int act = ACT_NONE;
-    if (alive_at_entry || x < g.live_thr) act = (!alive || swallowed) ? ACT_REMOVE : ACT_DEPOSIT;  // ref :211-212
+    // ref :211-212; the minimal variant tests within_bounds_before_move alone (ref :333)
+    if (alive_at_entry || (!minimal && x < g.live_thr)) act = (!alive || swallowed) ? ACT_REMOVE : ACT_DEPOSIT;
     x_io = (act == ACT_REMOVE) ? g.parked : x;
     v_io = v;
     return act;
@@ -207,7 +211,8 @@ __device__ __noinline__ unsigned quad_generic(const MoveArgs& a, int q, int n_sl
         if (s >= n_slots) break;
         float x = a.px[s], v = a.pv[s];
         int cell;
-        const int act = push_generic<PERIODIC>(g, x, v, dv, a.dt, upd, has_obj, a.grid, a.mask, cell, bad_any);
+        const int act = push_generic<PERIODIC>(g, x, v, dv, a.dt, upd, has_obj, a.grid, a.mask, cell, bad_any,
+                                               a.minimal != 0);
         a.px[s] = x;
         a.pv[s] = v;
         if (act == ACT_DEPOSIT) deposit_one<SMEM, true>(g, x, cell, s_lo, s_hi, a.acc);

@@ -283,16 +283,18 @@ int move_window_size(int n_points) { return n_points - 1 > kWinCells ? kWinCells
 
 int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic) {
     const size_t smem = (size_t)kWinNodes * 8;
-    static bool configured = false;
-    static int segs_per_cta = 4;
-    if (!configured) {
-        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_move_win<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_move_win<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (const char* e = getenv("ESPIC_WINDOW_SEGMENTS")) {  // tuning knob: segments per CTA
+    static int segs_per_cta = 0;  // process-wide tuning knob (an environment variable), not device state
+    if (!segs_per_cta) {
+        segs_per_cta = 4;
+        if (const char* e = getenv("ESPIC_WINDOW_SEGMENTS")) {  // segments per CTA
             const int s = atoi(e);
             if (s >= 1 && s <= 64) segs_per_cta = s;
         }
-        configured = true;
+    }
+    if (!ctx->win_configured) {  // per context: the opt-in belongs to this device's copy of the kernels
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_move_win<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_move_win<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->win_configured = true;
     }
     a.n_segments = ctx->sm_count * segs_per_cta;
     a.seg_counter = const_cast<int*>(a.flags_global) + 1;

@@ -157,6 +157,7 @@ struct SolveArgs {
     const float* peer_slot[ESPIC_MAX_RANKS];  // [2][n_pad] floats: ion row, electron row
     const unsigned* peer_flag[ESPIC_MAX_RANKS];
     int n_pad;
+    unsigned long long timeout_ns;            // how long to wait for a peer's publication
 };
 
 constexpr int kMaxTeam = 8;  // portable cluster size
@@ -683,23 +684,34 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     // ---- multi-GPU: the all-reduce of the two density grids (ref infMagSim_script.py:763, 773),
     // done by every rank for itself over NVLink peer memory.  Ranks are summed in rank order,
     // so all ranks obtain bit-identical densities and therefore bit-identical fields.
+    int timed_out = 0;  // CTA-uniform after the barrier below
     if (a.world > 1) {
+        int late = 0;
         if (tid < a.world) {
             // wait until peer `tid` has published its densities for this step (system-scope acquire)
             const unsigned* flag = a.peer_flag[tid];
-            const long long t0 = clock64();
+            unsigned long long t0 = 0ull;
             unsigned seen;
-            for (;;) {
+            for (unsigned spins = 0;; ++spins) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
                 if ((int)(seen - a.expect) >= 0) break;
-                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer died; fail loudly instead of hanging the GPU
-                    atomicOr(a.status, ESPIC_ST_EXCHANGE_TIMEOUT);
-                    break;
+                if ((spins & 63u) == 63u) {  // the wall clock is only consulted once the wait is long
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0ull) t0 = now;
+                    if (now - t0 > a.timeout_ns) {
+                        // a peer never published (it died, or lags by more than the configured bound):
+                        // FATAL.  The status bit is raised and this CTA's share of the potential is
+                        // poisoned with NaN below -- nothing is solved on stale or half-written slots.
+                        atomicOr(a.status, ESPIC_ST_EXCHANGE_TIMEOUT);
+                        late = 1;
+                        break;
+                    }
                 }
                 __nanosleep(200);
             }
         }
-        __syncthreads();
+        timed_out = __syncthreads_or(late);
         for (int j = tm.T; j < n; j += tm.Tn) {
             float si = 0.f, se = 0.f;
             for (int r = 0; r < a.world; ++r) {
@@ -799,6 +811,91 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             if (j < n) a.potential[j] = (float)r;
         }
     }
+    if (timed_out) {  // exchange timeout: every barrier above was still taken; the result is withdrawn
+        for (int i = 0; i < m; ++i) {
+            const int j = tm.T * m + i;
+            if (j < n) a.potential[j] = __int_as_float(0x7fc00000);
+        }
+    }
+}
+
+// ---- tridiagonal_solve_c (ref infMagSim_c.c:343-354) on device arrays -------------------------
+// The reference's generic Thomas routine: b and d are modified in place, x = d/b.  Its three
+// recurrences are strictly sequential and a caller may rely on the exact bits of b and d, so one
+// thread walks them in the reference's operation order ((d*a)/b, (c*a)/b: separately rounded
+// multiply, divide and subtract -- the library is built without FMA contraction) while the CTA
+// stages the rows through shared memory in coalesced chunks.  Not on the step path (the field
+// solve has its own scan kernels); a 65537-row system takes a few milliseconds.
+constexpr int kTriChunk = 1024;
+
+__global__ void __launch_bounds__(256) k_tridiagonal(const double* __restrict__ a, double* __restrict__ b,
+                                                     const double* __restrict__ c, double* __restrict__ d,
+                                                     double* __restrict__ x, int n) {
+    __shared__ double sa[kTriChunk], sc[kTriChunk], sb[kTriChunk], sd[kTriChunk];
+    __shared__ double s_carry[2];
+    const int tid = threadIdx.x;
+    // forward elimination, rows r = 1 .. n-1 (ref :346-349)
+    if (tid == 0) { s_carry[0] = b[0]; s_carry[1] = d[0]; }
+    for (int r0 = 1; r0 < n; r0 += kTriChunk) {
+        const int len = min(kTriChunk, n - r0);
+        for (int i = tid; i < len; i += blockDim.x) {
+            sa[i] = a[r0 + i - 1];
+            sc[i] = c[r0 + i - 1];
+            sb[i] = b[r0 + i];
+            sd[i] = d[r0 + i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double bp = s_carry[0], dp = s_carry[1];
+            for (int i = 0; i < len; ++i) {
+                const double dn = __dsub_rn(sd[i], __ddiv_rn(__dmul_rn(dp, sa[i]), bp));
+                const double bn = __dsub_rn(sb[i], __ddiv_rn(__dmul_rn(sc[i], sa[i]), bp));
+                sd[i] = dn;
+                sb[i] = bn;
+                dp = dn;
+                bp = bn;
+            }
+            s_carry[0] = bp;
+            s_carry[1] = dp;
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += blockDim.x) {
+            b[r0 + i] = sb[i];
+            d[r0 + i] = sd[i];
+        }
+        __syncthreads();
+    }
+    // back substitution, rows j = n-2 .. 0 (ref :350-351): d[j] -= d[j+1]*c[j]/b[j+1]
+    if (tid == 0) s_carry[1] = d[n - 1];
+    __syncthreads();
+    for (int hi = n - 1; hi > 0; hi -= kTriChunk) {  // rows [lo, hi)
+        const int lo = max(0, hi - kTriChunk), len = hi - lo;
+        for (int i = tid; i < len; i += blockDim.x) {
+            sc[i] = c[lo + i];
+            sb[i] = b[lo + i + 1];
+            sd[i] = d[lo + i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double dn = s_carry[1];
+            for (int i = len - 1; i >= 0; --i) {
+                dn = __dsub_rn(sd[i], __ddiv_rn(__dmul_rn(dn, sc[i]), sb[i]));
+                sd[i] = dn;
+            }
+            s_carry[1] = dn;
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += blockDim.x) d[lo + i] = sd[i];
+        __syncthreads();
+    }
+    for (int j = tid; j < n; j += blockDim.x) x[j] = __ddiv_rn(d[j], b[j]);  // ref :352-353
+}
+
+int launch_tridiagonal(espic_ctx* ctx, double* a, double* b, double* c, double* d, double* x, int n) {
+    if (n < 1) return fail(ctx, ESPIC_E_ARG, "tridiagonal_solve needs n >= 1");
+    k_tridiagonal<<<1, 256, 0, ctx->stream>>>(a, b, c, d, x, n);
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_tridiagonal launch");
 }
 
 __global__ void k_prepare_charge(float* __restrict__ ion, float* __restrict__ ele, float* __restrict__ charge,
@@ -836,9 +933,9 @@ static int team_size_for(int n) {
 static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
     const int n = a.n;
     if (n < 3) return fail(ctx, ESPIC_E_ARG, "poisson_solve needs n_points >= 3");
-    static bool configured = false;
-    static int max_team = kMaxTeam;
-    if (!configured) {  // static (19 KB) + dynamic (up to 128 KB) exceeds the 48 KB default
+    int& max_team = ctx->solve_max_team;
+    if (!ctx->solve_configured) {  // static (19 KB) + dynamic (up to 128 KB) exceeds the 48 KB default; per context/device
+        max_team = kMaxTeam;
         ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kSolveSmemRows * kSolveThreads * 8));
         ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_poisson<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -865,7 +962,7 @@ static int launch_poisson_impl(espic_ctx* ctx, SolveArgs& a) {
             cudaGetLastError();
             max_team /= 2;
         }
-        configured = true;
+        ctx->solve_configured = true;
     }
     int team = team_size_for(n);
     if (team > max_team) team = max_team;
@@ -1020,6 +1117,7 @@ int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const floa
     a.fold_ends = periodic_particles;
     a.world = x.world;
     a.expect = (unsigned)step;
+    a.timeout_ns = (unsigned long long)(ctx->exchange_timeout_s * 1e9);
     a.n_pad = (int)(x.slot_floats / 2);
     for (int r = 0; r < x.world; ++r) {
         a.peer_slot[r] = xch_slot(x.peer[r], x, parity & 1);

@@ -376,13 +376,12 @@ int launch_sort(espic_ctx* ctx, const float* grid, int n_points, float* particle
     float* px = particles;
     float* pv = particles + storage;
     cudaStream_t st = ctx->stream;
-    static bool configured = false;
-    if (!configured) {
+    if (!ctx->sort_configured) {
         ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_sort_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kSortScatterSmem));
         ESPIC_CUDA(ctx, cudaFuncSetAttribute(k_sort_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kSortScatterSmem));
-        configured = true;
+        ctx->sort_configured = true;
     }
     ESPIC_CUDA(ctx, cudaMemsetAsync(n_live, 0, sizeof(int), st));
     if (n > 0) {

@@ -94,11 +94,23 @@ class Recorder:
 _STORE_FIELDS = ("particles", "tags", "empty_slots")
 
 
+def _barrier(sim) -> None:
+    """Multi-rank runs with the fused exchange: moving gigabytes of checkpoint skews the ranks by far
+    more than a step; meet again before anyone publishes or waits (the exchange wait is bounded)."""
+    if sim.world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize(sim.device)
+        dist.barrier(group=sim.pg)
+
+
 def save_checkpoint(sim, path: str) -> None:
+    """Complete state of one rank: stores, stacks, tags, fields, pending deposits, the host generator,
+    the device sampler's stream position (Philox key + calls consumed) and the controller."""
+    sim.check_status()
     state = {"k": sim.k, "t": sim.t, "cfg": dict(sim.cfg.__dict__), "rank": sim.rank, "world": sim.world,
              "potential": sim.potential.cpu(), "densities": sim.densities.cpu(), "charge": sim.charge_density.cpu(),
              "hole": sim.hole_relative_positions.cpu(), "host_rng": sim.host_rng.get_state(),
-             "rng": (sim.ctx_rng_state() if hasattr(sim, "ctx_rng_state") else None),
+             "rng": sim.ctx.rng_state(),
              "ctrl": {"box": sim.ctrl.box.copy(), "ions_extra": sim.ctrl.ions_extra.copy(),
                       "hole_velocities": sim.ctrl.hole_velocities.copy(),
                       "filter_z": None if sim.ctrl.filter.z is None else sim.ctrl.filter.z.copy()}}
@@ -109,19 +121,31 @@ def save_checkpoint(sim, path: str) -> None:
         state[name]["top"] = s.current_empty_slot[0]
         state[name]["last"] = s.largest_index[0]
     torch.save(state, path)
+    _barrier(sim)
 
 
 def load_checkpoint(sim, path: str) -> None:
     """Restores a checkpoint into a Simulation built with the same configuration."""
     state = torch.load(path, weights_only=False)
-    if state["cfg"]["n_particles"] != sim.cfg.n_particles or state["cfg"]["n_cells"] != sim.cfg.n_cells:
-        raise ValueError("checkpoint was written for a different configuration")
+    # everything that shapes the state or the trajectory must match; n_steps (history length) and the
+    # sorting knobs (physically invisible) may differ
+    free = {"n_steps", "sort_interval_ions", "sort_interval_electrons", "track_hole", "phase_space_histograms"}
+    mine = dict(sim.cfg.__dict__)
+    diff = sorted(k for k in set(mine) | set(state["cfg"]) if k not in free and mine.get(k) != state["cfg"].get(k))
+    if diff:
+        raise ValueError(f"checkpoint was written for a different configuration: {diff}")
+    if state.get("rank", sim.rank) != sim.rank or state.get("world", sim.world) != sim.world:
+        raise ValueError(f"checkpoint of rank {state.get('rank')}/{state.get('world')} loaded on rank "
+                         f"{sim.rank}/{sim.world}")
     sim.k, sim.t = state["k"], state["t"]
     sim.potential.copy_(state["potential"])
     sim.densities.copy_(state["densities"])
     sim.charge_density.copy_(state["charge"])
-    sim.hole_relative_positions.copy_(state["hole"])
+    n_hist = min(sim.hole_relative_positions.shape[0], state["hole"].shape[0])
+    sim.hole_relative_positions[:n_hist].copy_(state["hole"][:n_hist])
     sim.host_rng.set_state(state["host_rng"])
+    if state.get("rng") is not None:
+        sim.ctx.set_rng_state(state["rng"])   # the resumed run draws what the uninterrupted run would have drawn
     den_i, den_e = sim._deposit_rows(sim.k)
     den_i.copy_(state["pending_densities"][0])
     den_e.copy_(state["pending_densities"][1])
@@ -135,5 +159,6 @@ def load_checkpoint(sim, path: str) -> None:
         sim.ctrl.hole_velocities = state["ctrl"]["hole_velocities"].copy()
         sim.ctrl.filter.z = None if state["ctrl"]["filter_z"] is None else state["ctrl"]["filter_z"].copy()
     sim._plan_sorting()   # sort intervals are derived from the configuration, not stored
+    _barrier(sim)
     if sim.xch is not None:
         sim.xch.publish(sim.k, sim.k)

@@ -521,9 +521,66 @@ class Simulation:
                                        s.largest_index, periodic_particles=self.cfg.periodic_particles, ctx=self.ctx,
                                        key_shift=key_shift, lookahead=lookahead_steps * self.dt)
 
-    def run(self, n_steps: int) -> None:
-        for _ in range(n_steps):
+    def run(self, n_steps: int, check_every: int = 256) -> None:
+        """n_steps timesteps.  The device status word is read every ``check_every`` steps and at the end
+        (one host synchronisation each): a fatal bit -- an exchange timeout, i.e. a rank that solved
+        on stale peer densities and withdrew its potential -- raises instead of producing fields."""
+        for i in range(n_steps):
             self.step()
+            if check_every and (i + 1) % check_every == 0:
+                self.check_status()
+        self.check_status()
+
+    FATAL_STATUS = 64   # ESPIC_ST_EXCHANGE_TIMEOUT (include/espic_b200.h)
+
+    def check_status(self) -> int:
+        """Reads and clears the status word; raises on a fatal bit, returns the word otherwise (the other
+        bits mirror situations in which the reference only prints: bad index, stack over/underflow...)."""
+        st = self.ctx.status()
+        self.status_seen = getattr(self, "status_seen", 0) | st
+        if st & self.FATAL_STATUS:
+            from ._lib import EspicError
+            raise EspicError(f"rank {self.rank}: the fused density exchange timed out at or before step {self.k} "
+                             "(a peer never published its densities); the potential of that step is NaN")
+        return st
+
+    def status_word(self) -> int:
+        """Every status bit raised since the run began (check_status clears the device word as it reads)."""
+        self.check_status()
+        return self.status_seen
+
+    def validate(self) -> dict:
+        """Self-checks of a run, to be called outside any timed region (synchronises): status word,
+        finite potential, charge conservation of the pending deposit (sum(density)*background_density
+        against the live particle count of this rank; the deposit accumulates integers, the only
+        rounding is the one float conversion per node), and -- multi-rank -- a hash of the potential
+        all-gathered over the ranks (the replicated field solve must give identical bits)."""
+        import hashlib
+        out = {"status": int(self.status_word()), "step": int(self.k)}
+        out["potential_finite"] = bool(torch.isfinite(self.potential).all().item())
+        live = self.n_active()
+        den_i, den_e = self._deposit_rows(self.k)
+        c = self.cfg
+        ions_counted = self.k == 0 or (self.k - 1) <= c.time_steps_immobile_ions   # else the row is all ones (:934)
+        rel = {}
+        for name, den in (("ions", den_i), ("electrons", den_e)):
+            if name == "ions" and not ions_counted:
+                continue
+            total = float(den.double().sum().item()) * self.background_density
+            rel[name] = abs(total - live[name]) / max(live[name], 1)
+        out["live"] = live
+        out["charge_conservation_rel_err"] = rel
+        out["charge_conserved"] = all(v < 2e-6 for v in rel.values())
+        digest = hashlib.sha256(self.potential.cpu().numpy().tobytes()).hexdigest()[:16]
+        out["potential_sha16"] = digest
+        if self.world > 1:
+            import torch.distributed as dist
+            digests = [None] * self.world
+            dist.all_gather_object(digests, digest, group=self.pg)
+            out["ranks_identical"] = len(set(digests)) == 1
+        out["ok"] = (out["status"] == 0 and out["potential_finite"] and out["charge_conserved"]
+                     and out.get("ranks_identical", True))
+        return out
 
     # ---- diagnostics ------------------------------------------------------------------------
     def energies(self):

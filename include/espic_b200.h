@@ -48,7 +48,8 @@ enum {
     ESPIC_ST_BAD_INJECT_INDEX = 8, /* ref infMagSim_cython.py:272-273 */
     ESPIC_ST_BAD_OBJECT_MASK = 16, /* ref infMagSim_c.c:468,482,485 */
     ESPIC_ST_SAMPLER_STALL = 32,   /* ref infMagSim_c.c:589-607 (1000 rejections) */
-    ESPIC_ST_EXCHANGE_TIMEOUT = 64 /* a peer never published its densities (multi-GPU exchange) */
+    ESPIC_ST_EXCHANGE_TIMEOUT = 64 /* FATAL: a peer never published its densities within the exchange
+                                    * timeout (multi-GPU exchange).  The potential of that step is NaN. */
 };
 
 #define ESPIC_MAX_RANKS 16
@@ -58,6 +59,8 @@ typedef struct espic_ctx espic_ctx;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int espic_abi_version(void);
+/* Contexts may be created on any device of the process, several per process; every entry point
+ * makes its context's device current for the duration of the call and restores the caller's. */
 int espic_create(espic_ctx **out, int device);
 void espic_destroy(espic_ctx *ctx);
 /* cudaStream_t as void*; NULL = the legacy default stream.  All work of this context is
@@ -250,6 +253,10 @@ int espic_field_solve_exchange(espic_ctx *ctx, int parity, int step, const float
                                float object_transparency, int boltzmann_electrons,
                                int periodic_potential, int n_points);
 
+/* How long the fused field solve waits for a peer's publication before it gives up (default 30 s).
+ * A timeout is fatal: ESPIC_ST_EXCHANGE_TIMEOUT is raised and the step's potential is NaN. */
+int espic_exchange_set_timeout(espic_ctx *ctx, double seconds);
+
 /* Replaces the body of inject_particles (ref infMagSim_cython.py:230-285) with both random
  * inputs supplied as device arrays: velocities[n_inject] (signed; the sign picks the wall)
  * and uniform01[n_inject] (partial-step fractions).  particles_hist = int[storage] tags.
@@ -271,6 +278,11 @@ int espic_inject_particles(espic_ctx *ctx, int n_inject, const float *grid, int 
 int espic_seed(espic_ctx *ctx, unsigned long seed);
 int espic_draw_velocities(espic_ctx *ctx, int n, float v_th, float v_d, float *v_out);
 int espic_genrand(espic_ctx *ctx, int n, float *out);
+/* Position of the sampler's stream for checkpoint / resume: state3 = {Philox key, number of
+ * sampler calls consumed so far, seeded flag}.  Restoring it makes a resumed run draw exactly
+ * what the uninterrupted run would have drawn. */
+int espic_rng_get_state(espic_ctx *ctx, unsigned long long *state3);
+int espic_rng_set_state(espic_ctx *ctx, const unsigned long long *state3);
 
 /* Exhaustive device-side check of the mover's 3-operation quotient RN((x-z_lo)/dz) (see
  * quotient_dz in csrc/espic_internal.cuh) against the IEEE division instruction, over EVERY
@@ -308,10 +320,19 @@ void move_particles_c(float *grid, float *object_mask, float *potential, float d
                       int *current_empty_slot, float a_b, int update_position,
                       int periodic_particles, int largest_allowed_slot, int n_points,
                       int particle_storage_length); /* ref infMagSim_c.c:121-125 */
+void move_particles_c_minimal(float *grid, float *object_mask, float *potential, float dt,
+                              float charge_to_mass, float background_density, int largest_index,
+                              float *particles, float *density, int *empty_slots,
+                              int *current_empty_slot, int update_position,
+                              int periodic_particles, int largest_allowed_slot, int n_points,
+                              int particle_storage_length); /* ref infMagSim_c.c:231-235 (declared
+                              cdef extern at infMagSim_cython.py:26-30, never called by the driver) */
 void poisson_solve_c(float *grid, float *object_mask, float *charge, float debye_length,
                      float *potential, float object_potential, float object_transparency,
                      int boltzmann_electrons, int periodic_potential,
                      int n_points); /* ref infMagSim_c.c:356-358 */
+void tridiagonal_solve_c(double *a, double *b, double *c, double *d, double *x,
+                         int n); /* ref infMagSim_c.c:343-354; also modifies b and d, as there */
 void draw_velocities_c(int n, float v_th, float v_d, float *v_array); /* ref :560 */
 void sgenrand(unsigned long seed);                                    /* ref :54-56 */
 float genrand(void);                                                  /* ref :67-69 */

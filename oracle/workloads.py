@@ -105,3 +105,31 @@ class HostUniformSampler:
 
     def get(self, n: int) -> np.ndarray:
         return self.rng.rand(int(n), 2)
+
+
+def make_hole_plasma(n: int, seed: int = 384, dimple_height: float = 0.95, dimple_velocity: float = 0.0,
+                     dimple_velocity_width: float = 0.3, dimple_spatial_width: float = 4.0,
+                     mass_ratio: float = MASS_RATIO):
+    """Initial particle arrays of the reference's electron-hole run (script defaults, C1/C5 of SURVEY.md
+    s.8d): uniform positions, Maxwellian velocities, and the phase-space "dimple" carved out of the
+    electrons by rejection -- a sample is redrawn (velocity only) with probability
+    height*exp(-(v-mu)^2/2sig^2)/(1+0.0002*exp(|x|/Lambda)) (infMagSim_script.py:518-520, 602-606).
+    Returns (ions_xv, electrons_xv), float32 [2, n] each: identical initial arrays for both sides of a
+    parity run."""
+    rng = np.random.default_rng(seed)
+    v_th_e = math.sqrt(mass_ratio)
+    out = []
+    for v_th, dimple in ((1.0, False), (v_th_e, True)):
+        x = rng.uniform(Z_MIN, Z_MAX, n)
+        v = rng.standard_normal(n) * v_th
+        if dimple:
+            sig = v_th_e * dimple_velocity_width
+            lam = dimple_spatial_width * DEBYE_LENGTH
+            todo = np.arange(n)
+            while todo.size:
+                d = dimple_height * np.exp(-(v[todo] - dimple_velocity) ** 2 / (2 * sig ** 2)) \
+                    / (1. + 0.0002 * np.exp(np.abs(x[todo]) / lam))
+                todo = todo[rng.random(todo.size) < d]
+                v[todo] = rng.standard_normal(todo.size) * v_th
+        out.append(np.stack([x.astype(np.float32), v.astype(np.float32)]))
+    return out

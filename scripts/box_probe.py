@@ -9,7 +9,7 @@ cfg = SimConfig(n_steps=400, n_particles=n, n_cells=512, periodic_particles=Fals
 sim = Simulation(cfg); sim.init_synthetic(); sim.initialize()
 sim.run(400)
 pos = sim.hole_relative_positions.cpu().numpy()
-print("status", sim.ctx.status())
+print("status", sim.status_word())
 for k in range(80, 400, 20):
     print(k, "pos", pos[k], "box v", sim.ctrl.box[0, k], "a", sim.ctrl.box[1, k], "hole v", sim.ctrl.hole_velocities[k])
 print("max potential", float(sim.potential.max()))

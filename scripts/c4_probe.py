@@ -21,4 +21,4 @@ ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / steps
 na = sim.n_active()
 tot = na["ions"] + na["electrons"]
-print("periodic" if periodic else "walls", f"ms/step {ms:.4f}  particle-steps/s {tot / ms * 1e3:.4e}  active {tot}  status {sim.ctx.status()}")
+print("periodic" if periodic else "walls", f"ms/step {ms:.4f}  particle-steps/s {tot / ms * 1e3:.4e}  active {tot}  status {sim.status_word()}")

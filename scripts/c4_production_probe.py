@@ -21,5 +21,5 @@ e1 = sim.energies(); a1 = sim.n_active()
 tot = a1["ions"] + a1["electrons"]
 pos = sim.hole_relative_positions.cpu().numpy()[100:100 + steps]
 print(json.dumps({"ms_per_step": ms, "particle_steps_per_s": tot / ms * 1e3, "active_start": a0, "active_end": a1,
-                  "energies_start": e0, "energies_end": e1, "status": sim.ctx.status(),
+                  "energies_start": e0, "energies_end": e1, "status": sim.status_word(),
                   "hole_position_last_10": [float(x) for x in pos[-10:]], "max_potential": float(sim.potential.max())}))

@@ -15,4 +15,4 @@ for label, kw in (("512 cells, no dimple", dict(n_cells=512, create_electron_dim
         sim.step()
         if k in (99, 399, 699):
             a = sim.n_active(); out.append((k + 1, a["ions"], a["electrons"]))
-    print(label, out, "status", sim.ctx.status(), "max phi", round(float(sim.potential.max()), 3), flush=True)
+    print(label, out, "status", sim.status_word(), "max phi", round(float(sim.potential.max()), 3), flush=True)

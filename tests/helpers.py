@@ -48,3 +48,44 @@ def assert_bits_equal(a, b, what=""):
         a, b = a.view(np.uint32), b.view(np.uint32)
     bad = np.flatnonzero(a.reshape(-1) != b.reshape(-1))
     assert bad.size == 0, f"{what}: {bad.size} mismatches, first at {bad[:5]}"
+
+
+def run_gpu_hole_history(n, steps, record_every=100, n_cells=512, seed=384, device=None, progress=None):
+    """The long hole-tracking run (BASELINE configs[4]) on the GPU: script-default parameters from the seeded
+    arrays of oracle.workloads.make_hole_plasma (the same arrays tests/golden/make_longrun_golden.py gives the
+    oracle), recording every ``record_every`` steps what SURVEY.md s.8d lists: max potential, tracked hole
+    position, kinetic energies per species, field energy, live populations.  Returns (history dict of numpy
+    arrays, Simulation)."""
+    import time
+
+    import torch
+
+    from espic_hole_tracking_b200.simulation import SimConfig, Simulation
+    cfg = SimConfig(n_steps=steps, n_particles=n, n_cells=n_cells, periodic_particles=False, track_hole=True, seed=seed)
+    sim = Simulation(cfg, device=device)
+    ions, electrons = wl.make_hole_plasma(n, seed=seed)
+    sim.load_particles(ions, electrons)
+    sim.initialize()
+    rec = {k: [] for k in ("step", "max_phi", "hole", "ke_i", "ke_e", "fe", "n_i", "n_e")}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        sim.step()
+        if k % record_every == record_every - 1:
+            e = sim.energies()
+            act = sim.n_active()
+            rec["step"].append(k)
+            rec["max_phi"].append(float(sim.potential.max()))
+            rec["hole"].append(float(sim.hole_relative_positions[k]))
+            rec["ke_i"].append(e["ke_ions"])
+            rec["ke_e"].append(e["ke_electrons"])
+            rec["fe"].append(e["fe"])
+            rec["n_i"].append(act["ions"])
+            rec["n_e"].append(act["electrons"])
+            if progress and (k + 1) % (100 * record_every) == 0:
+                progress(k + 1, time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    hist = {k: np.array(v) for k, v in rec.items()}
+    hist["seconds"] = np.array(time.perf_counter() - t0)
+    hist["status"] = np.array(sim.status_word())
+    return hist, sim

@@ -1,5 +1,10 @@
-"""Run under torchrun on >= 2 GPUs: the fused peer-memory density exchange against the NCCL
-all-reduce path, step by step, from identical particle arrays.
+"""Run under torchrun on >= 2 GPUs.
+
+Part 1: the P-way sharded run on P GPUs (fused peer-memory density exchange) against the ORACLE loop
+(oracle/loop.py over the compiled reference, infMagSim_script.py:756-1023) on the UNION of the shards on
+one CPU -- the reference's own statement of what a sharded run computes ("P-way sharded
+result == 1-GPU result up to summation order"), at 4096 and 65536 cells, periodic and wall-bounded.
+Part 2: the fused exchange against the NCCL all-reduce path, step by step, from identical particle arrays.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
 """
@@ -18,6 +23,86 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 ok = True
+
+
+def shard_particles(r, n, seed=11):
+    rng = np.random.default_rng(seed + 1000 * r)
+    out = []
+    for v_th in (1.0, float(np.sqrt(1836.0))):
+        x = rng.uniform(-3.0, 3.0, n)
+        x = x + 0.05 * np.sin(2 * np.pi * x / 6.0)
+        out.append(np.stack([x.astype(np.float32), (rng.standard_normal(n) * v_th).astype(np.float32)]))
+    return out
+
+
+def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
+    """Every rank pushes its own shard on its GPU; rank 0 also runs the oracle loop on all shards
+    concatenated (background density n*P*dz/L on both sides, ref :402, :510).  Wall injection draws
+    from generators that differ by construction (MT19937 vs Philox), so the wall-bounded case runs with
+    the injection counts forced to zero on both sides: removal at the walls is still exercised."""
+    from oracle import cpu as ocpu, loop as oloop
+    cfg = SimConfig(n_steps=steps + 2, n_particles=n, n_cells=n_cells, periodic_particles=periodic,
+                    periodic_potential=False, track_hole=False, extra_storage_factor=1.25,
+                    sort_interval_electrons=4 if n_cells > 20000 else None)
+    sim = Simulation(cfg, rank=rank, world_size=world, device=dev, exchange="p2p")
+    sim.injection_counts = lambda k: (0, 0)
+    sim.load_particles(*shard_particles(rank, n))
+    sim.initialize()
+    one = None
+    if rank == 0:
+        kind = "reference" if ocpu.have("reference") else "port"
+        one = oloop.CpuSimulation(world * n, n_cells, periodic, kind=kind, n_ranks=1, rank=0, periodic_potential=False)
+        shards = [shard_particles(r, n) for r in range(world)]
+        one.load_particles(np.concatenate([s[0] for s in shards], axis=1), np.concatenate([s[1] for s in shards], axis=1))
+        one.initialize()
+    worst_phi = worst_den = 0.0
+    good = True
+    for k in range(steps):
+        sim.step()   # solves step k's field from the all-rank sum of step k's densities, then pushes
+        gathered = [torch.empty_like(sim.potential) for _ in range(world)]
+        dist.all_gather(gathered, sim.potential)
+        good &= all(torch.equal(gathered[0], g) for g in gathered)   # replicated solve: identical bits on every rank
+        if rank == 0:
+            one.field_step()
+            phi = sim.potential.cpu().numpy().astype(np.float64)
+            scale = np.abs(one.potential).max()
+            worst_phi = max(worst_phi, float(np.abs(phi - one.potential).max() / scale))
+            # reduced, end-fixed densities the GPU solve used (written by the fused kernel) against the oracle's
+            for g, c in ((sim.ion_density, one.ion_density), (sim.electron_density, one.electron_density)):
+                worst_den = max(worst_den, float(np.abs(g.cpu().numpy().astype(np.float64) - c).max() / c.max()))
+            one.push_step()
+            one.t += one.dt
+            one.k += 1
+    live = sim.n_active()
+    counts = torch.tensor([live["ions"], live["electrons"]], device=dev)
+    dist.all_reduce(counts)
+    st = sim.status_word()
+    if rank == 0:
+        act = one.n_active()
+        # the densities differ from the oracle's by float32 summation order only (its serial accumulation is
+        # itself ~1e-6 off the exact sum at these counts); the solve amplifies that by ~(L/lambda_D)^2/8 ~ 300
+        # in the net-charge mode of the Robin system (same bound as tests/test_distributed_cpu.py)
+        good &= worst_den <= 5e-6 and worst_phi <= 3e-3
+        good &= [int(counts[0]), int(counts[1])] == [act["ions"], act["electrons"]]
+        # rank 0's own shard against the oracle's first n slots: same trajectories up to the field difference
+        x_gpu = sim.ions.particles[0, :n].cpu().numpy()
+        x_cpu = one.ions.particles[0, :n]
+        both = (x_gpu < 5.9) & (x_cpu < 5.9)
+        sorted_store = n_cells > 20000   # the windowed mover re-sorts: slots no longer correspond
+        dx = 0.0 if sorted_store else float(np.abs(x_gpu[both] - x_cpu[both]).max())
+        good &= dx <= 2e-5
+        print(f"ORACLE cells={n_cells} periodic={periodic} ranks={world}: max|phi-phi_oracle|/max|phi| = {worst_phi:.3e} "
+              f"(tol 3e-3), max density error / peak = {worst_den:.3e} (tol 5e-6), live (all ranks) {counts.tolist()} "
+              f"vs oracle {[act['ions'], act['electrons']]}, max ion |dx| = {dx:.2e}, status {st}, "
+              f"ranks bit-identical: {bool(good)}", flush=True)
+    good &= st == 0
+    return bool(good)
+
+
+for n_cells in [int(c) for c in os.environ.get("ESPIC_ORACLE_CELLS", "4096,65536").split(",") if c]:
+    for periodic in (True, False):
+        ok &= check_vs_oracle(n_cells, periodic)
+
 # 1024 cells: field solve as a 2-CTA cluster; 65536 cells: 8 CTAs with 9 rows per thread, the windowed mover and
 # its automatic re-sorting (local to each rank) under the exchange
 cells_list = [int(c) for c in os.environ.get("ESPIC_CHECK_CELLS", "1024,65536").split(",")]
@@ -43,7 +128,7 @@ for n_cells, periodic in [(c, p) for c in cells_list for p in (True, False)]:
         same = all(torch.equal(gathered[0], g) for g in gathered)
         ok &= same
     act = [sims[m].n_active() for m in sims]
-    st = [sims[m].ctx.status() for m in sims]
+    st = [sims[m].status_word() for m in sims]
     # with 2 ranks a+b is the same sum in any order: bitwise; more ranks: summation order only
     tol = 0.0 if world == 2 and periodic else (5e-2 if not periodic else 3e-3)
     good = worst <= tol and st == [0, 0] and (periodic is False or act[0] == act[1])

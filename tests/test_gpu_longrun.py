@@ -58,4 +58,48 @@ def test_hole_run_statistics_agree():
     assert abs(H["g_phi"][late].mean() / H["c_phi"][late].mean() - 1) < 0.10, (H["g_phi"], H["c_phi"])
     # ... and the matched filter finds it at the same place (within 0.15 = a bit more than a Debye length)
     assert np.median(np.abs(H["g_hole"][late] - H["c_hole"][late])) < 0.15, (H["g_hole"], H["c_hole"])
-    assert sim.ctx.status() == 0
+    assert sim.status_word() == 0
+
+
+def test_configs4_hundred_thousand_steps_against_oracle_history():
+    """BASELINE configs[4] at its stated length: 1e5 steps of the script-default hole run on the GPU (walls,
+    injection, dimple, hole tracking every step, ions frozen after step 30000 as in the reference,
+    infMagSim_script.py:929-939), diagnostics every 100 steps.
+    (1) the whole run: no status bit, populations and energies bounded, the hole stays tracked inside the box;
+    (2) the first 1e4 steps against the ORACLE's history from the same initial arrays
+    (tests/golden/longrun_c1_n1e5.npz: oracle/loop.py over the compiled reference,
+    infMagSim_script.py:756-1027) -- the two sides draw their injections from different generators, so the
+    agreement is statistical: kinetic energies, populations, hole depth and hole position."""
+    import os
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tests.helpers import run_gpu_hole_history
+    n, steps = 100_000, 100_000
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "longrun_c1_n1e5.npz"))
+    assert int(gold["n"]) == n and int(gold["record_every"]) == 100
+    hist, sim = run_gpu_hole_history(n, steps)
+    assert int(hist["status"]) == 0
+    assert len(hist["step"]) == steps // 100
+    # ---- (1) the whole 1e5-step run
+    for key in ("max_phi", "hole", "ke_i", "ke_e", "fe"):
+        assert np.all(np.isfinite(hist[key])), key
+    assert np.all(np.abs(hist["n_e"] / n - 1) < 0.05), (hist["n_e"].min(), hist["n_e"].max())
+    assert np.all(np.abs(hist["n_i"] / n - 1) < 0.05), (hist["n_i"].min(), hist["n_i"].max())
+    frozen = hist["step"] > sim.cfg.time_steps_immobile_ions + 100
+    assert np.all(hist["n_i"][frozen] == hist["n_i"][frozen][0])          # frozen ions are neither pushed nor injected
+    assert np.all(hist["ke_i"][frozen] == hist["ke_i"][frozen][0])
+    ke_e = hist["ke_e"]
+    assert np.all(np.abs(ke_e / ke_e[:100].mean() - 1) < 0.06), (ke_e.min(), ke_e.max(), ke_e[:100].mean())   # no secular heating
+    assert np.all(hist["fe"] < 0.05 * ke_e)                                # field energy stays a small fraction
+    assert np.all(np.abs(hist["hole"]) <= 3.0)
+    # ---- (2) the first 1e4 steps against the oracle history
+    m = len(gold["step"])
+    np.testing.assert_array_equal(gold["step"], hist["step"][:m])
+    assert np.all(np.abs(hist["ke_e"][:m] / gold["ke_e"] - 1) < 0.03)
+    assert np.all(np.abs(hist["ke_i"][:m] / gold["ke_i"] - 1) < 0.03)
+    assert np.all(np.abs(hist["n_e"][:m] / gold["n_e"] - 1) < 0.01)
+    assert np.all(np.abs(hist["n_i"][:m] / gold["n_i"] - 1) < 0.01)
+    late = slice(m // 2, m)
+    assert gold["max_phi"][late].mean() > 0.05                                                    # there is a hole
+    assert abs(hist["max_phi"][:m][late].mean() / gold["max_phi"][late].mean() - 1) < 0.10
+    assert np.median(np.abs(hist["hole"][:m][late] - gold["hole"][late])) < 0.15

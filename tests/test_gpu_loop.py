@@ -189,7 +189,7 @@ def test_nonperiodic_simulation_runs_and_conserves(pkg):
         x = s.particles[0].cpu().numpy()
         assert np.all(x[free] == np.float32(6.0))                       # every listed slot is parked
         assert (x < 5.9).sum() == act[name] == s.storage - (top + 1)    # every unlisted slot is live
-    assert sim.ctx.status() == 0
+    assert sim.status_word() == 0
     e = sim.energies()
     assert e["fe"] > 0 and e["ke_electrons"] > 0
     pos = sim.hole_relative_positions.cpu().numpy()
@@ -258,7 +258,7 @@ def test_large_grid_auto_sort_is_physically_invisible(pkg, periodic):
         if not never:
             assert sim.sort_intervals["electrons"] == (36 if periodic else 28) and sim.sort_key_shift == 8
         sim.run(25)
-        assert sim.ctx.status() == 0
+        assert sim.status_word() == 0
         runs.append((sim.ion_density.cpu().numpy().copy(), sim.electron_density.cpu().numpy().copy(),
                      sim.potential.cpu().numpy().copy(), _live_state(sim), sim.n_active()))
     a, b = runs
@@ -286,7 +286,7 @@ def test_moving_box_controller_in_the_loop(pkg):
     # a synthetic start has no settled hole yet: the tracked position jumps about, the law answers with
     # large accelerations, and a few injected particles can land outside the box ("bad left_index",
     # infMagSim_cython.py:272-273) exactly as they would in the reference; nothing else may be flagged
-    assert sim.ctx.status() & ~8 == 0
+    assert sim.status_word() & ~8 == 0
     pos = sim.hole_relative_positions.cpu().numpy()
     assert np.all(pos[:81] == 0) and np.abs(pos[81:]).max() > 0
     want_box, want_hv = _reference_box_loop(pos, sim.dt, 0.25, cfg.step_size, sim.v_th_e, cfg.debye_length, end)

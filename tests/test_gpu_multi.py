@@ -1,5 +1,6 @@
-"""N>1 on real GPUs: the peer-memory density exchange fused into the field-solve kernel against
-the NCCL all-reduce path (tests/multi_gpu_check.py under torchrun).  Needs >= 2 GPUs on the box;
+"""N>1 on real GPUs (tests/multi_gpu_check.py under torchrun): the 2-rank sharded run against the ORACLE loop
+on the union of the shards (4096 and 65536 cells, periodic and walls), and the peer-memory density exchange
+fused into the field-solve kernel against the NCCL all-reduce path.  Needs >= 2 GPUs on the box;
 the CPU-side sharding logic is covered by tests/test_distributed_cpu.py (gloo, world_size 2)."""
 import os
 import socket
@@ -22,5 +23,10 @@ def test_fused_exchange_matches_nccl_on_two_gpus():
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "multi_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    log_dir = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    if os.path.isdir(log_dir):   # kept: copied to profiles/ as the N>1 parity evidence
+        with open(os.path.join(log_dir, "multi_gpu_check.log"), "w") as fh:
+            fh.write(out.stdout + "\n--- stderr ---\n" + out.stderr[-4000:])
     assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("ORACLE cells=") == 4

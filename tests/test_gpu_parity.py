@@ -568,6 +568,51 @@ def test_hole_tracking_filter_and_histogram(ops, cpu):
     np.testing.assert_array_equal(h_gpu0.cpu().numpy(), h_ref0)
 
 
+def _tracking_potential(kind, grid, rng):
+    z = grid.astype(np.float64)
+    if kind == "hole":
+        phi = 0.3 * np.exp(-((z - 0.7) / 0.5) ** 2) + 0.002 * rng.standard_normal(len(z))
+    elif kind == "near_wall":
+        phi = 0.5 * np.exp(-((z + 2.6) / 0.3) ** 2) + 0.001 * rng.standard_normal(len(z))
+    elif kind == "two_holes":   # nearly equal depths: the maximum of the response is contested
+        phi = 0.30 * np.exp(-((z + 1.1) / 0.45) ** 2) + 0.3003 * np.exp(-((z - 1.4) / 0.45) ** 2)
+    elif kind == "noisy":       # particle-noise level of a coarse run
+        phi = 0.2 * np.exp(-(z / 0.6) ** 2) + 0.03 * rng.standard_normal(len(z))
+    else:                       # broad hole on a sinusoidal background
+        phi = 0.4 * np.exp(-((z - 0.2) / 1.2) ** 2) + 0.05 * np.sin(2 * np.pi * z / 1.7) + 0.002 * rng.standard_normal(len(z))
+    return phi.astype(np.float32)
+
+
+@pytest.mark.parametrize("n_points", [513, 4097, 65537])
+@pytest.mark.parametrize("kind", ["hole", "near_wall", "two_holes", "noisy", "broad"])
+def test_hole_tracking_argmax_at_baseline_grids(ops, cpu, n_points, kind):
+    """Hole position (ref infMagSim_c.c:668-683 + infMagSim_script.py:746-753) at the BASELINE grids: the same
+    fine-mesh INDEX as the compiled reference.  The reference accumulates 65537 float additions per mesh point;
+    where that noise makes two neighbouring points tie, +-1 index is accepted only if the float64-exact response
+    gap between the two points is below the reference's own accumulation error (measured here in float64)."""
+    grid = wl.make_grid(n_points - 1)
+    dz = 6.0 / (n_points - 1)
+    rng = np.random.default_rng(n_points + len(kind))
+    phi = _tracking_potential(kind, grid, rng)
+    fine = np.linspace(-3, 3, 1001).astype(np.float32)
+    sig = np.gradient(phi, dz).astype(np.float32)
+    r_ref = cpu.electric_field_filter(grid, sig, 0.5, fine)
+    r_gpu = ops.electric_field_filter(dev(grid), dev(sig), 0.5, dev(fine)).cpu().numpy()
+    pos = ops.hole_position_tracking(dev(phi), dz, 0.5, dev(grid), dev(fine), 6.0 / 1000).cpu().numpy()[0]
+    # float64-exact response on the reference's own float32 arguments s = fl(fl(x_i - g_j)/L) (ref :679)
+    exact = np.empty(len(fine))
+    for i0 in range(0, len(fine), 64):
+        s = ((fine[i0:i0 + 64, None] - grid[None, :]) / np.float32(0.5)).astype(np.float64)
+        exact[i0:i0 + 64] = (np.tanh(s) / np.cosh(s)) @ sig.astype(np.float64)
+    noise_ref = np.abs(r_ref - exact).max()
+    assert np.abs(r_gpu - exact).max() <= max(noise_ref, 2e-6 * np.abs(exact).max())   # at least as accurate as the reference
+    i_ref, i_gpu = int(np.argmax(r_ref)), int(np.argmax(r_gpu))
+    assert pos == fine[i_gpu]                                    # the fused gradient+filter+argmax kernel agrees with the filter
+    if i_gpu != i_ref:
+        assert abs(i_gpu - i_ref) <= 1, (i_gpu, i_ref)
+        assert abs(exact[i_gpu] - exact[i_ref]) <= noise_ref, (exact[i_gpu], exact[i_ref], noise_ref)
+
+
 def test_host_pointer_dropins(ops, cpu):
     """The reference-named symbols with HOST arrays (what a relinked Cython extension calls)."""
     import ctypes as C
