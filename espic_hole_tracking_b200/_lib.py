@@ -23,7 +23,7 @@ class Species(C.Structure):
     _fields_ = [("particles", c_void_p), ("empty_slots", c_void_p), ("current_empty_slot", c_void_p),
                 ("largest_index", c_void_p), ("density", c_void_p), ("potential", c_void_p),
                 ("particle_storage_length", c_int), ("largest_allowed_slot", c_int),
-                ("charge_to_mass", c_float), ("dt", c_float)]
+                ("charge_to_mass", c_float), ("dt", c_float), ("acc", c_void_p)]
 
 
 class StepArgs(C.Structure):
@@ -35,7 +35,8 @@ class StepArgs(C.Structure):
                 ("periodic_potential", c_int),
                 ("fix_ions", c_int), ("fix_electrons", c_int), ("exchange_parity", c_int),
                 ("exchange_step", c_int), ("reduced_ion_density", c_void_p),
-                ("reduced_electron_density", c_void_p), ("n_inject_ions", c_int), ("n_inject_electrons", c_int),
+                ("reduced_electron_density", c_void_p), ("ion_acc_pending", c_int), ("electron_acc_pending", c_int),
+                ("n_inject_ions", c_int), ("n_inject_electrons", c_int),
                 ("v_th_ions", c_float), ("v_d_ions", c_float), ("v_th_electrons", c_float),
                 ("v_d_electrons", c_float), ("inject_dt", c_float), ("step_index", c_int), ("ion_tags", c_void_p),
                 ("electron_tags", c_void_p), ("fine_mesh", c_void_p), ("filter_scratch", c_void_p),
@@ -72,6 +73,8 @@ SIGNATURES = {
     "espic_exchange_open": (c_int, [c_void_p, c_void_p]),
     "espic_exchange_slot": (c_int, [c_void_p, c_int, C.POINTER(c_void_p)]),
     "espic_exchange_publish": (c_int, [c_void_p, c_int, c_int]),
+    "espic_exchange_publish_fused": (c_int, [c_void_p, c_int, c_int, P, P, c_float]),
+    "espic_convert_density": (c_int, [c_void_p, P, P, c_int, c_float]),
     "espic_field_solve_exchange": (c_int, [c_void_p, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, c_float, P,
                                            c_float, c_float, c_int, c_int, c_int]),
     "espic_pic_step": (c_int, [c_void_p, C.POINTER(StepArgs)]),
@@ -94,6 +97,7 @@ SIGNATURES = {
     "move_particles_c_minimal": (None, [P, P, P, c_float, c_float, c_float, c_int, P, P, P, P, c_int,
                                         c_int, c_int, c_int, c_int]),
     "tridiagonal_solve_c": (None, [P, P, P, P, P, c_int]),
+    "espic_host_release": (None, []),
     "poisson_solve_c": (None, [P, P, P, c_float, P, c_float, c_float, c_int, c_int, c_int]),
     "draw_velocities_c": (None, [c_int, c_float, c_float, P]),
     "sgenrand": (None, [C.c_ulong]),

@@ -155,6 +155,7 @@ void espic_destroy(espic_ctx* ctx) {
     free_scratch(ctx->rng_ws);
     free_scratch(ctx->sort_ws);
     free_scratch(ctx->host_stage);
+    free_scratch(ctx->filter_ws);
     for (int r = 0; r < ctx->xch.world; ++r)
         if (r != ctx->xch.rank && ctx->xch.peer[r]) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
     if (ctx->xch.local) cudaFree(ctx->xch.local);
@@ -162,6 +163,10 @@ void espic_destroy(espic_ctx* ctx) {
         for (int i = 0; i < ctx->ev_cap; ++i) cudaEventDestroy(ctx->ev[i]);
         free(ctx->ev);
     }
+    for (int i = 0; i < ctx->pipe_ev_cap; ++i) cudaEventDestroy(ctx->pipe_ev[i]);
+    free(ctx->pipe_ev);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
     delete ctx;
 }
 
@@ -357,6 +362,20 @@ int espic_exchange_publish(espic_ctx* ctx, int parity, int step) {
     return exchange_publish(ctx, parity, step);
 }
 
+int espic_exchange_publish_fused(espic_ctx* ctx, int parity, int step, unsigned long long* ion_acc,
+                                 unsigned long long* electron_acc, float background_density) {
+    DeviceGuard guard(ctx);
+    if (!ctx) return ESPIC_E_ARG;
+    return exchange_publish(ctx, parity, step, ion_acc, electron_acc, background_density);
+}
+
+int espic_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points,
+                          float background_density) {
+    DeviceGuard guard(ctx);
+    if (!ctx || !acc || !density) return ESPIC_E_ARG;
+    return launch_convert_density(ctx, acc, density, n_points, background_density);
+}
+
 int espic_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* object_mask,
                                float* ion_density, float* electron_density, float* charge, int periodic_particles,
                                int fix_ions, int fix_electrons, float debye_length, float* potential,
@@ -382,6 +401,9 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
             !sp[i]->density)
             return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null species pointer");
     int rc;
+    unsigned long long* acc[2] = {a->ions.acc, a->electrons.acc};
+    if ((acc[0] == nullptr) != (acc[1] == nullptr))
+        return fail(ctx, ESPIC_E_ARG, "espic_pic_step: give both species an accumulator plane or neither");
     if (a->exchange_parity >= 0) {
         if (!a->reduced_ion_density || !a->reduced_electron_density)
             return fail(ctx, ESPIC_E_ARG, "espic_pic_step: exchange mode needs the reduced density buffers");
@@ -393,7 +415,9 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
     } else {
         rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
                                 a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
-                                a->object_potential, a->object_transparency, 0, a->periodic_potential, a->n_points);
+                                a->object_potential, a->object_transparency, 0, a->periodic_potential, a->n_points,
+                                a->ion_acc_pending ? acc[0] : nullptr, a->electron_acc_pending ? acc[1] : nullptr,
+                                a->background_density);
     }
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
@@ -401,7 +425,7 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,
                          s->charge_to_mass, a->background_density, -1, s->largest_index, s->particles, s->density,
                          s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic_particles, s->largest_allowed_slot,
-                         a->n_points, s->particle_storage_length);
+                         a->n_points, s->particle_storage_length, 0, 0, 1, acc[i]);
         if (rc) return rc;
     }
     if (a->hole_position_out) {
@@ -428,7 +452,7 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         const espic_species* s = sp[i];
         rc = launch_inject(ctx, n_inj[i], a->grid, a->n_points, a->inject_dt, a->background_density, vel, uni, a->a_b,
                            a->step_index, tags[i], s->particles, s->particle_storage_length, s->empty_slots,
-                           s->current_empty_slot, s->largest_index, s->density, true);
+                           s->current_empty_slot, s->largest_index, s->density, true, acc[i]);
         if (rc) return rc;
     }
     return ESPIC_OK;
@@ -580,6 +604,14 @@ static void pin_host_range(const void* ptr, size_t bytes, size_t capacity) {
     }
 }
 
+static void unpin_all() {
+    for (int i = 0; i < g_n_pinned; ++i) {
+        cudaHostUnregister(const_cast<void*>(g_pinned[i].ptr));
+        cudaGetLastError();
+    }
+    g_n_pinned = 0;
+}
+
 static void report_status(espic_ctx* ctx) {
     int st = 0;
     if (espic_status(ctx, &st)) return;
@@ -626,39 +658,101 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
         pin_host_range(particles, used * sizeof(float), S * sizeof(float));
         pin_host_range(particles + S, used * sizeof(float), S * sizeof(float));
     }
-    H2D(d_grid, grid, n, float);
-    if (minimal) {  // move_particles_c_minimal never looks at the mask (ref infMagSim_c.c:321-332, commented out)
-        if ((rc = check_cuda(ctx, cudaMemsetAsync(d_mask, 0, n * sizeof(float), ctx->stream), "memset"))) die(ctx, who, rc);
-    } else {
-        H2D(d_mask, object_mask, n, float);
-    }
-    H2D(d_phi, potential, n, float);
-    if (used) {
-        H2D(d_part, particles, used, float);
-        H2D(d_part + S, particles + S, used, float);
-    }
     // the mover only APPENDS to the stack (ref infMagSim_c.c:214-217): nothing to upload, and only
     // the entries between the old and the new top come back
     const int top_in = *current_empty_slot;
-    H2D(d_top, current_empty_slot, 1, int);
-    rc = launch_move(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, largest_index, nullptr,
-                     d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles, largest_allowed_slot,
-                     n_points, particle_storage_length, minimal);
-    if (rc) die(ctx, who, rc);
-    if (used) {
-        D2H(particles, d_part, used, float);
-        D2H(particles + S, d_part + S, used, float);
+
+    // Chunked pipeline: the used part of the store crosses PCIe in both directions every call
+    // (16 B per slot), the mover itself needs ~3 ps per slot.  The slots are cut into chunks; chunk
+    // i+1 is uploaded while chunk i is pushed and chunk i-1 is downloaded, on three streams (PCIe is
+    // full duplex and the GPU has separate copy engines for the two directions).  Every chunk is a
+    // complete mover call on its slot range (launch_move with slot_offset): removed slots reach the
+    // stack chunk by chunk in ascending slot order, exactly the reference's order, and the integer
+    // deposit accumulates over the chunks and is converted once, after the last one.
+    size_t chunk = 8u << 20;  // slots per chunk: 32 MB per row and direction
+    if (const char* e = getenv("ESPIC_HOST_CHUNK")) {  // tuning / test knob, read at every call
+        const long long v = atoll(e);
+        if (v >= 1024) chunk = (size_t)v & ~(size_t)1023;
     }
-    D2H(density, d_den, n, float);
-    D2H(current_empty_slot, d_top, 1, int);
-    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, who, rc);
+    const size_t n_chunks = used ? (used + chunk - 1) / chunk : 1;
+    const bool pipelined = n_chunks > 1;
+    cudaStream_t s_up = ctx->stream, s_run = ctx->stream, s_down = ctx->stream;
+    if (pipelined) {
+        for (int i = 0; i < 3; ++i)
+            if (!ctx->pipe_stream[i] &&
+                (rc = check_cuda(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking), "stream")))
+                die(ctx, who, rc);
+        if ((int)(2 * n_chunks) > ctx->pipe_ev_cap) {
+            const int cap = (int)(2 * n_chunks) + 16;
+            cudaEvent_t* ev = (cudaEvent_t*)calloc((size_t)cap, sizeof(cudaEvent_t));
+            if (!ev) die(ctx, who, ESPIC_E_NOMEM);
+            for (int i = 0; i < ctx->pipe_ev_cap; ++i) ev[i] = ctx->pipe_ev[i];
+            for (int i = ctx->pipe_ev_cap; i < cap; ++i)
+                if ((rc = check_cuda(ctx, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming), "event"))) die(ctx, who, rc);
+            free(ctx->pipe_ev);
+            ctx->pipe_ev = ev;
+            ctx->pipe_ev_cap = cap;
+        }
+        // whatever the caller queued on the context's stream comes first
+        if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, who, rc);
+        s_up = ctx->pipe_stream[0];
+        s_run = ctx->pipe_stream[1];
+        s_down = ctx->pipe_stream[2];
+    }
+#define COPY(dst, src, count, T, kind, st) \
+    if ((rc = check_cuda(ctx, cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(T), kind, st), "copy"))) die(ctx, who, rc)
+    COPY(d_grid, grid, n, float, cudaMemcpyHostToDevice, s_run);
+    if (minimal) {  // move_particles_c_minimal never looks at the mask (ref infMagSim_c.c:321-332, commented out)
+        if ((rc = check_cuda(ctx, cudaMemsetAsync(d_mask, 0, n * sizeof(float), s_run), "memset"))) die(ctx, who, rc);
+    } else {
+        COPY(d_mask, object_mask, n, float, cudaMemcpyHostToDevice, s_run);
+    }
+    COPY(d_phi, potential, n, float, cudaMemcpyHostToDevice, s_run);
+    COPY(d_top, current_empty_slot, 1, int, cudaMemcpyHostToDevice, s_run);
+    cudaStream_t saved = ctx->stream;
+    ctx->stream = s_run;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t off = c * chunk;
+        const size_t len = used ? (used - off < chunk ? used - off : chunk) : 0;
+        if (len) {
+            COPY(d_part + off, particles + off, len, float, cudaMemcpyHostToDevice, s_up);
+            COPY(d_part + S + off, particles + S + off, len, float, cudaMemcpyHostToDevice, s_up);
+        }
+        if (pipelined) {
+            cudaEventRecord(ctx->pipe_ev[2 * c], s_up);
+            cudaStreamWaitEvent(s_run, ctx->pipe_ev[2 * c], 0);
+        }
+        rc = launch_move(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, (int)len - 1, nullptr,
+                         d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles,
+                         largest_allowed_slot, n_points, particle_storage_length, minimal, (int)off,
+                         c + 1 == n_chunks ? 1 : 0);
+        if (rc) {
+            ctx->stream = saved;
+            die(ctx, who, rc);
+        }
+        if (pipelined) {
+            cudaEventRecord(ctx->pipe_ev[2 * c + 1], s_run);
+            cudaStreamWaitEvent(s_down, ctx->pipe_ev[2 * c + 1], 0);
+        }
+        if (len) {
+            COPY(particles + off, d_part + off, len, float, cudaMemcpyDeviceToHost, s_down);
+            COPY(particles + S + off, d_part + S + off, len, float, cudaMemcpyDeviceToHost, s_down);
+        }
+    }
+    ctx->stream = saved;
+    COPY(density, d_den, n, float, cudaMemcpyDeviceToHost, s_run);
+    COPY(current_empty_slot, d_top, 1, int, cudaMemcpyDeviceToHost, s_run);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(s_run), "sync"))) die(ctx, who, rc);
     {
         const long long first = (long long)top_in + 1;
         long long last = *current_empty_slot;
         if (last > largest_allowed_slot) last = largest_allowed_slot;
-        if (first >= 0 && last >= first) D2H(empty_slots + first, d_stack + first, last - first + 1, int);
+        if (first >= 0 && last >= first)
+            COPY(empty_slots + first, d_stack + first, last - first + 1, int, cudaMemcpyDeviceToHost, s_run);
     }
-    if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, who, rc);
+    if ((rc = check_cuda(ctx, cudaStreamSynchronize(s_run), "sync"))) die(ctx, who, rc);
+    if (pipelined && (rc = check_cuda(ctx, cudaStreamSynchronize(s_down), "sync"))) die(ctx, who, rc);
+#undef COPY
     report_status(ctx);
 }
 
@@ -715,6 +809,14 @@ void tridiagonal_solve_c(double* a, double* b, double* c, double* d, double* x, 
     D2H(d, d_d, n, double);
     D2H(x, d_x, n, double);
     if ((rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync"))) die(ctx, __func__, rc);
+}
+
+// The host-array movers page-lock the caller's particle arrays on first use and keep them registered (the
+// reference's driver passes the same arrays at every step).  A caller that frees or reallocates those arrays
+// calls this first; so does anything that wants the pages back.
+void espic_host_release(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    unpin_all();
 }
 
 void poisson_solve_c(float* grid, float* object_mask, float* charge, float debye_length, float* potential,

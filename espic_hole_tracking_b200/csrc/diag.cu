@@ -6,17 +6,75 @@
 
 namespace espic {
 
-// tanh(s)/cosh(s) with one exponential: with e = exp(-|s|),
-// tanh = (1-e^2)/(1+e^2), 1/cosh = 2e/(1+e^2).  Single precision with the hardware exponential
-// and reciprocal: ~3e-7 relative, two orders below the rounding noise of the reference's own
-// float accumulation over n_points terms (ref infMagSim_c.c:676-680), so the maximum it feeds
-// lands on the same fine-mesh point.
-__device__ __forceinline__ float tanh_over_cosh(float s) {
-    const float e = __expf(-fabsf(s));
-    const float e2 = e * e;
-    const float den = 1.f + e2;
-    const float r = __fdividef(2.f * e * (1.f - e2), den * den);
-    return copysignf(r, s);
+// ---- the hole-tracking filter -----------------------------------------------------------------------
+// Res[i] = sum_j K((fine[i]-grid[j])/L) * signal[j],  K(s) = tanh(s)/cosh(s)   (ref infMagSim_c.c:676-680)
+// is n_fine x n_points kernel evaluations -- 6.6e7 on the 65537-point grid, every step, each with two
+// special functions.  K is smooth on the scale of the grid spacing (dz/L = 1.8e-4 there), so the grid is
+// cut into blocks of G consecutive points with |grid[j] - centre|/L <= 6e-3 and K is expanded around the
+// block centre to third order:
+//     K(u - d) = K(u) - d K1(u) + d^2/2 K2(u) - d^3/6 K3(u) + O(d^4 K4/24)   (< 1e-9 relative)
+//     Res[i]  = sum_blocks  K(u_ib) M0_b + K1(u_ib) M1_b + K2(u_ib) M2_b + K3(u_ib) M3_b,
+// u_ib = (fine[i] - centre_b)/L, M_k,b = sum_{j in b} (-(grid[j]-centre_b)/L)^k / k! * signal[j]: the
+// moments cost one pass over the grid, the evaluations drop by the factor G (64 at 65537 points, 4 at
+// 4097, 1 -- i.e. the plain sum -- at 513) and everything runs in double precision: the result is the
+// exactly rounded response to ~1e-9, where the float accumulation of the reference (one rounding per
+// term, ref :679) is off by ~1e-5 of the response at 65537 points.  With t = tanh u, c = sech u the
+// derivatives are  K = t c,  K1 = c (1 - 2 t^2),  K2 = -t c (5 - 6 t^2),  K3 = c (-5 + 28 t^2 - 24 t^4).
+constexpr int kFilterMaxGroup = 64;
+constexpr double kFilterMaxDelta = 6e-3;
+
+struct FilterMoments {   // planes of n_blocks doubles
+    double* centre;
+    double* m[4];
+};
+
+// One warp per block of G grid points: centre and the four moments (fixed summation tree: deterministic).
+// GRADIENT: the signal is numpy's float32 gradient of `data` (central differences, one-sided ends,
+// ref infMagSim_script.py:746-749), formed here instead of in a pass of its own.
+template <bool GRADIENT>
+__global__ void __launch_bounds__(256) k_filter_moments(int n, int G, int n_blocks, const float* __restrict__ grid,
+                                                        const float* __restrict__ data, float div_mid, float div_end,
+                                                        double inv_L, FilterMoments mo, int* status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = warp; b < n_blocks; b += n_warps) {
+        const int j0 = b * G, j1 = min(n, j0 + G);
+        const double c = 0.5 * ((double)grid[j0] + (double)grid[j1 - 1]);
+        double m0 = 0., m1 = 0., m2 = 0., m3 = 0., dmax = 0.;
+        for (int j = j0 + lane; j < j1; j += 32) {
+            float sig;
+            if (GRADIENT) {
+                if (j == 0) sig = __fdiv_rn(__fsub_rn(data[1], data[0]), div_end);
+                else if (j == n - 1) sig = __fdiv_rn(__fsub_rn(data[n - 1], data[n - 2]), div_end);
+                else sig = __fdiv_rn(__fsub_rn(data[j + 1], data[j - 1]), div_mid);
+            } else {
+                sig = data[j];
+            }
+            const double d = -((double)grid[j] - c) * inv_L, sd = (double)sig;
+            m0 += sd;
+            m1 += sd * d;
+            m2 += sd * (0.5 * d * d);
+            m3 += sd * (d * d * d * (1. / 6.));
+            dmax = fmax(dmax, fabs(d));
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            m0 += __shfl_xor_sync(0xffffffffu, m0, s);
+            m1 += __shfl_xor_sync(0xffffffffu, m1, s);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, s);
+            m3 += __shfl_xor_sync(0xffffffffu, m3, s);
+            dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, s));
+        }
+        if (lane == 0) {
+            mo.centre[b] = c;
+            mo.m[0][b] = m0;
+            mo.m[1][b] = m1;
+            mo.m[2][b] = m2;
+            mo.m[3][b] = m3;
+            // a grid far from uniform can stretch a block beyond the range the expansion was sized for
+            if (dmax > 4. * kFilterMaxDelta) atomicOr(status, ESPIC_ST_FILTER_GRID);
+        }
+    }
 }
 
 // fine[argmax(res)] with numpy's first-maximum tie rule, by one CTA (any width that is a multiple of 32)
@@ -56,53 +114,37 @@ __device__ __forceinline__ void argmax_position(int n_fine, const float* res, co
 }
 
 constexpr int kFilterFine = 7;       // fine-mesh points per CTA: the 1001-point mesh makes 143 CTAs, one wave
-constexpr int kFilterThreads = 1024;
+constexpr int kFilterThreads = 256;
 
-// Res[i] = sum_j tanh((fine[i]-grid[j])/L) / cosh((fine[i]-grid[j])/L) * signal[j].
-// GRADIENT=false: data is the signal.  GRADIENT=true: data is a potential and the signal is
-// numpy's gradient of it in float32 (central differences, one-sided ends).
-// n_fine x n_points kernel evaluations (6.6e7 on the 65537-point grid, every step) bound by the
-// two special-function operations each costs: a CTA takes kFilterFine mesh points at once so that
-// grid and signal are loaded (and the gradient formed) once for all of them.  A thread sums its
-// n_points/1024 products in float (64 terms on the largest grid), the partial sums are reduced in
-// double.
-template <bool GRADIENT>
-__global__ void __launch_bounds__(kFilterThreads) k_field_filter(int n, const float* __restrict__ grid,
-                                                                 const float* __restrict__ data, float div_mid,
-                                                                 float div_end, float L, int n_fine,
-                                                                 const float* __restrict__ fine, float* res,
-                                                                 float* __restrict__ pos_out, unsigned* ticket) {
+// Res for kFilterFine mesh points per CTA from the block moments; with pos_out the last CTA to finish
+// takes fine[argmax(Res)] (ref infMagSim_script.py:750-753).
+__global__ void __launch_bounds__(kFilterThreads) k_filter_eval(int n_blocks, FilterMoments mo, double inv_L, int n_fine,
+                                                                const float* __restrict__ fine, float* res,
+                                                                float* __restrict__ pos_out, unsigned* ticket) {
     __shared__ double s_red[kFilterFine][kFilterThreads / 32];
     __shared__ int s_last;
-    const float inv_L = 1.f / L;
-    const bool exact_inv = (inv_L * L == 1.f) && (__float_as_uint(L) & 0x007fffffu) == 0u;  // L a power of two
     for (int i0 = blockIdx.x * kFilterFine; i0 < n_fine; i0 += gridDim.x * kFilterFine) {
-        float xf[kFilterFine], part[kFilterFine];
+        double xf[kFilterFine], part[kFilterFine];
 #pragma unroll
         for (int f = 0; f < kFilterFine; ++f) {
-            xf[f] = fine[min(i0 + f, n_fine - 1)];
-            part[f] = 0.f;
+            xf[f] = (double)fine[min(i0 + f, n_fine - 1)];
+            part[f] = 0.;
         }
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            float sig;
-            if (GRADIENT) {
-                if (j == 0) sig = __fdiv_rn(__fsub_rn(data[1], data[0]), div_end);
-                else if (j == n - 1) sig = __fdiv_rn(__fsub_rn(data[n - 1], data[n - 2]), div_end);
-                else sig = __fdiv_rn(__fsub_rn(data[j + 1], data[j - 1]), div_mid);
-            } else {
-                sig = data[j];
-            }
-            const float g = grid[j];
+        for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+            const double c = mo.centre[b], m0 = mo.m[0][b], m1 = mo.m[1][b], m2 = mo.m[2][b], m3 = mo.m[3][b];
 #pragma unroll
             for (int f = 0; f < kFilterFine; ++f) {
-                const float d = __fsub_rn(xf[f], g);
-                const float s = exact_inv ? d * inv_L : __fdiv_rn(d, L);   // ref :679, a float quotient
-                part[f] = fmaf(tanh_over_cosh(s), sig, part[f]);
+                const double u = (xf[f] - c) * inv_L;
+                const double e = exp(-fabs(u)), e2 = e * e, r = 1. / (1. + e2);
+                const double t = copysign((1. - e2) * r, u), ch = 2. * e * r, t2 = t * t;   // tanh u, sech u
+                const double k0 = t * ch, k1 = ch * (1. - 2. * t2), k2 = -k0 * (5. - 6. * t2),
+                             k3 = ch * (-5. + t2 * (28. - 24. * t2));
+                part[f] += k0 * m0 + k1 * m1 + k2 * m2 + k3 * m3;
             }
         }
 #pragma unroll
         for (int f = 0; f < kFilterFine; ++f) {
-            double p = (double)part[f];
+            double p = part[f];
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) p += __shfl_xor_sync(0xffffffffu, p, d);
             if ((threadIdx.x & 31) == 0) s_red[f][threadIdx.x >> 5] = p;
@@ -115,7 +157,7 @@ __global__ void __launch_bounds__(kFilterThreads) k_field_filter(int n, const fl
         }
         __syncthreads();
     }
-    if (pos_out) {  // hole position = fine[argmax(Res)] (ref infMagSim_script.py:746-753), by the last CTA to finish
+    if (pos_out) {  // hole position = fine[argmax(Res)], by the last CTA to finish
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
@@ -157,25 +199,60 @@ __global__ void __launch_bounds__(256) k_histogram(const float* __restrict__ xs,
     }
 }
 
+// Block size of the expansion for this grid and filter width: |grid[j] - centre|/L <= kFilterMaxDelta for a
+// uniform grid (the reference builds its grid with np.linspace); 1 = plain summation.
+static int filter_group(const float* grid_ends, int n_points, float L) {
+    const double dz = fabs((double)grid_ends[1] - (double)grid_ends[0]) / (double)(n_points > 1 ? n_points - 1 : 1);
+    if (!(dz > 0.) || !(L > 0.f)) return 1;
+    const double g = 2. * kFilterMaxDelta * (double)L / dz;
+    return g >= (double)kFilterMaxGroup ? kFilterMaxGroup : (g < 1. ? 1 : (int)g);
+}
+
+template <bool GRADIENT>
+static int run_filter(espic_ctx* ctx, int n_points, const float* grid, const float* data, float div_mid, float div_end,
+                      float L, int n_fine, const float* fine, float* res, float* pos_out) {
+    // the end points of the grid decide the block size; they never change in a run, so they are fetched once
+    // per (grid pointer, n_points) and cached in the context
+    if (ctx->filter_grid != grid || ctx->filter_n != n_points) {
+        float ends[2];
+        ESPIC_CUDA(ctx, cudaMemcpyAsync(&ends[0], grid, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        ESPIC_CUDA(ctx, cudaMemcpyAsync(&ends[1], grid + n_points - 1, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        ESPIC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->filter_grid = grid;
+        ctx->filter_n = n_points;
+        ctx->filter_ends[0] = ends[0];
+        ctx->filter_ends[1] = ends[1];
+    }
+    const int G = filter_group(ctx->filter_ends, n_points, L);
+    const int n_blocks = (n_points + G - 1) / G;
+    int rc = ensure(ctx, ctx->filter_ws, (size_t)5 * n_blocks * sizeof(double) + 64, "filter moments");
+    if (rc) return rc;
+    FilterMoments mo;
+    mo.centre = (double*)ctx->filter_ws.ptr;
+    for (int k = 0; k < 4; ++k) mo.m[k] = mo.centre + (size_t)(k + 1) * n_blocks;
+    const double inv_L = 1. / (double)L;
+    int mg = (n_blocks + 7) / 8;   // 8 warps per CTA, one block per warp
+    if (mg > 2 * ctx->sm_count) mg = 2 * ctx->sm_count;
+    k_filter_moments<GRADIENT><<<mg, 256, 0, ctx->stream>>>(n_points, G, n_blocks, grid, data, div_mid, div_end, inv_L, mo,
+                                                          ctx->status);
+    const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
+    k_filter_eval<<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
+        n_blocks, mo, inv_L, n_fine, fine, res, pos_out, (unsigned*)(ctx->status + 9));
+    ctx->launches += 2;
+    return check_cuda(ctx, cudaGetLastError(), "field filter launch");
+}
+
 int launch_field_filter(espic_ctx* ctx, int n_points, const float* grid, const float* data, float L,
                         int n_fine, const float* fine, float* res) {
     if (n_points < 1 || n_fine < 1) return 0;
-    const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
-    k_field_filter<false><<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
-        n_points, grid, data, 1.f, 1.f, L, n_fine, fine, res, nullptr, nullptr);
-    ctx->launches++;
-    return check_cuda(ctx, cudaGetLastError(), "k_field_filter launch");
+    return run_filter<false>(ctx, n_points, grid, data, 1.f, 1.f, L, n_fine, fine, res, nullptr);
 }
 
 int launch_hole_position(espic_ctx* ctx, int n_points, const float* grid, const float* potential, double dz,
                          float L, int n_fine, const float* fine, float* scratch_res, float* pos_out) {
     if (n_points < 2 || n_fine < 1) return fail(ctx, ESPIC_E_ARG, "hole_position needs n_points>=2, n_fine>=1");
-    const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
-    k_field_filter<true><<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
-        n_points, grid, potential, (float)(2. * dz), (float)dz, L, n_fine, fine, scratch_res, pos_out,
-        (unsigned*)(ctx->status + 9));
-    ctx->launches++;
-    return check_cuda(ctx, cudaGetLastError(), "hole position launch");
+    return run_filter<true>(ctx, n_points, grid, potential, (float)(2. * dz), (float)dz, L, n_fine, fine, scratch_res,
+                            pos_out);
 }
 
 int launch_histogram(espic_ctx* ctx, const float* xs, const float* ys, int n_data, const int* tags,

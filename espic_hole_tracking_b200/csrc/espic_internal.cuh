@@ -167,7 +167,15 @@ struct espic_ctx {
     espic::Scratch rng_ws;              // MT19937 state + stream buffers
     espic::Scratch sort_ws;             // radix-sort ping-pong buffers and histograms
     espic::Scratch host_stage;          // device staging for the host-pointer entry points
+    espic::Scratch filter_ws;           // block centres + moments of the hole-tracking filter
+    const float* filter_grid = nullptr; // grid whose end points are cached below
+    int filter_n = 0;
+    float filter_ends[2] = {0.f, 0.f};
     int* dev_int2 = nullptr;            // two device ints used by the host-pointer wrappers
+    // the pipelined host-array mover: upload / compute / download streams and per-chunk events
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t* pipe_ev = nullptr;
+    int pipe_ev_cap = 0;
 
     // multi-GPU density exchange (see solve.cu)
     struct Exchange {
@@ -242,7 +250,8 @@ struct DeviceGuard {
 int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const float* phi, float dt,
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
-                int periodic, int largest_allowed_slot, int n_points, int storage, int minimal = 0);
+                int periodic, int largest_allowed_slot, int n_points, int storage, int minimal = 0,
+                int slot_offset = 0, int finish_density = 1, unsigned long long* acc_fused = nullptr);
 int launch_tridiagonal(espic_ctx* ctx, double* a, double* b, double* c, double* d, double* x, int n);
 int move_window_cells(espic_ctx* ctx, int n_points);  // 0: whole-grid tables fit in shared memory
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);
@@ -256,10 +265,12 @@ int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const f
 int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, float* ion, float* ele,
                        float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
                        float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
-                       int n_points);
+                       int n_points, unsigned long long* acc_i = nullptr, unsigned long long* acc_e = nullptr,
+                       float bg = 1.f);
 int exchange_create(espic_ctx* ctx, int n_points, int world, int rank, void* handle_out);
 int exchange_open(espic_ctx* ctx, const void* handles);
-int exchange_publish(espic_ctx* ctx, int parity, int step);
+int exchange_publish(espic_ctx* ctx, int parity, int step, unsigned long long* acc_i = nullptr,
+                     unsigned long long* acc_e = nullptr, float bg = 1.f);
 int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* mask,
                                 float* ion, float* ele, float* charge_out, int periodic_particles, int fix_i,
                                 int fix_e, float debye, float* potential, float obj_pot, float transparency,
@@ -268,9 +279,11 @@ int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge,
                           int fix_i, int fix_e);
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
-                  int storage, int* empty_slots, int* top, int* largest, float* density, bool classified = false);
+                  int storage, int* empty_slots, int* top, int* largest, float* density, bool classified = false,
+                  unsigned long long* acc_fused = nullptr);
 int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
                              const float* grid, int n_points, float dt, float bg, float a_b);
+int launch_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points, float bg);
 int rng_seed(espic_ctx* ctx, unsigned long seed);
 int rng_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out);
 int rng_uniforms(espic_ctx* ctx, int n, float* out);

@@ -256,7 +256,7 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
     const int n = a.n_points;
     // injected particles sit within |v| dt of a wall: unless a deposit went further in, only the
     // two wall regions can hold anything
-    const int span = everywhere ? n : 2 * kWallNodes;
+    const int span = a.density ? (everywhere ? n : 2 * kWallNodes) : 0;  // fused step path: the deposit stays in the accumulators
     for (int jj = threadIdx.x; jj < span; jj += blockDim.x) {
         const int j = everywhere ? jj : (jj < kWallNodes ? jj : (n - kWallNodes) + (jj - kWallNodes));
         const unsigned long long v = __ldcg(a.acc + j);
@@ -381,11 +381,16 @@ static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const f
 
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
-                  int storage, int* empty_slots, int* top, int* largest, float* density, bool classified) {
+                  int storage, int* empty_slots, int* top, int* largest, float* density, bool classified,
+                  unsigned long long* acc_fused) {
     if (n_inject <= 0) return 0;
     InjectArgs a{};
     int rc = fill_inject_args(ctx, a, n_inject, grid, n_points, dt, bg, a_b);
     if (rc) return rc;
+    if (acc_fused) {  // step path: add to the caller's accumulators (converted by the next field solve)
+        a.acc = acc_fused;
+        density = nullptr;
+    }
     a.vel = vel;
     a.uni = uni;
     a.px = particles;

@@ -42,6 +42,54 @@
 namespace espic {
 
 
+// Removal bookkeeping of the round-robin (per-unit ranges) periodic variant by ONE CTA, the last one to finish
+// (MoveArgs::epilogue): nothing to do unless a slot was removed, which a periodic run practically never does;
+// then the per-unit counts are scanned and the staged ids pushed on the stack in ascending slot order, as
+// k_finish + k_scatter would.  Out of line: none of this may weigh on the register allocation of the main loop.
+__device__ __noinline__ void removal_epilogue_strided(const MoveArgs& a, int n_slots) {
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int total = __ldcg(a.total_removed);
+    if (total != 0) {  // uniform
+        const int n_chunks = (n_slots >> 2) / kUnitQuads + 1;  // the units + the tail range
+        const int per = (n_chunks + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int i0 = min(tid * per, n_chunks), i1 = min(i0 + per, n_chunks);
+        int sum = 0;
+        for (int i = i0; i < i1; ++i) sum += __ldcg(a.counts + i);
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int ww = 0; ww < w; ++ww) before += s_warp[ww];
+        int run = before + incl - sum;
+        const int old_top = *a.top;
+        for (int i = i0; i < i1; ++i) {
+            const int cnt = __ldcg(a.counts + i);
+            if (cnt) {
+                const int* src = a.staging + (size_t)i * kUnitSlots;
+                for (int q = 0; q < cnt; ++q) {
+                    const int dst = old_top + 1 + run + q;
+                    if (dst >= 0 && dst <= a.largest_allowed_slot) a.empty_slots[dst] = __ldcg(src + q) + a.slot_offset;
+                }
+                a.counts[i] = 0;  // per-unit counts are kept zeroed between launches
+                run += cnt;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            *a.top = old_top + total;
+            if (old_top + total > a.largest_allowed_slot) atomicOr(a.status, ESPIC_ST_STACK_OVERFLOW);
+            *a.total_removed = 0;
+        }
+    }
+    if (tid == 0) *a.ticket = 0u;
+}
+
 // FAST: complete units run the register fast path on float4 quads; everything else (the slots behind the last
 // complete unit, unaligned stores, start-up calls with update_position=0, an absorbing
 // object, exotic dz) goes quad by quad through quad_generic.
@@ -121,14 +169,17 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
                 const float4* src = ring + stage * 128 + lane;
                 Quad p0, p1;
                 unpack_quad(src[0], src[32], p0);
-                unpack_quad(src[64], src[96], p1);
-                if (u + du < ue) issue(u + du, stage ^ 1);  // uniform
+                if (u + du < ue) issue(u + du, stage ^ 1);  // uniform; fills the OTHER stage
                 if (lane < 16 && u + a.prefetch_units * du < split.n_units) {
                     const float* row = (lane & 8) ? a.pv : a.px;
                     const float* line = row + (size_t)(u + a.prefetch_units * du) * kUnitSlots + (lane & 7) * 32;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
                 }
                 const unsigned r0 = quad_fast<PERIODIC, SMEM>(a, g, p0, q0, n_slots, dv, s_lo, s_hi);
+                // the second quad is read from the ring only now: its stage is not overwritten before the next
+                // iteration, and nothing of it has to survive the first quad in registers (or in local memory:
+                // both quads held at once spilled 16 words per iteration at 64 registers per thread)
+                unpack_quad(src[64], src[96], p1);
                 const unsigned r1 = quad_fast<PERIODIC, SMEM>(a, g, p1, q1, n_slots, dv, s_lo, s_hi);
                 if (!PERIODIC || __any_sync(0xffffffffu, (r0 | r1) != 0u)) {
                     if (STRIDED) {  // every unit is its own range: staged behind the unit, counted per unit
@@ -223,6 +274,17 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
             if (lo | hi) atomicAdd(a.acc + jj, ((unsigned long long)hi << 32) | lo);
         }
     }
+    if (STRIDED && a.epilogue) {  // uniform
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            removal_epilogue_strided(a, n_slots);
+        }
+    }
 }
 
 // Kick table + object flag for the large-grid path.
@@ -258,6 +320,8 @@ struct FinishArgs {
     int n_points;
     double inv_scale;   // 2^-24 / background_density
     int* flags_global;  // [0] object flag, [1] segment counter: reset for the next large-grid launch
+    int convert;        // 0: leave the accumulators as they are (a later launch over another part of the
+                        // store adds to them and converts: chunked host-array calls)
 };
 
 // Fixed-point accumulators -> float density (and re-zero them), by all CTAs; then CTA 0:
@@ -266,10 +330,12 @@ struct FinishArgs {
 __global__ void __launch_bounds__(1024) k_finish(const FinishArgs a) {
     __shared__ int s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int j = blockIdx.x * blockDim.x + tid; j < a.n_points; j += gridDim.x * blockDim.x) {
-        const unsigned long long v = a.acc[j];
-        a.density[j] = (float)((double)v * a.inv_scale);
-        a.acc[j] = 0ull;
+    if (a.convert) {
+        for (int j = blockIdx.x * blockDim.x + tid; j < a.n_points; j += gridDim.x * blockDim.x) {
+            const unsigned long long v = a.acc[j];
+            a.density[j] = (float)((double)v * a.inv_scale);
+            a.acc[j] = 0ull;
+        }
     }
     if (blockIdx.x != 0) return;  // large grids: the other CTAs only help with the conversion
     const int total = a.scatter_hdr[3];
@@ -334,7 +400,8 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging
                                                  const int* __restrict__ offsets,
                                                  const int* __restrict__ hdr, int* __restrict__ empty_slots,
                                                  int largest_allowed_slot, const int* largest_index_dev,
-                                                 int largest_index, int mover_warps, int* strided_counts) {
+                                                 int largest_index, int mover_warps, int* strided_counts,
+                                                 int slot_offset) {
     const int total = hdr[1];
     if (total == 0) return;
     const int old_top = hdr[0], n_chunks = hdr[2];
@@ -354,12 +421,29 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging
                              ? staging + (size_t)c * kUnitSlots
                              : staging + (size_t)(c < mover_warps ? split.first_unit(c) : split.n_units) * kUnitSlots;
         const int dst = old_top + 1 + i;
-        if (dst >= 0 && dst <= largest_allowed_slot) empty_slots[dst] = src[i - __ldg(offsets + c)];
+        if (dst >= 0 && dst <= largest_allowed_slot) empty_slots[dst] = src[i - __ldg(offsets + c)] + slot_offset;
     }
     // per-unit counts are only ever written when non-zero: leave them zeroed for the next launch
     if (strided_counts)
         for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += stride)
             if (strided_counts[c]) strided_counts[c] = 0;
+}
+
+// Fixed-point accumulators -> float density (the conversion k_finish makes), accumulators cleared.
+__global__ void k_convert_density(unsigned long long* __restrict__ acc, float* __restrict__ density, int n,
+                                  double inv_scale) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        density[j] = (float)((double)acc[j] * inv_scale);
+        acc[j] = 0ull;
+    }
+}
+
+int launch_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points, float bg) {
+    if (n_points < 1) return 0;
+    k_convert_density<<<(n_points + 1023) / 1024, 1024, 0, ctx->stream>>>(acc, density, n_points,
+                                                                         1.0 / ((double)kWeightOne * (double)bg));
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_convert_density launch");
 }
 
 __global__ void k_shift_velocities(float* __restrict__ v, int n, double v_b) {
@@ -425,8 +509,16 @@ static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
 int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const float* phi, float dt,
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
-                int periodic, int largest_allowed_slot, int n_points, int storage, int minimal) {
+                int periodic, int largest_allowed_slot, int n_points, int storage, int minimal, int slot_offset,
+                int finish_density, unsigned long long* acc_fused) {
+    // acc_fused (the step path, espic_pic_step): the deposit is ADDED to these caller-owned fixed-point
+    // accumulators and left there -- the next field solve converts it -- and `density` is not touched.
+    // slot_offset / finish_density: the call covers slots [slot_offset, slot_offset + largest_index] of the
+    // store only; removed slots are reported with their store-wide numbers, and the density is converted
+    // (and the accumulators cleared) only when finish_density is set -- a store processed in several
+    // consecutive calls (the pipelined host-array drop-in) deposits exactly what one call would.
     if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
+    if (slot_offset < 0 || (slot_offset & 3)) return fail(ctx, ESPIC_E_ARG, "slot_offset must be a multiple of 4");
     if (storage < 1) return fail(ctx, ESPIC_E_ARG, "particle_storage_length must be >= 1");
     if (!largest_index_dev && largest_index >= storage)
         return fail(ctx, ESPIC_E_ARG, "largest_index %d >= storage %d", largest_index, storage);
@@ -451,16 +543,21 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.grid = grid;
     a.mask = mask;
     a.phi = phi;
-    a.px = particles;
-    a.pv = particles + storage;
+    a.px = particles + slot_offset;
+    a.pv = particles + storage + slot_offset;
     a.staging = (int*)ctx->staging.ptr;
     int* counts_contiguous = (int*)ctx->chunk_counts.ptr + 8;  // first 8 ints: scatter header
     int* counts_strided = counts_contiguous + max_ranges + 8;
     int* offsets = (int*)ctx->range_offsets.ptr;
     a.counts = counts_contiguous;
     a.total_removed = (int*)ctx->chunk_counts.ptr + 3;
-    a.acc = ctx->acc;
+    a.acc = acc_fused ? acc_fused : ctx->acc;
     a.status = ctx->status;
+    a.ticket = (unsigned*)(ctx->status + 10);
+    a.top = top;
+    a.empty_slots = empty_slots;
+    a.largest_allowed_slot = largest_allowed_slot;
+    a.slot_offset = slot_offset;
     a.largest_index_dev = largest_index_dev;
     a.largest_index = largest_index;
     a.n_points = n_points;
@@ -499,6 +596,8 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     }
     a.strided = (a.staged && strided_env) ? 1 : 0;
     if (a.strided) a.counts = counts_strided;
+    // windowed / global-table launches never take the round-robin kernel
+    a.epilogue = (acc_fused && a.strided && periodic && use_smem) ? 1 : 0;
     const size_t smem = use_smem ? tile + (a.staged ? ring : 0) : 0;
     // L2 prefetch distance, measured on B200 (1e8 particles, 4096 cells): one unit ahead of the next
     // fetch is best in both modes -- 0.373 ms without it, 0.305 ms with it (staged)
@@ -530,9 +629,10 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
         rc = use_smem ? launch_move_variant<false, true>(ctx, a, smem) : launch_move_variant<false, false>(ctx, a, 0);
     }
     if (rc) return rc;
+    if (a.epilogue) return 0;  // the mover's last CTA has done the removal bookkeeping; the deposit stays in acc_fused
 
     FinishArgs f{};
-    f.acc = ctx->acc;
+    f.acc = a.acc;
     f.density = density;
     f.counts = a.counts;
     f.offsets = offsets;
@@ -549,12 +649,13 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     f.n_points = n_points;
     f.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
     f.flags_global = flags;
+    f.convert = acc_fused ? 0 : finish_density;
     k_finish<<<n_points <= 8192 ? 1 : (n_points + 4095) / 4096, 1024, 0, ctx->stream>>>(f);
     ctx->launches++;
     ESPIC_CUDA(ctx, cudaGetLastError());
     k_scatter<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(a.staging, offsets, f.scatter_hdr, empty_slots,
                                                       largest_allowed_slot, largest_index_dev, largest_index,
-                                                      mover_warps, a.strided ? a.counts : nullptr);
+                                                      mover_warps, a.strided ? a.counts : nullptr, slot_offset);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "mover epilogue launch");
 }

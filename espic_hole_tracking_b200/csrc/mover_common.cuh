@@ -39,6 +39,15 @@ struct MoveArgs {
     int strided;         // experiment: units dealt round-robin to the warps instead of in contiguous ranges
     int* seg_counter;    // windowed kernel: next segment to hand out (reset by k_finish)
     int n_segments;      // windowed kernel: segments of 32 ranges each
+    // fused step path, round-robin periodic variant: the last CTA to finish does the removal bookkeeping
+    // itself when (and only when) a slot was removed -- in a periodic box that needs a particle flung past
+    // 0.99*2*z_max -- so a step needs no k_finish / k_scatter launch
+    int epilogue;
+    unsigned* ticket;
+    int* top;
+    int* empty_slots;
+    int largest_allowed_slot;
+    int slot_offset;
     int minimal;  // move_particles_c_minimal (ref infMagSim_c.c:231-341): no mask, and a slot that is out of
                   // bounds on entry is left alone even when it does not carry the parked marker (ref :333)
 };
@@ -135,28 +144,27 @@ __device__ __forceinline__ void deposit_one(const Geom& g, float x, int cell, un
     }
 }
 
-// Deposit of a whole quad without per-slot branches: the eight atomics are issued
-// unconditionally and their (practically never set) carries are collected in a bit mask that
-// is resolved behind one warp vote.
+// Deposit of a whole quad without per-slot branches: the eight atomics are issued unconditionally.
+// A word can only wrap when its old value lies within 2^24 of 2^32 (a weight is at most 2^24), so one
+// running maximum over the eight returned values tells whether ANY of them might have carried; the exact
+// per-word test and the carry into the high plane run behind one warp vote, practically never.
 template <bool SMEM>
 __device__ __forceinline__ void deposit_quad_all(const Geom& g, const float* x, const int* cell, unsigned* s_lo,
                                                  unsigned* s_hi, unsigned long long* acc) {
     if (SMEM) {
-        unsigned carries = 0;
+        unsigned w[8], old[8], top = 0u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            unsigned w0, w1;
-            node_weights_fixed(g, x[c], cell[c], w0, w1);
-            const unsigned old0 = atomicAdd(s_lo + cell[c], w0);
-            const unsigned old1 = atomicAdd(s_lo + cell[c] + 1, w1);
-            if (old0 > ~w0) carries |= 1u << (2 * c);
-            if (old1 > ~w1) carries |= 2u << (2 * c);
+            node_weights_fixed(g, x[c], cell[c], w[2 * c], w[2 * c + 1]);
+            old[2 * c] = atomicAdd(s_lo + cell[c], w[2 * c]);
+            old[2 * c + 1] = atomicAdd(s_lo + cell[c] + 1, w[2 * c + 1]);
+            top = max(top, max(old[2 * c], old[2 * c + 1]));
         }
-        if (__any_sync(0xffffffffu, carries != 0u)) {
+        if (__any_sync(0xffffffffu, top >= 0xFF000000u)) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (carries & (1u << (2 * c))) atomicAdd(s_hi + cell[c], 1u);
-                if (carries & (2u << (2 * c))) atomicAdd(s_hi + cell[c] + 1, 1u);
+                if (old[2 * c] > ~w[2 * c]) atomicAdd(s_hi + cell[c], 1u);
+                if (old[2 * c + 1] > ~w[2 * c + 1]) atomicAdd(s_hi + cell[c] + 1, 1u);
             }
         }
     } else {

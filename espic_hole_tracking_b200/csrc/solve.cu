@@ -158,6 +158,12 @@ struct SolveArgs {
     const unsigned* peer_flag[ESPIC_MAX_RANKS];
     int n_pad;
     unsigned long long timeout_ns;            // how long to wait for a peer's publication
+    // fused deposit: when set, the density of that species is still in the movers' fixed-point
+    // accumulators; the prologue converts it (the one float rounding per node k_finish would have
+    // made), stores it in ion / ele and clears the accumulators for the next pushes
+    unsigned long long* acc_i;
+    unsigned long long* acc_e;
+    double inv_scale;                         // 2^-24 / background_density
 };
 
 constexpr int kMaxTeam = 8;  // portable cluster size
@@ -730,7 +736,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     const bool cacheable = (a.transparency == 1.f) && !a.boltzmann;
     if (tid == 0) {
         if (a.ion) {  // every CTA works the fixed end values out for itself; CTA 0 stores them
-            float i0 = a.ion[0], i1 = a.ion[n - 1], e0 = a.ele[0], e1 = a.ele[n - 1];
+            float i0 = a.acc_i ? (float)((double)__ldcg(a.acc_i) * a.inv_scale) : a.ion[0];
+            float i1 = a.acc_i ? (float)((double)__ldcg(a.acc_i + n - 1) * a.inv_scale) : a.ion[n - 1];
+            float e0 = a.acc_e ? (float)((double)__ldcg(a.acc_e) * a.inv_scale) : a.ele[0];
+            float e1 = a.acc_e ? (float)((double)__ldcg(a.acc_e + n - 1) * a.inv_scale) : a.ele[n - 1];
             if (a.fold_ends) {
                 if (a.fix_i) { i0 = __fadd_rn(i0, i1); i1 = i0; }
                 if (a.fix_e) { e0 = __fadd_rn(e0, e1); e1 = e0; }
@@ -755,8 +764,23 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         for (int i = 0; i < m; ++i) {
             const int j = tm.T * m + i;
             if (j >= n) break;
-            const float x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : a.ion[j];
-            const float yv = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : a.ele[j];
+            float x, yv;
+            if (a.acc_i) {  // every CTA has read the raw end nodes before the barrier above: the words can go
+                x = (float)((double)__ldcg(a.acc_i + j) * a.inv_scale);
+                a.acc_i[j] = 0ull;
+                if (j != 0 && j != n - 1) a.ion[j] = x;
+            } else {
+                x = a.ion[j];
+            }
+            if (a.acc_e) {
+                yv = (float)((double)__ldcg(a.acc_e + j) * a.inv_scale);
+                a.acc_e[j] = 0ull;
+                if (j != 0 && j != n - 1) a.ele[j] = yv;
+            } else {
+                yv = a.ele[j];
+            }
+            x = (j == 0) ? s_end[0] : (j == n - 1) ? s_end[1] : x;
+            yv = (j == 0) ? s_end[2] : (j == n - 1) ? s_end[3] : yv;
             a.charge_out[j] = __fsub_rn(x, yv);
         }
         charge = a.charge_out;
@@ -1011,7 +1035,7 @@ int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const f
 int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, float* ion, float* ele,
                        float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
                        float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
-                       int n_points) {
+                       int n_points, unsigned long long* acc_i, unsigned long long* acc_e, float bg) {
     SolveArgs a{};
     a.grid = grid;
     a.mask = mask;
@@ -1028,6 +1052,9 @@ int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, flo
     a.fix_e = fix_e;
     a.n = n_points;
     a.fold_ends = periodic_particles;  // the driver ties the two flags (infMagSim_script.py:146); they are independent here
+    a.acc_i = acc_i;
+    a.acc_e = acc_e;
+    a.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
     return launch_poisson_impl(ctx, a);
 }
 
@@ -1077,17 +1104,37 @@ int exchange_open(espic_ctx* ctx, const void* handles) {
     return 0;
 }
 
-__global__ void k_publish(unsigned* flag, unsigned value) {
+// One CTA.  Fused deposit: the rows still sitting in the movers' fixed-point accumulators are converted
+// into this rank's exchange slot first (and the accumulators cleared for the next pushes).
+__global__ void __launch_bounds__(1024) k_publish(unsigned* flag, unsigned value, unsigned long long* acc_i,
+                                                  unsigned long long* acc_e, float* slot, int n, int n_pad,
+                                                  double inv_scale) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        if (acc_i) {
+            slot[j] = (float)((double)acc_i[j] * inv_scale);
+            acc_i[j] = 0ull;
+        }
+        if (acc_e) {
+            slot[n_pad + j] = (float)((double)acc_e[j] * inv_scale);
+            acc_e[j] = 0ull;
+        }
+    }
     // everything enqueued before this kernel on the stream (pushes, injections) has completed;
-    // make it visible system-wide, then publish
+    // make it -- and the rows written above -- visible system-wide, then publish
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
-int exchange_publish(espic_ctx* ctx, int parity, int step) {
+int exchange_publish(espic_ctx* ctx, int parity, int step, unsigned long long* acc_i, unsigned long long* acc_e,
+                     float bg) {
     auto& x = ctx->xch;
     if (!x.local) return fail(ctx, ESPIC_E_ARG, "espic_exchange_publish: no exchange");
-    k_publish<<<1, 1, 0, ctx->stream>>>(xch_flag(x.local, x, parity & 1), (unsigned)step);
+    const bool convert = acc_i || acc_e;
+    k_publish<<<1, convert ? 1024 : 32, 0, ctx->stream>>>(xch_flag(x.local, x, parity & 1), (unsigned)step, acc_i, acc_e,
+                                                       xch_slot(x.local, x, parity & 1), convert ? x.n_points : 0,
+                                                       (int)(x.slot_floats / 2),
+                                                       convert ? 1.0 / ((double)kWeightOne * (double)bg) : 0.);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_publish launch");
 }

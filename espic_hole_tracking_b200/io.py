@@ -107,6 +107,7 @@ def save_checkpoint(sim, path: str) -> None:
     """Complete state of one rank: stores, stacks, tags, fields, pending deposits, the host generator,
     the device sampler's stream position (Philox key + calls consumed) and the controller."""
     sim.check_status()
+    sim.flush_pending()   # a fused deposit still in its accumulators becomes the float rows stored below
     state = {"k": sim.k, "t": sim.t, "cfg": dict(sim.cfg.__dict__), "rank": sim.rank, "world": sim.world,
              "potential": sim.potential.cpu(), "densities": sim.densities.cpu(), "charge": sim.charge_density.cpu(),
              "hole": sim.hole_relative_positions.cpu(), "host_rng": sim.host_rng.get_state(),
@@ -138,6 +139,8 @@ def load_checkpoint(sim, path: str) -> None:
         raise ValueError(f"checkpoint of rank {state.get('rank')}/{state.get('world')} loaded on rank "
                          f"{sim.rank}/{sim.world}")
     sim.k, sim.t = state["k"], state["t"]
+    sim.acc.zero_()
+    sim._acc_pending = [False, False]
     sim.potential.copy_(state["potential"])
     sim.densities.copy_(state["densities"])
     sim.charge_density.copy_(state["charge"])

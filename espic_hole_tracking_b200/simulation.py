@@ -199,6 +199,13 @@ class Simulation:
             self.sampler = injection_sampler or DeviceUniformSampler(self.ctx, self.device)
             self.xch = dd.DensityExchange(self.ctx, n_points, world_size, rank, self.device, process_group)
         self.periodic_potential = c.periodic_particles if c.periodic_potential is None else c.periodic_potential
+        # Fused deposit (espic_species.acc): the pushes and injections of a step leave their deposit in two
+        # caller-owned planes of fixed-point accumulators; the next field solve (or, multi-GPU, the publication
+        # of the exchange slot) converts it.  No conversion pass and no epilogue launch on the step path.
+        # Not with exchange="nccl": torch's all-reduce needs the float rows.
+        self.fused_deposit = self.exchange_mode in ("none", "p2p")
+        self.acc = torch.zeros((2, (n_points + 63) & ~63), dtype=torch.int64, device=self.device)
+        self._acc_pending = [False, False]
         self.k = 0
         self.t = 0.0
         self.sort_intervals = {"ions": 0, "electrons": 0}   # set by initialize() (_plan_sorting)
@@ -355,6 +362,8 @@ class Simulation:
             a.debye_length, a.object_potential, a.object_transparency = c.debye_length, -3., 1.
             a.periodic_particles = int(c.periodic_particles)
             a.periodic_potential = int(self.periodic_potential)
+            if self.fused_deposit:
+                a.ions.acc, a.electrons.acc = self.acc[0].data_ptr(), self.acc[1].data_ptr()
             a.ion_tags, a.electron_tags = self.ions.tags.data_ptr(), self.electrons.tags.data_ptr()
             a.v_th_ions, a.v_th_electrons = self.v_th_i / math.sqrt(c.sigma), self.v_th_e
             self._filter_scratch = torch.empty_like(self.fine_mesh)
@@ -390,6 +399,7 @@ class Simulation:
                 a.reduced_electron_density = self.electron_density.data_ptr()
             else:
                 a.exchange_parity = -1
+            a.ion_acc_pending, a.electron_acc_pending = int(self._acc_pending[0]), int(self._acc_pending[1])
             a.a_b = a_b
             a.fix_ions = int(periodic or k <= c.time_steps_immobile_ions)
             a.fix_electrons = 1
@@ -397,15 +407,18 @@ class Simulation:
             a.electrons.dt = 0. if k < c.time_steps_immobile_electrons else self.dt
             track = c.track_hole and k > c.initial_transient_steps and k < self.hole_relative_positions.shape[0]
             a.hole_position_out = self.hole_relative_positions[k:k + 1].data_ptr() if track else None   # :896-897
-            device_inject = (not periodic) and isinstance(self.sampler, DeviceUniformSampler) and ions_mobile
+            device_inject = (not periodic) and isinstance(self.sampler, DeviceUniformSampler)
             if device_inject:   # counts on the host (:965-975, 1005-1009), everything else in the same host call
-                a.n_inject_ions, a.n_inject_electrons = self.injection_counts(k)
+                n_i, n_e = self.injection_counts(k)
+                a.n_inject_ions, a.n_inject_electrons = (n_i if ions_mobile else 0), n_e   # frozen ions: :986
                 a.v_d_ions, a.v_d_electrons = v_inj_ions, v_inj
                 a.step_index, a.inject_dt = k, self.dt
             else:
                 a.n_inject_ions = a.n_inject_electrons = 0
             self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
             self.ctx.check(self.ctx._lib.espic_pic_step(self.ctx.handle, a), "espic_pic_step")
+            if self.fused_deposit:   # the solve consumed what was pending; the pushes left the next deposit in acc
+                self._acc_pending = [True, True]
             done_tracking, done_inject = True, device_inject
         else:
             done_tracking = self._step_operator_by_operator(k, ions_mobile, ramp)
@@ -417,6 +430,11 @@ class Simulation:
         den_i, den_e = self._deposit_rows(k + 1)
         if not ions_mobile:
             den_i.fill_(1.0)   # :934 (every rank sets ones; the next all-reduce sums them, as in the reference)
+            if self._acc_pending[0]:   # the frozen ions' own deposit is discarded, as the reference discards it
+                self.acc[0].zero_()
+                self._acc_pending[0] = False
+        if not periodic and not done_inject and any(self._acc_pending):
+            self.flush_pending(k + 1)  # the operator-level injection below adds to the float rows
         if (not done_tracking and c.track_hole and k > c.initial_transient_steps
                 and k < self.hole_relative_positions.shape[0]):                                   # :896-897
             ops.hole_position_tracking(self.potential, self.dz, c.debye_length * 4., self.grid, self.fine_mesh,
@@ -436,18 +454,44 @@ class Simulation:
                                      v_inj, a_b, k, s.tags, s.particles, s.empty_slots,
                                      s.current_empty_slot, s.largest_index, den_e, ctx=self.ctx)
         if self.xch is not None:
-            self.xch.publish(k + 1, k + 1)
+            self._publish(k + 1)
         self.t += self.dt
         self.k += 1
         for n, every in self.sort_intervals.items():
             if every and self.k % every == 0:
                 self.sort_particles((n,), key_shift=self.sort_key_shift, lookahead_steps=0.5 * every)
 
+    def flush_pending(self, k: int | None = None) -> None:
+        """Converts a pending fused deposit into the float density rows step k (default: the next step to
+        run) reads (espic_convert_density: the conversion the field solve would have made, bit for bit)."""
+        rows = self._deposit_rows(self.k if k is None else k)
+        for sp in (0, 1):
+            if self._acc_pending[sp]:
+                self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+                self.ctx.check(self.ctx._lib.espic_convert_density(self.ctx.handle, self.acc[sp].data_ptr(),
+                                                                   rows[sp].data_ptr(), self.n_points,
+                                                                   self.background_density), "espic_convert_density")
+                self._acc_pending[sp] = False
+
+    def _publish(self, k: int) -> None:
+        """Multi-GPU: makes this rank's densities for step k visible to its peers (slot k&1); a pending
+        fused deposit is converted into the slot by the same launch."""
+        if any(self._acc_pending):
+            P = lambda sp: self.acc[sp].data_ptr() if self._acc_pending[sp] else None
+            self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            self.ctx.check(self.ctx._lib.espic_exchange_publish_fused(self.ctx.handle, k & 1, int(k), P(0), P(1),
+                                                                      self.background_density),
+                           "espic_exchange_publish_fused")
+            self._acc_pending = [False, False]
+        else:
+            self.xch.publish(k, k)
+
     def _step_operator_by_operator(self, k: int, ions_mobile: bool, ramp: int) -> bool:
         """The same step through the individual operators, in the reference's order (used when the
         ion potential carries a background ramp, the moving-box controller is on or the per-step
         histograms are wanted).  Returns whether the hole position of this step has been tracked."""
         c = self.cfg
+        self.flush_pending(k)   # the operators read and write the float density rows
         periodic = c.periodic_particles
         fix_ions = periodic or k <= c.time_steps_immobile_ions
         if self.xch is not None:
@@ -563,10 +607,14 @@ class Simulation:
         c = self.cfg
         ions_counted = self.k == 0 or (self.k - 1) <= c.time_steps_immobile_ions   # else the row is all ones (:934)
         rel = {}
-        for name, den in (("ions", den_i), ("electrons", den_e)):
+        for sp, (name, den) in enumerate((("ions", den_i), ("electrons", den_e))):
             if name == "ions" and not ions_counted:
                 continue
-            total = float(den.double().sum().item()) * self.background_density
+            if self._acc_pending[sp]:   # fused deposit still in its integer accumulators: the check is EXACT
+                total = int(self.acc[sp].sum().item()) / float(1 << 24)
+                out.setdefault("charge_conservation_exact", {})[name] = (int(self.acc[sp].sum().item()) == live[name] << 24)
+            else:
+                total = float(den.double().sum().item()) * self.background_density
             rel[name] = abs(total - live[name]) / max(live[name], 1)
         out["live"] = live
         out["charge_conservation_rel_err"] = rel

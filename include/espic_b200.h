@@ -48,6 +48,8 @@ enum {
     ESPIC_ST_BAD_INJECT_INDEX = 8, /* ref infMagSim_cython.py:272-273 */
     ESPIC_ST_BAD_OBJECT_MASK = 16, /* ref infMagSim_c.c:468,482,485 */
     ESPIC_ST_SAMPLER_STALL = 32,   /* ref infMagSim_c.c:589-607 (1000 rejections) */
+    ESPIC_ST_FILTER_GRID = 128,    /* hole-tracking filter: the grid is too far from uniform for the block
+                                    * expansion (see csrc/diag.cu); the response may be off by > 1e-8 */
     ESPIC_ST_EXCHANGE_TIMEOUT = 64 /* FATAL: a peer never published its densities within the exchange
                                     * timeout (multi-GPU exchange).  The potential of that step is NaN. */
 };
@@ -170,12 +172,17 @@ typedef struct {
     int *empty_slots;            /* int[largest_allowed_slot + 1] */
     int *current_empty_slot;     /* device int */
     int *largest_index;          /* device int */
-    float *density;              /* float[n_points], overwritten by the push */
+    float *density;              /* float[n_points], overwritten by the push (acc == NULL) */
     const float *potential;      /* potential felt by this species, or NULL */
     int particle_storage_length;
     int largest_allowed_slot;
     float charge_to_mass;
     float dt;
+    unsigned long long *acc;     /* NULL, or u64[n_points] fixed-point deposit accumulators owned by the caller
+                                  * (zero before the first step): the pushes and injections of the step ADD their
+                                  * deposit here (weights scaled by 2^24) and leave `density` alone; the next
+                                  * step's field solve converts it (one float rounding per node, the same the
+                                  * un-fused path makes) -- no conversion pass, no epilogue launch on the step path */
 } espic_species;
 
 typedef struct {
@@ -203,6 +210,9 @@ typedef struct {
     int exchange_step;
     float *reduced_ion_density;  /* only read when exchange_parity >= 0 */
     float *reduced_electron_density;
+    int ion_acc_pending;         /* single rank, species.acc != NULL: 1 = this step's density of that species is still */
+    int electron_acc_pending;    /* in its accumulators (the previous step left it there): the solve converts it into
+                                  * species.density and clears them; 0 = species.density already holds it */
     /* wall injection after the pushes (ref infMagSim_script.py:986-1019) with the device sampler:
      * counts come from the host (expected flux + stochastic rounding, ref :965-975, 1005-1009) */
     int n_inject_ions;
@@ -243,6 +253,15 @@ int espic_exchange_slot(espic_ctx *ctx, int parity, float **slot_out);
 /* Marks slot `parity` of this rank as holding the densities that enter step `step` (0-based;
  * call after the pushes and injections that produced them).  Stream-ordered. */
 int espic_exchange_publish(espic_ctx *ctx, int parity, int step);
+/* The same for the fused deposit (espic_species.acc): the given accumulator planes (either may be NULL) are
+ * converted into this rank's slot rows -- ion row / electron row -- and cleared, then the slot is published. */
+int espic_exchange_publish_fused(espic_ctx *ctx, int parity, int step, unsigned long long *ion_acc,
+                                 unsigned long long *electron_acc, float background_density);
+/* density[j] = (float)(acc[j] * 2^-24 / background_density), acc cleared: what the field solve does with a
+ * pending fused deposit; for drivers that need the float density between steps (checkpoints, a change of
+ * step mode). */
+int espic_convert_density(espic_ctx *ctx, unsigned long long *acc, float *density, int n_points,
+                          float background_density);
 /* espic_field_solve over the rank-ordered sum of all ranks' slots of `parity` for `step`.
  * ion_density / electron_density (local, n_points each) receive the reduced, end-fixed densities. */
 int espic_field_solve_exchange(espic_ctx *ctx, int parity, int step, const float *grid,
@@ -341,6 +360,11 @@ void electric_field_filter_c(int n_points, float *grid, float *data_array, float
 void histogram2d_uniform_grid_c(float *X, float *Y, float x_min, float step_x, float y_min,
                                 float step_y, int n_bins_x, int n_bins_y, int n_data,
                                 int *hist); /* ref :543-544 */
+/* The host-array movers page-lock the caller's particle arrays on first use (copies at full PCIe
+ * speed, upload / push / download pipelined in chunks) and keep them registered, because the
+ * reference driver passes the same arrays at every step.  Call this before freeing or reallocating
+ * those arrays. */
+void espic_host_release(void);
 /* New symbol (the reference's injection body is Cython, infMagSim_cython.py:230-285):
  * host-pointer form of espic_inject_particles. */
 void inject_particles_c(int n_inject, float *grid, int n_points, float dt,

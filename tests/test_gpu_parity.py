@@ -613,11 +613,16 @@ def test_hole_tracking_argmax_at_baseline_grids(ops, cpu, n_points, kind):
         assert abs(exact[i_gpu] - exact[i_ref]) <= noise_ref, (exact[i_gpu], exact[i_ref], noise_ref)
 
 
-def test_host_pointer_dropins(ops, cpu):
-    """The reference-named symbols with HOST arrays (what a relinked Cython extension calls)."""
+@pytest.mark.parametrize("chunk_slots", [0, 4096])
+def test_host_pointer_dropins(ops, cpu, chunk_slots, monkeypatch):
+    """The reference-named symbols with HOST arrays (what a relinked Cython extension calls).  With
+    ESPIC_HOST_CHUNK=4096 the 20 000-slot store crosses the device in 5 pipelined chunks (upload / push /
+    download on three streams), each with removals: particle state, stack order and top must not change."""
     import ctypes as C
     from espic_hole_tracking_b200._lib import lib
     L = lib()
+    if chunk_slots:
+        monkeypatch.setenv("ESPIC_HOST_CHUNK", str(chunk_slots))
     n_cells = 512
     grid = wl.make_grid(n_cells)
     mask = np.zeros_like(grid)
@@ -636,6 +641,10 @@ def test_host_pointer_dropins(ops, cpu):
     assert_bits_equal(h.particles, c.particles, "particles")
     assert_bits_equal(h.empty_slots[:top.value + 1], c.empty_slots[:top.value + 1], "stack")
     np.testing.assert_allclose(d_h, d_ref, rtol=0, atol=2e-6 * d_ref.max())
+    removed = c.empty_slots[sp.current_empty_slot[0] + 1:top.value + 1]
+    assert len(removed) > 50 and np.all(np.diff(removed) > 0)          # ascending slot order, as the reference pushes
+    if chunk_slots:
+        assert len(np.unique(removed // chunk_slots)) >= 3            # removals in at least three chunks
     charge = (d_ref - d_ref.mean()).astype(np.float32)
     p_ref, p_h = np.zeros_like(grid), np.zeros_like(grid)
     cpu.poisson_solve(grid, mask, charge, 0.125, p_ref)
