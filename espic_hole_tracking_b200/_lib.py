@@ -12,7 +12,8 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libespic_b200.so")
+# ESPIC_LIB_PATH: development knob, an A/B build of the same library (scripts/build_variants.sh)
+LIB_PATH = os.environ.get("ESPIC_LIB_PATH") or os.path.join(HERE, "libespic_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 c_void_p, c_int, c_float, c_double = C.c_void_p, C.c_int, C.c_float, C.c_double
@@ -38,7 +39,7 @@ class StepArgs(C.Structure):
                 ("reduced_electron_density", c_void_p), ("ion_acc_pending", c_int), ("electron_acc_pending", c_int),
                 ("n_inject_ions", c_int), ("n_inject_electrons", c_int),
                 ("v_th_ions", c_float), ("v_d_ions", c_float), ("v_th_electrons", c_float),
-                ("v_d_electrons", c_float), ("inject_dt", c_float), ("step_index", c_int), ("ion_tags", c_void_p),
+                ("v_d_electrons", c_float), ("inject_dt", c_float), ("step_index", c_int), ("inject_by_side", c_int), ("ion_tags", c_void_p),
                 ("electron_tags", c_void_p), ("fine_mesh", c_void_p), ("filter_scratch", c_void_p),
                 ("hole_position_out", c_void_p), ("n_fine", c_int), ("tracking_dz", c_double),
                 ("tracking_width", c_float)]

@@ -452,7 +452,7 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         const espic_species* s = sp[i];
         rc = launch_inject(ctx, n_inj[i], a->grid, a->n_points, a->inject_dt, a->background_density, vel, uni, a->a_b,
                            a->step_index, tags[i], s->particles, s->particle_storage_length, s->empty_slots,
-                           s->current_empty_slot, s->largest_index, s->density, true, acc[i]);
+                           s->current_empty_slot, s->largest_index, s->density, true, acc[i], a->inject_by_side);
         if (rc) return rc;
     }
     return ESPIC_OK;

@@ -280,7 +280,7 @@ int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge,
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
                   int storage, int* empty_slots, int* top, int* largest, float* density, bool classified = false,
-                  unsigned long long* acc_fused = nullptr);
+                  unsigned long long* acc_fused = nullptr, int by_side = 0);
 int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
                              const float* grid, int n_points, float dt, float bg, float a_b);
 int launch_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points, float bg);

@@ -166,6 +166,10 @@ struct InjectArgs {
     int* status;
     int* ws;  // [0] bad count, [1] stack top after a sequential replay, [2] a deposit went past the wall tiles
     unsigned* ticket;  // last-CTA-done counter of the commit kernel
+    // Slot assignment by wall (sorted stores, see k_inject_commit): left_count[c] = particles of chunk c (of
+    // kSampleThreads consecutive particles) that enter at the left wall, written by k_sample_classify
+    int* left_count;
+    int by_side;
     int n_inject, n_points, k;
     float dt, a_b;
     double inv_scale;
@@ -201,18 +205,29 @@ __global__ void k_inject_classify(const InjectArgs a) {
 
 // The device sampler's two draws and the classification above in one launch: fractions and
 // velocities are written out for the commit kernel, the bad-index count goes to ws[0].
-__global__ void __launch_bounds__(128) k_sample_classify(const InjectArgs a, const SamplerConsts k, float* __restrict__ uni_out,
-                                                         float* __restrict__ vel_out, unsigned long long seed,
-                                                         unsigned long long call_uni, unsigned long long call_vel) {
+constexpr int kSampleThreads = 128;
+
+__global__ void __launch_bounds__(kSampleThreads) k_sample_classify(const InjectArgs a, const SamplerConsts k,
+                                                                    float* __restrict__ uni_out, float* __restrict__ vel_out,
+                                                                    unsigned long long seed, unsigned long long call_uni,
+                                                                    unsigned long long call_vel) {
     const Geom g = make_geom(a.grid, a.n_points);
     Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
     int bad = 0;
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x) {
-        const float u = uniform_at(ph, l, call_uni);
-        const float v = draw_velocity(ph, l, call_vel, k, a.status);
-        uni_out[l] = u;
-        vel_out[l] = v;
-        bad += place_injected(g, v, u, a.dt, a.a_b).bad ? 1 : 0;
+    const int n_chunks = (a.n_inject + kSampleThreads - 1) / kSampleThreads;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {  // uniform trip count per CTA
+        const int l = chunk * kSampleThreads + threadIdx.x;
+        int left = 0;
+        if (l < a.n_inject) {
+            const float u = uniform_at(ph, l, call_uni);
+            const float v = draw_velocity(ph, l, call_vel, k, a.status);
+            uni_out[l] = u;
+            vel_out[l] = v;
+            bad += place_injected(g, v, u, a.dt, a.a_b).bad ? 1 : 0;
+            left = !(v < 0.f);  // enters at z_min (ref infMagSim_cython.py:263-268)
+        }
+        left = __syncthreads_count(left);
+        if (threadIdx.x == 0 && a.left_count) a.left_count[chunk] = left;
     }
     bad = __syncthreads_count(bad);
     if (threadIdx.x == 0 && bad) atomicAdd(a.ws, bad);
@@ -280,9 +295,20 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
     }
 }
 
+// Slot assignment.  The reference pops one stack entry per injected particle, in order: particle l takes entry
+// top-l (by_side == 0: bit-identical slots).  On a store kept sorted by position (large grids, csrc/sort.cu)
+// which of the free slots a new particle takes is physically irrelevant but decides whether it lands in a
+// segment of the store whose shared-memory window covers its wall: the mover pushes the slots it frees in
+// ascending slot order, i.e. left-wall leavers below right-wall leavers, so with by_side != 0 the particles that
+// enter at the left wall take the entries of the consumed range [top-n+1, top] from the bottom up and those that
+// enter at the right wall take them from the top down -- the same entries, each used once, deterministically
+// (ranks from a scan, no atomics).  Half of all injected electrons would otherwise sit 65536 cells away from
+// their segment until the next sort and be served from global memory.
 __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
     __shared__ unsigned s_wall[2 * kWallNodes];
     __shared__ int s_last;
+    __shared__ int s_scan[8];
+    __shared__ int s_base_left;
     const Geom g = make_geom(a.grid, a.n_points);
     const int top0 = *a.top;
     const int n_bad = a.ws[0];
@@ -291,14 +317,58 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
         __syncthreads();
         int my_max = -1;
         bool interior = false;
-        for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < a.n_inject; l += gridDim.x * blockDim.x) {
-            const int sp = top0 - l;
+        // contiguous runs of 256-particle rounds per CTA, so that the left-wall rank of a round is the rank
+        // of the previous one plus its count
+        const int n_rounds = (a.n_inject + 255) / 256;
+        const int per_cta = (n_rounds + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int r0 = min((int)blockIdx.x * per_cta, n_rounds), r1 = min(r0 + per_cta, n_rounds);
+        int base_left = 0;
+        if (a.by_side && r0 < r1) {  // particles entering at the left wall in front of this CTA's first round
+            int part = 0;
+            for (int c = threadIdx.x; c < 2 * r0; c += blockDim.x) part += a.left_count[c];  // two sampler chunks per round
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if ((threadIdx.x & 31) == 0) s_scan[threadIdx.x >> 5] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int t = 0;
+                for (int w = 0; w < 8; ++w) t += s_scan[w];
+                s_base_left = t;
+            }
+            __syncthreads();
+            base_left = s_base_left;
+            __syncthreads();
+        }
+        for (int r = r0; r < r1; ++r) {
+            const int l = r * 256 + (int)threadIdx.x;
+            const bool have = l < a.n_inject;
+            const float vel = have ? a.vel[l] : 0.f;
+            int sp = top0 - l;  // the reference's pop order
+            if (a.by_side) {
+                const bool left = have && !(vel < 0.f);
+                const unsigned lanes = __ballot_sync(0xffffffffu, left);
+                const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+                if (lane == 0) s_scan[w] = __popc(lanes);
+                __syncthreads();
+                int before = 0, round_left = 0;
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) {
+                    before += ww < w ? s_scan[ww] : 0;
+                    round_left += s_scan[ww];
+                }
+                const int rank_left = base_left + before + __popc(lanes & ((1u << lane) - 1u));
+                const int rank_right = l - rank_left;  // particles in front of l that enter at the right wall
+                sp = left ? top0 - a.n_inject + 1 + rank_left : top0 - rank_right;
+                base_left += round_left;
+                __syncthreads();
+            }
+            if (!have) continue;
             if (sp < 0) {  // ref :255-256 "no empty slots" (the reference then reads empty_slots[-1])
                 atomicOr(a.status, ESPIC_ST_STACK_EMPTY);
                 continue;
             }
             const int slot = a.empty_slots[sp];
-            const Injected p = place_injected(g, a.vel[l], a.uni[l], a.dt, a.a_b);
+            const Injected p = place_injected(g, vel, a.uni[l], a.dt, a.a_b);
             a.hist[slot] = a.k;
             a.pv[slot] = p.v;
             a.px[slot] = p.x;
@@ -364,7 +434,8 @@ static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const f
     if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
     int rc = ensure_acc(ctx, n_points);
     if (rc) return rc;
-    rc = ensure(ctx, ctx->inject_ws, 64, "inject workspace");
+    // [16 ints of counters][one int per sampler chunk: particles entering at the left wall]
+    rc = ensure(ctx, ctx->inject_ws, 64 + ((size_t)n_inject / kSampleThreads + 2) * sizeof(int), "inject workspace");
     if (rc) return rc;
     a.grid = grid;
     a.acc = ctx->acc;
@@ -382,7 +453,7 @@ static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const f
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
                   int storage, int* empty_slots, int* top, int* largest, float* density, bool classified,
-                  unsigned long long* acc_fused) {
+                  unsigned long long* acc_fused, int by_side) {
     if (n_inject <= 0) return 0;
     InjectArgs a{};
     int rc = fill_inject_args(ctx, a, n_inject, grid, n_points, dt, bg, a_b);
@@ -401,6 +472,9 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
     a.largest = largest;
     a.density = density;
     a.k = k;
+    // assignment by wall needs the per-chunk counts the device sampler leaves behind (rng_sample_for_injection)
+    a.by_side = (by_side && classified) ? 1 : 0;
+    a.left_count = (int*)ctx->inject_ws.ptr + 16;
     int grid_dim = (n_inject + 255) / 256;
     if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
     if (!classified) {
@@ -425,9 +499,10 @@ int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d
     if (rc) return rc;
     const unsigned long long key = rng_key(ctx);
     const unsigned long long call_uni = ctx->rng_consumed++, call_vel = ctx->rng_consumed++;
-    int grid_dim = (n_inject + 127) / 128;
+    a.left_count = (int*)ctx->inject_ws.ptr + 16;
+    int grid_dim = (n_inject + kSampleThreads - 1) / kSampleThreads;
     if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
-    k_sample_classify<<<grid_dim, 128, 0, ctx->stream>>>(a, sampler_consts(v_th, v_d), uni, vel, key, call_uni, call_vel);
+    k_sample_classify<<<grid_dim, kSampleThreads, 0, ctx->stream>>>(a, sampler_consts(v_th, v_d), uni, vel, key, call_uni, call_vel);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_sample_classify launch");
 }

@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
                 const float4* src = ring + stage * 128 + lane;
                 Quad p0, p1;
                 unpack_quad(src[0], src[32], p0);
+#if !ESPIC_VAR_UNPACK
+                unpack_quad(src[64], src[96], p1);
+#endif
                 if (u + du < ue) issue(u + du, stage ^ 1);  // uniform; fills the OTHER stage
                 if (lane < 16 && u + a.prefetch_units * du < split.n_units) {
                     const float* row = (lane & 8) ? a.pv : a.px;
@@ -179,7 +182,9 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
                 // the second quad is read from the ring only now: its stage is not overwritten before the next
                 // iteration, and nothing of it has to survive the first quad in registers (or in local memory:
                 // both quads held at once spilled 16 words per iteration at 64 registers per thread)
+#if ESPIC_VAR_UNPACK
                 unpack_quad(src[64], src[96], p1);
+#endif
                 const unsigned r1 = quad_fast<PERIODIC, SMEM>(a, g, p1, q1, n_slots, dv, s_lo, s_hi);
                 if (!PERIODIC || __any_sync(0xffffffffu, (r0 | r1) != 0u)) {
                     if (STRIDED) {  // every unit is its own range: staged behind the unit, counted per unit
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
             if (lo | hi) atomicAdd(a.acc + jj, ((unsigned long long)hi << 32) | lo);
         }
     }
-    if (STRIDED && a.epilogue) {  // uniform
+    if (ESPIC_VAR_EPILOGUE && STRIDED && a.epilogue) {  // uniform
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
@@ -597,7 +602,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.strided = (a.staged && strided_env) ? 1 : 0;
     if (a.strided) a.counts = counts_strided;
     // windowed / global-table launches never take the round-robin kernel
-    a.epilogue = (acc_fused && a.strided && periodic && use_smem) ? 1 : 0;
+    a.epilogue = (ESPIC_VAR_EPILOGUE && acc_fused && a.strided && periodic && use_smem) ? 1 : 0;
     const size_t smem = use_smem ? tile + (a.staged ? ring : 0) : 0;
     // L2 prefetch distance, measured on B200 (1e8 particles, 4096 cells): one unit ahead of the next
     // fetch is best in both modes -- 0.373 ms without it, 0.305 ms with it (staged)

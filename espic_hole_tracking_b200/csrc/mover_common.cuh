@@ -6,6 +6,17 @@
 
 #include "espic_internal.cuh"
 
+// development switches for A/B builds (scripts/build_variants.sh); the defaults are the shipped code
+#ifndef ESPIC_VAR_CARRY
+#define ESPIC_VAR_CARRY 1     // 1: one running maximum over the eight returned words; 0: one compare per word
+#endif
+#ifndef ESPIC_VAR_UNPACK
+#define ESPIC_VAR_UNPACK 1    // 1: the second quad is read from the ring after the first has been pushed
+#endif
+#ifndef ESPIC_VAR_EPILOGUE
+#define ESPIC_VAR_EPILOGUE 1  // 1: last-CTA removal epilogue compiled into the round-robin periodic kernel
+#endif
+
 namespace espic {
 
 constexpr int kMoveThreads = 1024;  // one 32-warp CTA per SM (64 registers per thread): one tile to zero and flush per SM
@@ -152,6 +163,7 @@ template <bool SMEM>
 __device__ __forceinline__ void deposit_quad_all(const Geom& g, const float* x, const int* cell, unsigned* s_lo,
                                                  unsigned* s_hi, unsigned long long* acc) {
     if (SMEM) {
+#if ESPIC_VAR_CARRY
         unsigned w[8], old[8], top = 0u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -167,6 +179,25 @@ __device__ __forceinline__ void deposit_quad_all(const Geom& g, const float* x, 
                 if (old[2 * c + 1] > ~w[2 * c + 1]) atomicAdd(s_hi + cell[c] + 1, 1u);
             }
         }
+#else
+        unsigned carries = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned w0, w1;
+            node_weights_fixed(g, x[c], cell[c], w0, w1);
+            const unsigned old0 = atomicAdd(s_lo + cell[c], w0);
+            const unsigned old1 = atomicAdd(s_lo + cell[c] + 1, w1);
+            if (old0 > ~w0) carries |= 1u << (2 * c);
+            if (old1 > ~w1) carries |= 2u << (2 * c);
+        }
+        if (__any_sync(0xffffffffu, carries != 0u)) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (carries & (1u << (2 * c))) atomicAdd(s_hi + cell[c], 1u);
+                if (carries & (2u << (2 * c))) atomicAdd(s_hi + cell[c] + 1, 1u);
+            }
+        }
+#endif
     } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {

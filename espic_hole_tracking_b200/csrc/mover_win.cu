@@ -30,6 +30,13 @@
 
 #include "mover_common.cuh"
 
+#ifndef ESPIC_VAR_WINCARRY
+#define ESPIC_VAR_WINCARRY 1   // development switch: 1 = running-maximum carry test, 0 = one compare per word
+#endif
+#ifndef ESPIC_VAR_WINWRAP
+#define ESPIC_VAR_WINWRAP 1    // development switch: 1 = no-wrap windows take the one-subtraction mapping
+#endif
+
 namespace espic {
 
 constexpr int kWinCells = 27648;
@@ -40,10 +47,17 @@ constexpr int kWinThreads = 1024;
 // cell -> index into the window tables.  Cells at or above w_lo map to cell - w_lo; cells that
 // wrapped (below w_lo) map one further so that node n_cells (right end) and node 0 (left end)
 // stay distinct.  `inside` says whether the cell belongs to the window at all.
+// WRAP = false: the window ends before the seam (w_lo + kWinCells <= n_cells, true for every segment
+// but the ones next to a wall or straddling the periodic seam) and the mapping is one subtraction.
+template <bool WRAP>
 struct WinMap {
     int w_lo, n_cells;
     __device__ __forceinline__ int operator()(int cell, bool& inside) const {
         const int t = cell - w_lo;
+        if (!WRAP) {
+            inside = (unsigned)t < (unsigned)kWinCells;
+            return t;
+        }
         const int m = t >> 31;
         const int rel = t + (n_cells & m);
         inside = (unsigned)rel < (unsigned)kWinCells;
@@ -56,10 +70,11 @@ struct WinMap {
     }
 };
 
+template <bool WRAP>
 struct KickWindow {
     const float* s_dv;
     const float* dv_global;
-    WinMap map;
+    WinMap<WRAP> map;
     __device__ __forceinline__ float operator()(int c) const {
         bool inside;
         const int j = map(c, inside);
@@ -68,10 +83,47 @@ struct KickWindow {
     }
 };
 
-// Deposit of the slots of a quad named by `dep`: window cells through the shared-memory planes,
-// the others straight into the global accumulators.
+// Deposit of the slots of a quad named by `dep`: window cells through the shared-memory plane, the others
+// straight into the global accumulators.  A word of the plane can only wrap when its old value lies within
+// 2^24 of 2^32, so one running maximum over the returned values decides whether any carry has to be looked
+// for at all (see deposit_quad_all).
+template <bool WRAP>
 __device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, const int* cell, unsigned dep,
-                                                 const WinMap& map, unsigned* s_lo, unsigned long long* acc) {
+                                                 const WinMap<WRAP>& map, unsigned* s_lo, unsigned long long* acc) {
+#if ESPIC_VAR_WINCARRY
+    unsigned old[8], top = 0u, outside = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned w0, w1;
+        node_weights_fixed(g, x[c], cell[c], w0, w1);
+        bool inside;
+        const int j = map(cell[c], inside);
+        const bool on = (dep >> c) & 1u;
+        old[2 * c] = old[2 * c + 1] = 0u;
+        if (on && inside) {
+            old[2 * c] = atomicAdd(s_lo + j, w0);
+            old[2 * c + 1] = atomicAdd(s_lo + j + 1, w1);
+        }
+        top = max(top, max(old[2 * c], old[2 * c + 1]));
+        if (on && !inside) outside |= 1u << c;
+    }
+    if (__any_sync(0xffffffffu, (top >= 0xFF000000u) | (outside != 0u))) {  // rare: weights and indices are made again
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned w0, w1;
+            node_weights_fixed(g, x[c], cell[c], w0, w1);
+            bool inside;
+            const int j = map(cell[c], inside);
+            // the word wrapped: its 2^32 goes straight to the global accumulator of that node
+            if (old[2 * c] > ~w0) atomicAdd(acc + map.node_of(j), 1ull << 32);
+            if (old[2 * c + 1] > ~w1) atomicAdd(acc + map.node_of(j + 1), 1ull << 32);
+            if (outside & (1u << c)) {
+                atomicAdd(acc + cell[c], (unsigned long long)w0);
+                atomicAdd(acc + cell[c] + 1, (unsigned long long)w1);
+            }
+        }
+    }
+#else
     unsigned carries = 0, outside = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -91,26 +143,24 @@ __device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, 
     if (__any_sync(0xffffffffu, (carries | outside) != 0u)) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            if (carries & (3u << (2 * c))) {
-                bool inside;
-                const int j = map(cell[c], inside);
-                // the word wrapped: its 2^32 goes straight to the global accumulator of that node
-                if (carries & (1u << (2 * c))) atomicAdd(acc + map.node_of(j), 1ull << 32);
-                if (carries & (2u << (2 * c))) atomicAdd(acc + map.node_of(j + 1), 1ull << 32);
-            }
+            unsigned w0, w1;
+            node_weights_fixed(g, x[c], cell[c], w0, w1);
+            bool inside;
+            const int j = map(cell[c], inside);
+            if (carries & (1u << (2 * c))) atomicAdd(acc + map.node_of(j), 1ull << 32);
+            if (carries & (2u << (2 * c))) atomicAdd(acc + map.node_of(j + 1), 1ull << 32);
             if (outside & (1u << c)) {
-                unsigned w0, w1;
-                node_weights_fixed(g, x[c], cell[c], w0, w1);
                 atomicAdd(acc + cell[c], (unsigned long long)w0);
                 atomicAdd(acc + cell[c] + 1, (unsigned long long)w1);
             }
         }
     }
+#endif
 }
 
-template <bool PERIODIC>
+template <bool PERIODIC, bool WRAP>
 __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
-                                                  const KickWindow& kick, unsigned* s_lo) {
+                                                  const KickWindow<WRAP>& kick, unsigned* s_lo) {
     int cell[4];
     bool rare = false;
     if (PERIODIC) {
@@ -119,7 +169,7 @@ __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom&
         if (__any_sync(0xffffffffu, rare))
             return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
         store_quad(a, q, p);
-        deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
+        deposit_quad_win<WRAP>(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
         return 0u;
     } else {
         unsigned dep = 0, rem = 0;
@@ -134,10 +184,68 @@ __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom&
             return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
         store_quad(a, q, p);
         if (__all_sync(0xffffffffu, dep == 0xFu))  // uniform: the whole warp deposits (no per-slot predicates)
-            deposit_quad_win(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
+            deposit_quad_win<WRAP>(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
         else
-            deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, a.acc);
+            deposit_quad_win<WRAP>(g, p.x, cell, dep, kick.map, s_lo, a.acc);
         return rem;
+    }
+}
+
+// One warp's range of units of a segment through the window tables.
+template <bool PERIODIC, bool WRAP>
+__device__ __forceinline__ void win_range(const MoveArgs& a, const Geom& g, const Split& split, int range, int n_ranges,
+                                          int n_slots, int n_quads, int lane, bool fast, bool has_obj,
+                                          const float* s_dv, unsigned* s_lo, int w_lo, int n_cells) {
+    const KickWindow<WRAP> kick{s_dv, a.dv_global, WinMap<WRAP>{w_lo, n_cells}};
+    int removed = 0;
+    const int u0 = split.first_unit(range), u1 = u0 + split.unit_count(range);
+    int* stage_ids = a.staging + (size_t)u0 * kUnitSlots;
+    if (fast) {
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+            const int q0 = u * kUnitQuads + lane, q1 = q0 + 32;
+            if (lane < 16 && u + a.prefetch_units < u1) {
+                const float* row = (lane & 8) ? a.pv : a.px;
+                const float* line = row + (size_t)(u + a.prefetch_units) * kUnitSlots + (lane & 7) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+            }
+            Quad p0, p1;
+            load_quad(a, q0, p0);
+            load_quad(a, q1, p1);
+            const unsigned rem0 = quad_fast_win<PERIODIC, WRAP>(a, g, p0, q0, n_slots, kick, s_lo);
+            const unsigned rem1 = quad_fast_win<PERIODIC, WRAP>(a, g, p1, q1, n_slots, kick, s_lo);
+            if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
+                stage_removed(rem0, q0, lane, stage_ids, removed);
+                stage_removed(rem1, q1, lane, stage_ids, removed);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int q = u0 * kUnitQuads + lane; q < u1 * kUnitQuads; q += 32) {
+            const unsigned r = quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, has_obj, nullptr, nullptr);
+            stage_removed(r, q, lane, stage_ids, removed);
+        }
+    }
+    if (lane == 0) {
+        a.counts[range] = removed;
+        if (removed) atomicAdd(a.total_removed, removed);
+    }
+    if (range == n_ranges - 1) {
+        // the slots behind the last complete unit: generic, bounds-checked, all global
+        int removed_tail = 0;
+        int* stage = a.staging + (size_t)split.n_units * kUnitSlots;
+#pragma unroll 1
+        for (int qb = split.n_units * kUnitQuads; qb < n_quads; qb += 32) {
+            const int q = qb + lane;
+            unsigned r = 0;
+            if (q < n_quads)
+                r = quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, has_obj, nullptr, nullptr);
+            stage_removed(r, q, lane, stage, removed_tail);
+        }
+        if (lane == 0) {
+            a.counts[n_ranges] = removed_tail;
+            if (removed_tail) atomicAdd(a.total_removed, removed_tail);
+        }
     }
 }
 
@@ -203,7 +311,9 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
             s_w_lo = best * bucket_cells;
         }
         __syncthreads();
-        const WinMap map{s_w_lo, n_cells};
+        const int w_lo = s_w_lo;
+        const bool wraps = !ESPIC_VAR_WINWRAP || w_lo + kWinCells > n_cells;  // uniform
+        const WinMap<true> map{w_lo, n_cells};          // the general mapping for table build and flush
 
         // 2. the window's tables
         for (int j = tid; j < kWinNodes; j += blockDim.x) {
@@ -213,61 +323,10 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
         }
         __syncthreads();
 
-        // 3. this warp's range
-        {
-            const KickWindow kick{s_dv, a.dv_global, map};
-            const int range = r0 + warp;
-            int removed = 0;
-            const int u0 = split.first_unit(range), u1 = u0 + split.unit_count(range);
-            int* stage_ids = a.staging + (size_t)u0 * kUnitSlots;
-            if (fast) {
-#pragma unroll 1
-                for (int u = u0; u < u1; ++u) {
-                    const int q0 = u * kUnitQuads + lane, q1 = q0 + 32;
-                    if (lane < 16 && u + a.prefetch_units < u1) {
-                        const float* row = (lane & 8) ? a.pv : a.px;
-                        const float* line = row + (size_t)(u + a.prefetch_units) * kUnitSlots + (lane & 7) * 32;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-                    }
-                    Quad p0, p1;
-                    load_quad(a, q0, p0);
-                    load_quad(a, q1, p1);
-                    const unsigned rem0 = quad_fast_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo);
-                    const unsigned rem1 = quad_fast_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo);
-                    if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
-                        stage_removed(rem0, q0, lane, stage_ids, removed);
-                        stage_removed(rem1, q1, lane, stage_ids, removed);
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (int q = u0 * kUnitQuads + lane; q < u1 * kUnitQuads; q += 32) {
-                    const unsigned r = quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, has_obj, nullptr, nullptr);
-                    stage_removed(r, q, lane, stage_ids, removed);
-                }
-            }
-            if (lane == 0) {
-                a.counts[range] = removed;
-                if (removed) atomicAdd(a.total_removed, removed);
-            }
-            if (range == n_ranges - 1) {
-                // the slots behind the last complete unit: generic, bounds-checked, all global
-                int removed_tail = 0;
-                int* stage = a.staging + (size_t)split.n_units * kUnitSlots;
-#pragma unroll 1
-                for (int qb = split.n_units * kUnitQuads; qb < n_quads; qb += 32) {
-                    const int q = qb + lane;
-                    unsigned r = 0;
-                    if (q < n_quads)
-                        r = quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, has_obj, nullptr, nullptr);
-                    stage_removed(r, q, lane, stage, removed_tail);
-                }
-                if (lane == 0) {
-                    a.counts[n_ranges] = removed_tail;
-                    if (removed_tail) atomicAdd(a.total_removed, removed_tail);
-                }
-            }
-        }
+        // 3. this warp's range (the common no-wrap mapping and the general one are two instantiations;
+        //    which one runs is uniform over the CTA)
+        if (wraps) win_range<PERIODIC, true>(a, g, split, r0 + warp, n_ranges, n_slots, n_quads, lane, fast, has_obj, s_dv, s_lo, w_lo, n_cells);
+        else win_range<PERIODIC, false>(a, g, split, r0 + warp, n_ranges, n_slots, n_quads, lane, fast, has_obj, s_dv, s_lo, w_lo, n_cells);
         __syncthreads();
 
         // 4. flush

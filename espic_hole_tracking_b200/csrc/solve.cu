@@ -760,19 +760,41 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         if (tm.T == 0) {
             a.ion[0] = s_end[0]; a.ion[n - 1] = s_end[1]; a.ele[0] = s_end[2]; a.ele[n - 1] = s_end[3];
         }
+        // Fused deposit still in the accumulators.  One row per thread: the row's owner converts it in place
+        // (coalesced as it is).  Several rows per thread (the transposed layout, j = T*m + i): a conversion
+        // pass of its own with consecutive threads on consecutive nodes, then one more barrier -- walking the
+        // 8-byte accumulators with a stride of m rows made the 65537-point solve twice as slow.
+        bool pending_i = a.acc_i != nullptr, pending_e = a.acc_e != nullptr;
+        if (!ONE_ROW && (pending_i || pending_e)) {
+            for (int j = tm.T; j < n; j += tm.Tn) {
+                const bool interior = j != 0 && j != n - 1;
+                if (pending_i) {
+                    const float x = (float)((double)__ldcg(a.acc_i + j) * a.inv_scale);
+                    a.acc_i[j] = 0ull;
+                    if (interior) a.ion[j] = x;
+                }
+                if (pending_e) {
+                    const float y = (float)((double)__ldcg(a.acc_e + j) * a.inv_scale);
+                    a.acc_e[j] = 0ull;
+                    if (interior) a.ele[j] = y;
+                }
+            }
+            team_sync(tm);
+            pending_i = pending_e = false;
+        }
         // each thread makes the charge of its own rows: nobody else reads them in this kernel
         for (int i = 0; i < m; ++i) {
             const int j = tm.T * m + i;
             if (j >= n) break;
             float x, yv;
-            if (a.acc_i) {  // every CTA has read the raw end nodes before the barrier above: the words can go
+            if (pending_i) {  // every CTA has read the raw end nodes before the barrier above: the words can go
                 x = (float)((double)__ldcg(a.acc_i + j) * a.inv_scale);
                 a.acc_i[j] = 0ull;
                 if (j != 0 && j != n - 1) a.ion[j] = x;
             } else {
                 x = a.ion[j];
             }
-            if (a.acc_e) {
+            if (pending_e) {
                 yv = (float)((double)__ldcg(a.acc_e + j) * a.inv_scale);
                 a.acc_e[j] = 0ull;
                 if (j != 0 && j != n - 1) a.ele[j] = yv;

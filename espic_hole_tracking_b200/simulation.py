@@ -413,6 +413,8 @@ class Simulation:
                 a.n_inject_ions, a.n_inject_electrons = (n_i if ions_mobile else 0), n_e   # frozen ions: :986
                 a.v_d_ions, a.v_d_electrons = v_inj_ions, v_inj
                 a.step_index, a.inject_dt = k, self.dt
+                # sorted stores (large grids): new particles take the freed slots of their own wall
+                a.inject_by_side = int(bool(self.sort_intervals["electrons"] or self.sort_intervals["ions"]))
             else:
                 a.n_inject_ions = a.n_inject_electrons = 0
             self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)

@@ -221,6 +221,12 @@ typedef struct {
     float v_th_electrons, v_d_electrons; /* ref :1016-1019 */
     float inject_dt;                     /* the driver's dt (partial-step placement), independent of a frozen species */
     int step_index;                      /* k: written into the injection tags */
+    int inject_by_side;                  /* 0: particle l takes stack entry top-l, the reference's pop order (ref
+                                          * infMagSim_cython.py:254-257, 282-283).  1 (stores kept sorted by position):
+                                          * the same n entries, but particles entering at the left wall take them
+                                          * from the bottom up and those entering at the right wall from the top down
+                                          * (the mover pushes freed slots in ascending slot order), so a new particle
+                                          * lands among its neighbours in the store.  Physically invisible. */
     int *ion_tags;                       /* int[storage] injection histories; may be NULL when nothing is injected */
     int *electron_tags;
     /* hole tracking after the solve (ref :896-897): position_out == NULL switches it off */

@@ -83,8 +83,11 @@ def test_configs4_hundred_thousand_steps_against_oracle_history():
     # ---- (1) the whole 1e5-step run
     for key in ("max_phi", "hole", "ke_i", "ke_e", "fe"):
         assert np.all(np.isfinite(hist[key])), key
-    assert np.all(np.abs(hist["n_e"] / n - 1) < 0.05), (hist["n_e"].min(), hist["n_e"].max())
-    assert np.all(np.abs(hist["n_i"] / n - 1) < 0.05), (hist["n_i"].min(), hist["n_i"].max())
+    # the violent start expels ~5 % of both species (the oracle's populations dip to 0.948 / 0.951 of n around
+    # step 1800 and recover as the walls refill the box)
+    assert np.all(np.abs(hist["n_e"] / n - 1) < 0.08), (hist["n_e"].min(), hist["n_e"].max())
+    assert np.all(np.abs(hist["n_i"] / n - 1) < 0.08), (hist["n_i"].min(), hist["n_i"].max())
+    assert np.all(np.abs(hist["n_e"][hist["step"] > 20000] / n - 1) < 0.01)
     frozen = hist["step"] > sim.cfg.time_steps_immobile_ions + 100
     assert np.all(hist["n_i"][frozen] == hist["n_i"][frozen][0])          # frozen ions are neither pushed nor injected
     assert np.all(hist["ke_i"][frozen] == hist["ke_i"][frozen][0])
