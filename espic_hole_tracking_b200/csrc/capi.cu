@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "espic_internal.cuh"
 
@@ -404,6 +405,19 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
     unsigned long long* acc[2] = {a->ions.acc, a->electrons.acc};
     if ((acc[0] == nullptr) != (acc[1] == nullptr))
         return fail(ctx, ESPIC_E_ARG, "espic_pic_step: give both species an accumulator plane or neither");
+    // removals pushed directly by the periodic movers (mover_common.cuh, direct_push): counted in the word behind
+    // the last node of the species' plane, put into ascending order by the next solve
+    StackFix fix{};
+    int* pushed[2] = {nullptr, nullptr};
+    if (acc[0]) {
+        for (int i = 0; i < 2; ++i) {
+            pushed[i] = reinterpret_cast<int*>(acc[i] + a->n_points);
+            fix.pushed[i] = pushed[i];
+            fix.empty_slots[i] = sp[i]->empty_slots;
+            fix.top[i] = sp[i]->current_empty_slot;
+            fix.largest_allowed_slot[i] = sp[i]->largest_allowed_slot;
+        }
+    }
     if (a->exchange_parity >= 0) {
         if (!a->reduced_ion_density || !a->reduced_electron_density)
             return fail(ctx, ESPIC_E_ARG, "espic_pic_step: exchange mode needs the reduced density buffers");
@@ -411,13 +425,13 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
                                          a->reduced_ion_density, a->reduced_electron_density, a->charge,
                                          a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length,
                                          a->potential, a->object_potential, a->object_transparency, 0,
-                                         a->periodic_potential, a->n_points);
+                                         a->periodic_potential, a->n_points, acc[0] ? &fix : nullptr);
     } else {
         rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
                                 a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
                                 a->object_potential, a->object_transparency, 0, a->periodic_potential, a->n_points,
                                 a->ion_acc_pending ? acc[0] : nullptr, a->electron_acc_pending ? acc[1] : nullptr,
-                                a->background_density);
+                                a->background_density, acc[0] ? &fix : nullptr);
     }
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
@@ -425,7 +439,7 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,
                          s->charge_to_mass, a->background_density, -1, s->largest_index, s->particles, s->density,
                          s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic_particles, s->largest_allowed_slot,
-                         a->n_points, s->particle_storage_length, 0, 0, 1, acc[i]);
+                         a->n_points, s->particle_storage_length, 0, 0, 1, acc[i], pushed[i]);
         if (rc) return rc;
     }
     if (a->hole_position_out) {
@@ -674,7 +688,27 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
         const long long v = atoll(e);
         if (v >= 1024) chunk = (size_t)v & ~(size_t)1023;
     }
-    const size_t n_chunks = used ? (used + chunk - 1) / chunk : 1;
+    // Chunk schedule: full chunks in the middle, halving chunks towards both ends -- the first upload and the last
+    // download cannot overlap with anything, so they are kept short (1/8 of a chunk).
+    std::vector<size_t> bounds;  // chunk c covers slots [bounds[c], bounds[c+1])
+    bounds.push_back(0);
+    if (used > chunk) {
+        const size_t ramp[3] = {(chunk / 8) & ~(size_t)1023, (chunk / 4) & ~(size_t)1023, (chunk / 2) & ~(size_t)1023};
+        const size_t ramp_total = ramp[0] + ramp[1] + ramp[2];
+        size_t pos = 0;
+        if (used > 2 * ramp_total + chunk && ramp[0] >= 1024) {
+            for (int i = 0; i < 3; ++i) bounds.push_back(pos += ramp[i]);
+            while (used - pos > ramp_total + chunk) bounds.push_back(pos += chunk);
+            const size_t mid = (used - pos - ramp_total) & ~(size_t)1023;   // what is left in front of the down-ramp
+            if (mid) bounds.push_back(pos += mid);
+            bounds.push_back(pos += ramp[2]);
+            bounds.push_back(pos += ramp[1]);
+        } else {
+            while (used - pos > chunk) bounds.push_back(pos += chunk);
+        }
+    }
+    bounds.push_back(used);
+    const size_t n_chunks = bounds.size() - 1;
     const bool pipelined = n_chunks > 1;
     cudaStream_t s_up = ctx->stream, s_run = ctx->stream, s_down = ctx->stream;
     if (pipelined) {
@@ -712,8 +746,8 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
     cudaStream_t saved = ctx->stream;
     ctx->stream = s_run;
     for (size_t c = 0; c < n_chunks; ++c) {
-        const size_t off = c * chunk;
-        const size_t len = used ? (used - off < chunk ? used - off : chunk) : 0;
+        const size_t off = bounds[c];
+        const size_t len = bounds[c + 1] - bounds[c];
         if (len) {
             COPY(d_part + off, particles + off, len, float, cudaMemcpyHostToDevice, s_up);
             COPY(d_part + S + off, particles + S + off, len, float, cudaMemcpyHostToDevice, s_up);

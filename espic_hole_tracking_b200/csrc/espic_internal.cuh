@@ -246,12 +246,22 @@ struct DeviceGuard {
         if (_rc) return _rc;                                       \
     } while (0)
 
+// Stacks whose newest entries were pushed by direct_push movers (mover_common.cuh) in arrival order: the field
+// solve sorts the last *pushed entries of each into ascending slot order and clears the counter.
+struct StackFix {
+    int* pushed[2];       // device counters: the word behind the last node of each species' accumulator plane
+    int* empty_slots[2];
+    const int* top[2];
+    int largest_allowed_slot[2];
+};
+
 // launchers implemented in the other translation units
 int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const float* phi, float dt,
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage, int minimal = 0,
-                int slot_offset = 0, int finish_density = 1, unsigned long long* acc_fused = nullptr);
+                int slot_offset = 0, int finish_density = 1, unsigned long long* acc_fused = nullptr,
+                int* pushed = nullptr);
 int launch_tridiagonal(espic_ctx* ctx, double* a, double* b, double* c, double* d, double* x, int n);
 int move_window_cells(espic_ctx* ctx, int n_points);  // 0: whole-grid tables fit in shared memory
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);
@@ -266,7 +276,7 @@ int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, flo
                        float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
                        float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
                        int n_points, unsigned long long* acc_i = nullptr, unsigned long long* acc_e = nullptr,
-                       float bg = 1.f);
+                       float bg = 1.f, const StackFix* fix = nullptr);
 int exchange_create(espic_ctx* ctx, int n_points, int world, int rank, void* handle_out);
 int exchange_open(espic_ctx* ctx, const void* handles);
 int exchange_publish(espic_ctx* ctx, int parity, int step, unsigned long long* acc_i = nullptr,
@@ -274,7 +284,7 @@ int exchange_publish(espic_ctx* ctx, int parity, int step, unsigned long long* a
 int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* mask,
                                 float* ion, float* ele, float* charge_out, int periodic_particles, int fix_i,
                                 int fix_e, float debye, float* potential, float obj_pot, float transparency,
-                                int boltzmann, int periodic_potential, int n_points);
+                                int boltzmann, int periodic_potential, int n_points, const StackFix* fix = nullptr);
 int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge, int n, int periodic,
                           int fix_i, int fix_e);
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,

@@ -515,7 +515,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage, int minimal, int slot_offset,
-                int finish_density, unsigned long long* acc_fused) {
+                int finish_density, unsigned long long* acc_fused, int* pushed) {
     // acc_fused (the step path, espic_pic_step): the deposit is ADDED to these caller-owned fixed-point
     // accumulators and left there -- the next field solve converts it -- and `density` is not touched.
     // slot_offset / finish_density: the call covers slots [slot_offset, slot_offset + largest_index] of the
@@ -603,6 +603,8 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     if (a.strided) a.counts = counts_strided;
     // windowed / global-table launches never take the round-robin kernel
     a.epilogue = (ESPIC_VAR_EPILOGUE && acc_fused && a.strided && periodic && use_smem) ? 1 : 0;
+    a.direct_push = (!a.epilogue && acc_fused && pushed && a.strided && periodic && use_smem) ? 1 : 0;
+    a.pushed = pushed;
     const size_t smem = use_smem ? tile + (a.staged ? ring : 0) : 0;
     // L2 prefetch distance, measured on B200 (1e8 particles, 4096 cells): one unit ahead of the next
     // fetch is best in both modes -- 0.373 ms without it, 0.305 ms with it (staged)
@@ -634,7 +636,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
         rc = use_smem ? launch_move_variant<false, true>(ctx, a, smem) : launch_move_variant<false, false>(ctx, a, 0);
     }
     if (rc) return rc;
-    if (a.epilogue) return 0;  // the mover's last CTA has done the removal bookkeeping; the deposit stays in acc_fused
+    if (a.epilogue || a.direct_push) return 0;  // removal bookkeeping done inside the mover; the deposit stays in acc_fused
 
     FinishArgs f{};
     f.acc = a.acc;

@@ -8,13 +8,16 @@
 
 // development switches for A/B builds (scripts/build_variants.sh); the defaults are the shipped code
 #ifndef ESPIC_VAR_CARRY
-#define ESPIC_VAR_CARRY 1     // 1: one running maximum over the eight returned words; 0: one compare per word
+#define ESPIC_VAR_CARRY 0     // 1: one running maximum over the eight returned words; 0: one compare per word
+                              // (measured on B200, 1e8 particles: 0.2937 vs 0.2920 ms per launch -- no gain in k_move)
 #endif
 #ifndef ESPIC_VAR_UNPACK
-#define ESPIC_VAR_UNPACK 1    // 1: the second quad is read from the ring after the first has been pushed
+#define ESPIC_VAR_UNPACK 0    // 1: the second quad is read from the ring after the first has been pushed (no spill in
+                              // the loop, but the exposed LDS latency costs more: 0.3058 vs 0.2920 ms per launch)
 #endif
 #ifndef ESPIC_VAR_EPILOGUE
-#define ESPIC_VAR_EPILOGUE 1  // 1: last-CTA removal epilogue compiled into the round-robin periodic kernel
+#define ESPIC_VAR_EPILOGUE 0  // 1: last-CTA removal epilogue compiled into the round-robin periodic kernel (the extra
+                              // code at the end of the kernel perturbs the main loop: 0.3038 vs 0.2920 ms per launch)
 #endif
 
 namespace espic {
@@ -50,9 +53,13 @@ struct MoveArgs {
     int strided;         // experiment: units dealt round-robin to the warps instead of in contiguous ranges
     int* seg_counter;    // windowed kernel: next segment to hand out (reset by k_finish)
     int n_segments;      // windowed kernel: segments of 32 ranges each
-    // fused step path, round-robin periodic variant: the last CTA to finish does the removal bookkeeping
-    // itself when (and only when) a slot was removed -- in a periodic box that needs a particle flung past
-    // 0.99*2*z_max -- so a step needs no k_finish / k_scatter launch
+    // fused step path, periodic variant with per-unit ranges: a removed slot -- in a periodic box that needs a
+    // particle flung past 0.99*2*z_max in one step -- is pushed on the stack right away by the (out-of-line,
+    // practically never executed) generic slot update, so a step needs no k_finish / k_scatter launch.  Slots
+    // removed by one launch reach the stack in arrival order; the next field solve puts that stretch of the
+    // stack into the ascending order the reference's sequential loop produces (solve.cu, StackFix).
+    int direct_push;
+    int* pushed;      // slots pushed this way since the last fix-up
     int epilogue;
     unsigned* ticket;
     int* top;
@@ -255,7 +262,14 @@ __device__ __noinline__ unsigned quad_generic(const MoveArgs& a, int q, int n_sl
         a.px[s] = x;
         a.pv[s] = v;
         if (act == ACT_DEPOSIT) deposit_one<SMEM, true>(g, x, cell, s_lo, s_hi, a.acc);
-        rem |= (act == ACT_REMOVE) ? (1u << c) : 0u;
+        if (act == ACT_REMOVE && a.direct_push) {
+            const int pos = atomicAdd(a.top, 1) + 1;
+            if (pos > a.largest_allowed_slot) atomicOr(a.status, ESPIC_ST_STACK_OVERFLOW);
+            else if (pos >= 0) a.empty_slots[pos] = s + a.slot_offset;
+            atomicAdd(a.pushed, 1);
+        } else {
+            rem |= (act == ACT_REMOVE) ? (1u << c) : 0u;
+        }
     }
     if (bad_any) atomicOr(a.status, ESPIC_ST_BAD_LEFT_INDEX);
     return rem;

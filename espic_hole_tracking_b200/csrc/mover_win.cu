@@ -32,9 +32,12 @@
 
 #ifndef ESPIC_VAR_WINCARRY
 #define ESPIC_VAR_WINCARRY 1   // development switch: 1 = running-maximum carry test, 0 = one compare per word
+                               // (measured: production-like 65536-cell step 1.26 vs 1.31 ms)
 #endif
 #ifndef ESPIC_VAR_WINWRAP
-#define ESPIC_VAR_WINWRAP 1    // development switch: 1 = no-wrap windows take the one-subtraction mapping
+#define ESPIC_VAR_WINWRAP 0    // development switch: 1 = no-wrap windows take the one-subtraction mapping in an instantiation
+                               // of their own (measured: the duplicated loop costs more in instruction fetch than the
+                               // shorter mapping saves -- production-like 65536-cell step 1.43 vs 1.31 ms)
 #endif
 
 namespace espic {

@@ -164,7 +164,33 @@ struct SolveArgs {
     unsigned long long* acc_i;
     unsigned long long* acc_e;
     double inv_scale;                         // 2^-24 / background_density
+    StackFix fix;                             // see espic_internal.cuh; pushed[s] == nullptr: nothing to look at
 };
+
+// Practically never executed: the periodic movers of the previous step removed slots and pushed them in
+// arrival order.  One thread puts the new stretch of each stack into ascending slot order (what the
+// reference's slot-ordered loop produces, ref infMagSim_c.c:214-217) -- an insertion sort: the stretch
+// holds a handful of entries when it exists at all.
+__device__ __noinline__ void fix_stack_order(const StackFix& f) {
+    for (int s = 0; s < 2; ++s) {
+        if (!f.pushed[s]) continue;
+        const int n = *f.pushed[s];
+        if (n == 0) continue;
+        const int hi = min(*f.top[s], f.largest_allowed_slot[s]);
+        const int lo = max(*f.top[s] - n + 1, 0);
+        int* st = f.empty_slots[s];
+        for (int i = lo + 1; i <= hi; ++i) {
+            const int v = st[i];
+            int j = i - 1;
+            while (j >= lo && st[j] > v) {
+                st[j + 1] = st[j];
+                --j;
+            }
+            st[j + 1] = v;
+        }
+        *f.pushed[s] = 0;
+    }
+}
 
 constexpr int kMaxTeam = 8;  // portable cluster size
 
@@ -731,6 +757,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         team_sync(tm);  // the cluster barrier releases / acquires the global writes above
     }
 
+    if (tm.T == 0 && a.fix.pushed[0] && (__ldcg(a.fix.pushed[0]) | __ldcg(a.fix.pushed[1]))) fix_stack_order(a.fix);
+
     // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
     const RowConsts k = row_consts(a);
     const bool cacheable = (a.transparency == 1.f) && !a.boltzmann;
@@ -1057,7 +1085,8 @@ int launch_poisson(espic_ctx* ctx, const float* grid, const float* mask, const f
 int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, float* ion, float* ele,
                        float* charge_out, int periodic_particles, int fix_i, int fix_e, float debye,
                        float* potential, float obj_pot, float transparency, int boltzmann, int periodic_potential,
-                       int n_points, unsigned long long* acc_i, unsigned long long* acc_e, float bg) {
+                       int n_points, unsigned long long* acc_i, unsigned long long* acc_e, float bg,
+                       const StackFix* fix) {
     SolveArgs a{};
     a.grid = grid;
     a.mask = mask;
@@ -1077,6 +1106,7 @@ int launch_field_solve(espic_ctx* ctx, const float* grid, const float* mask, flo
     a.acc_i = acc_i;
     a.acc_e = acc_e;
     a.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
+    if (fix) a.fix = *fix;
     return launch_poisson_impl(ctx, a);
 }
 
@@ -1164,7 +1194,7 @@ int exchange_publish(espic_ctx* ctx, int parity, int step, unsigned long long* a
 int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float* grid, const float* mask,
                                 float* ion, float* ele, float* charge_out, int periodic_particles, int fix_i,
                                 int fix_e, float debye, float* potential, float obj_pot, float transparency,
-                                int boltzmann, int periodic_potential, int n_points) {
+                                int boltzmann, int periodic_potential, int n_points, const StackFix* fix) {
     auto& x = ctx->xch;
     if (!x.opened && x.world > 1) return fail(ctx, ESPIC_E_ARG, "espic_field_solve_exchange: exchange not opened");
     if (!x.local || n_points != x.n_points) return fail(ctx, ESPIC_E_ARG, "espic_field_solve_exchange: n_points mismatch");
@@ -1185,6 +1215,7 @@ int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const floa
     a.n = n_points;
     a.fold_ends = periodic_particles;
     a.world = x.world;
+    if (fix) a.fix = *fix;
     a.expect = (unsigned)step;
     a.timeout_ns = (unsigned long long)(ctx->exchange_timeout_s * 1e9);
     a.n_pad = (int)(x.slot_floats / 2);

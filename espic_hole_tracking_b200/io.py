@@ -139,7 +139,7 @@ def load_checkpoint(sim, path: str) -> None:
         raise ValueError(f"checkpoint of rank {state.get('rank')}/{state.get('world')} loaded on rank "
                          f"{sim.rank}/{sim.world}")
     sim.k, sim.t = state["k"], state["t"]
-    sim.acc.zero_()
+    sim.acc.zero_()   # (flush_pending ran before the checkpoint was written: nothing was pending)
     sim._acc_pending = [False, False]
     sim.potential.copy_(state["potential"])
     sim.densities.copy_(state["densities"])

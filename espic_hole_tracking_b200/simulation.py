@@ -204,7 +204,7 @@ class Simulation:
         # of the exchange slot) converts it.  No conversion pass and no epilogue launch on the step path.
         # Not with exchange="nccl": torch's all-reduce needs the float rows.
         self.fused_deposit = self.exchange_mode in ("none", "p2p")
-        self.acc = torch.zeros((2, (n_points + 63) & ~63), dtype=torch.int64, device=self.device)
+        self.acc = torch.zeros((2, (n_points + 64) & ~63), dtype=torch.int64, device=self.device)   # >= n_points + 1
         self._acc_pending = [False, False]
         self.k = 0
         self.t = 0.0
@@ -433,7 +433,7 @@ class Simulation:
         if not ions_mobile:
             den_i.fill_(1.0)   # :934 (every rank sets ones; the next all-reduce sums them, as in the reference)
             if self._acc_pending[0]:   # the frozen ions' own deposit is discarded, as the reference discards it
-                self.acc[0].zero_()
+                self.acc[0, :self.n_points].zero_()
                 self._acc_pending[0] = False
         if not periodic and not done_inject and any(self._acc_pending):
             self.flush_pending(k + 1)  # the operator-level injection below adds to the float rows
@@ -613,8 +613,9 @@ class Simulation:
             if name == "ions" and not ions_counted:
                 continue
             if self._acc_pending[sp]:   # fused deposit still in its integer accumulators: the check is EXACT
-                total = int(self.acc[sp].sum().item()) / float(1 << 24)
-                out.setdefault("charge_conservation_exact", {})[name] = (int(self.acc[sp].sum().item()) == live[name] << 24)
+                fixed = int(self.acc[sp, :self.n_points].sum().item())
+                total = fixed / float(1 << 24)
+                out.setdefault("charge_conservation_exact", {})[name] = (fixed == live[name] << 24)
             else:
                 total = float(den.double().sum().item()) * self.background_density
             rel[name] = abs(total - live[name]) / max(live[name], 1)

@@ -178,8 +178,9 @@ typedef struct {
     int largest_allowed_slot;
     float charge_to_mass;
     float dt;
-    unsigned long long *acc;     /* NULL, or u64[n_points] fixed-point deposit accumulators owned by the caller
-                                  * (zero before the first step): the pushes and injections of the step ADD their
+    unsigned long long *acc;     /* NULL, or u64[n_points + 1] fixed-point deposit accumulators owned by the caller
+                                  * (zero before the first step; the word behind the last node is bookkeeping of
+                                  * the library): the pushes and injections of the step ADD their
                                   * deposit here (weights scaled by 2^24) and leave `density` alone; the next
                                   * step's field solve converts it (one float rounding per node, the same the
                                   * un-fused path makes) -- no conversion pass, no epilogue launch on the step path */

@@ -6,8 +6,9 @@ import torch
 from espic_hole_tracking_b200.simulation import SimConfig, Simulation
 n = int(float(os.environ.get("PROBE_N", "1e8")))
 steps = int(os.environ.get("PROBE_STEPS", "600"))
+sort_e = os.environ.get("PROBE_SORT_E")
 cfg = SimConfig(n_steps=steps + 200, n_particles=n, n_cells=65536, periodic_particles=False, track_hole=True,
-                extra_storage_factor=1.1)
+                extra_storage_factor=1.1, sort_interval_electrons=int(sort_e) if sort_e else None)
 sim = Simulation(cfg); sim.init_synthetic(); sim.initialize()
 print("sort intervals", sim.sort_intervals, "key_shift", sim.sort_key_shift, flush=True)
 for _ in range(100): sim.step()
