@@ -161,37 +161,124 @@ __device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, 
 #endif
 }
 
+// One quad through the window tables.  The common case -- every live slot of the warp gathers from and
+// deposits into the window -- is straight-line code: four table loads, eight shared-memory atomics, no
+// per-lane branch (ncu on the first version, which mapped and tested every slot on its own: 109
+// instructions per particle, 5 branches and 5.5 convergence barriers among them).  A warp that holds a slot
+// whose gather or deposit cell lies outside the window takes the per-lane path for that part, behind one
+// vote per quad.  Slots that do not take part (dead on entry, removed) use table index 0 with zero weights.
 template <bool PERIODIC, bool WRAP>
 __device__ __forceinline__ unsigned quad_fast_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
                                                   const KickWindow<WRAP>& kick, unsigned* s_lo) {
-    int cell[4];
+    const unsigned last = (unsigned)g.last_cell;
+    const WinMap<WRAP>& map = kick.map;
     bool rare = false;
-    if (PERIODIC) {
+    int c0[4], j0[4];
+    unsigned alive = 0, in0 = 0;
+    float x0[4];
+    // ---- entry: liveness, cell, window index (ref infMagSim_c.c:146-165)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) push_fast_periodic(g, p.x[c], p.v[c], kick, a.dt, cell[c], rare);
-        if (__any_sync(0xffffffffu, rare))
-            return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
-        store_quad(a, q, p);
-        deposit_quad_win<WRAP>(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
-        return 0u;
+    for (int c = 0; c < 4; ++c) {
+        bool ok;
+        if (PERIODIC) {
+            const float a0 = __fsub_rn(p.x[c], g.z_lo);
+            x0[c] = __fadd_rn(a0, g.z_lo);
+            const float b0 = __fsub_rn(x0[c], g.z_lo);
+            rare |= !(a0 >= 0.f);
+            rare |= !(b0 < g.cell_span);
+            c0[c] = (int)min((unsigned)__float2int_rz(quotient_dz<true>(g, b0)), last);
+            ok = true;
+        } else {
+            x0[c] = p.x[c];
+            ok = (x0[c] > g.lo_edge) && (x0[c] < g.hi_edge);
+            const int cr = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x0[c], g.z_lo)));
+            c0[c] = (int)min((unsigned)cr, last);
+            rare |= ok && (c0[c] != cr);
+        }
+        alive |= ok ? (1u << c) : 0u;
+        bool inside;
+        const int j = map(c0[c], inside);
+        j0[c] = (inside && ok) ? j : 0;
+        in0 |= (inside || !ok) ? (1u << c) : 0u;
+    }
+    // ---- gather (ref :166-168): one table load per slot
+    float kv[4];
+    if (__all_sync(0xffffffffu, in0 == 0xFu)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kv[c] = kick.s_dv[j0[c]];
     } else {
-        unsigned dep = 0, rem = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            bool removed;
-            const bool d = push_fast_walls(g, p.x[c], p.v[c], kick, a.dt, cell[c], removed, rare);
-            dep |= d ? (1u << c) : 0u;
+        for (int c = 0; c < 4; ++c) kv[c] = (in0 & (1u << c)) ? kick.s_dv[j0[c]] : __ldg(kick.dv_global + c0[c]);
+    }
+    // ---- push, boundaries, exit cell (ref :166-189, :211-217)
+    int c1[4], j1[4];
+    unsigned dep = 0, rem = 0, in1 = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool ok0 = (alive >> c) & 1u;
+        const float v1 = __fadd_rn(p.v[c], kv[c]);
+        const float x1 = __fadd_rn(x0[c], __fmul_rn(v1, a.dt));
+        bool deposits;
+        if (PERIODIC) {
+            const float a1 = __fsub_rn(x1, g.z_lo);
+            rare |= !(a1 > g.fold_lo);
+            rare |= !(a1 < g.fold_hi);
+            const float off = __fsub_rn(a1, (a1 >= g.span) ? g.span : 0.f);
+            const float x2 = __fadd_rn(off, (off >= 0.f) ? g.z_lo : g.z_hi);
+            const float b2 = __fsub_rn(x2, g.z_lo);
+            rare |= !(b2 < g.cell_span);
+            c1[c] = (int)min((unsigned)__float2int_rz(quotient_dz<true>(g, b2)), last);
+            p.x[c] = x2;
+            p.v[c] = v1;
+            deposits = true;
+        } else {
+            const bool ok1 = (x1 > g.lo_edge) && (x1 < g.hi_edge);
+            const int cr = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x1, g.z_lo)));
+            c1[c] = (int)min((unsigned)cr, last);
+            rare |= ok0 && ((ok1 && (c1[c] != cr)) || !(x1 == x1));
+            const bool removed = ok0 ? !ok1 : (p.x[c] < g.live_thr);
+            deposits = ok0 && ok1;
+            p.x[c] = removed ? g.parked : (ok0 ? x1 : p.x[c]);
+            p.v[c] = ok0 ? v1 : p.v[c];
             rem |= removed ? (1u << c) : 0u;
         }
-        if (__any_sync(0xffffffffu, rare))
-            return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
-        store_quad(a, q, p);
-        if (__all_sync(0xffffffffu, dep == 0xFu))  // uniform: the whole warp deposits (no per-slot predicates)
-            deposit_quad_win<WRAP>(g, p.x, cell, 0xFu, kick.map, s_lo, a.acc);
-        else
-            deposit_quad_win<WRAP>(g, p.x, cell, dep, kick.map, s_lo, a.acc);
-        return rem;
+        dep |= deposits ? (1u << c) : 0u;
+        bool inside;
+        const int j = map(c1[c], inside);
+        j1[c] = (inside && deposits) ? j : 0;
+        in1 |= (inside || !deposits) ? (1u << c) : 0u;
     }
+    if (__any_sync(0xffffffffu, rare))
+        return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
+    store_quad(a, q, p);
+    // ---- deposit (ref :219-225)
+    if (__all_sync(0xffffffffu, in1 == 0xFu)) {
+        unsigned old[8], top = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned w0, w1;
+            node_weights_fixed(g, p.x[c], c1[c], w0, w1);
+            const bool on = (dep >> c) & 1u;
+            w0 = on ? w0 : 0u;
+            w1 = on ? w1 : 0u;
+            old[2 * c] = atomicAdd(s_lo + j1[c], w0);
+            old[2 * c + 1] = atomicAdd(s_lo + j1[c] + 1, w1);
+            top = max(top, max(old[2 * c], old[2 * c + 1]));
+        }
+        if (__any_sync(0xffffffffu, top >= 0xFF000000u)) {  // a word of the plane may have wrapped: look, and
+#pragma unroll                                             // credit its 2^32 to the global accumulator
+            for (int c = 0; c < 4; ++c) {
+                unsigned w0, w1;
+                node_weights_fixed(g, p.x[c], c1[c], w0, w1);
+                const bool on = (dep >> c) & 1u;
+                if (on && old[2 * c] > ~w0) atomicAdd(a.acc + map.node_of(j1[c]), 1ull << 32);
+                if (on && old[2 * c + 1] > ~w1) atomicAdd(a.acc + map.node_of(j1[c] + 1), 1ull << 32);
+            }
+        }
+    } else {
+        deposit_quad_win<WRAP>(g, p.x, c1, dep, map, s_lo, a.acc);
+    }
+    return rem;
 }
 
 // One warp's range of units of a segment through the window tables.
@@ -311,7 +398,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
             int best = 0;
             for (int b = 1; b < kWinBuckets; ++b)
                 if (s_score[b] > s_score[best]) best = b;
-            s_w_lo = best * bucket_cells;
+            s_w_lo = (n_cells <= kWinCells) ? 0 : best * bucket_cells;  // a window as large as the grid starts at cell 0
         }
         __syncthreads();
         const int w_lo = s_w_lo;
@@ -341,13 +428,16 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     }
 }
 
-int move_window_size(int n_points) { return n_points - 1 > kWinCells ? kWinCells : 0; }
+// Cells of the window for a grid whose whole-grid tables do not fit (the caller has checked that).  Grids of
+// up to kWinCells cells (about 19k - 27.6k cells) are covered completely: every cell is inside the window of
+// every segment, nothing is ever served from global memory and no sorting is needed.
+int move_window_size(int n_points) { return n_points >= 2 ? kWinCells : 0; }
 
 int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic) {
     const size_t smem = (size_t)kWinNodes * 8;
     static int segs_per_cta = 0;  // process-wide tuning knob (an environment variable), not device state
     if (!segs_per_cta) {
-        segs_per_cta = 4;
+        segs_per_cta = 2;  // measured (production-like 65536-cell step): 2 -> 1.231, 3 -> 1.250, 4 -> 1.280, 6 -> 1.346 ms
         if (const char* e = getenv("ESPIC_WINDOW_SEGMENTS")) {  // segments per CTA
             const int s = atoi(e);
             if (s >= 1 && s <= 64) segs_per_cta = s;

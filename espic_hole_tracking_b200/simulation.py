@@ -300,7 +300,7 @@ class Simulation:
             self.sort_key_shift += 1
         auto = {}
         for name, v_th in (("ions", self.v_th_i / math.sqrt(c.sigma)), ("electrons", self.v_th_e)):
-            if window <= 0:
+            if window <= 0 or window >= c.n_cells:   # whole grid in shared memory, or a window that covers it
                 auto[name] = 0
                 continue
             margin = 0.5 * window - (1 << self.sort_key_shift)

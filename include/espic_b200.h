@@ -75,7 +75,8 @@ int espic_status(espic_ctx *ctx, int *status_out);
 int espic_device_info(espic_ctx *ctx, int *sm_count, int *mover_grid, int *mover_block);
 /* Cells of the shared-memory window the mover keeps per segment of the store when the grid is
  * too large for whole-grid tables (0 when the whole grid fits, i.e. up to ~19k points).  Drivers
- * use it to decide how often to call espic_sort_particles_coarse. */
+ * use it to decide how often to call espic_sort_particles_coarse; a window of at least n_points-1
+ * cells covers the grid completely and needs no sorting. */
 int espic_mover_window_cells(espic_ctx *ctx, int n_points);
 /* Kernels launched on this context since creation (bench's gpu_launches). */
 long long espic_launch_count(espic_ctx *ctx);

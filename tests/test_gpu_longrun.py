@@ -112,10 +112,11 @@ def test_configs4_hundred_thousand_steps_against_oracle_history():
     assert np.all(np.abs(hist["n_e"][:m] / gold["n_e"] - 1) < 0.015)
     assert np.all(np.abs(hist["n_i"][:m] / gold["n_i"] - 1) < 0.01)
     assert abs(hist["max_phi"][:10].mean() / gold["max_phi"][:10].mean() - 1) < 0.15      # hole depth while it lives
-    # same hole, same early trajectory: the first 200 steps coincide; afterwards two REFERENCE runs already sit 0.5
-    # apart at step 400 and 1.5 apart at step 900, so only the mean position of the first 1000 steps is compared
+    # same hole, same early trajectory: the first 200 steps coincide; at steps 300 / 400 eleven REFERENCE runs that
+    # differ only in the injection seed scatter over [-0.53, -0.23] / [-0.62, -0.01], and from step 500 on the hole
+    # runs off to either side (their mean positions over the first 1000 steps range from -1.5 to +0.55)
     assert np.all(np.abs(hist["hole"][:2] - gold["hole"][:2]) < 0.15)
-    assert abs(hist["hole"][:10].mean() - gold["hole"][:10].mean()) < 0.6
+    assert np.all(np.abs(hist["hole"][2:4] - gold["hole"][2:4]) < 0.7)
     late = slice(m // 2, m)                                                               # after the hole has left
     assert abs(hist["ke_e"][:m][late].mean() / gold["ke_e"][late].mean() - 1) < 0.02
     assert abs(hist["max_phi"][:m][late].mean()) < 0.25 and abs(gold["max_phi"][late].mean()) < 0.25

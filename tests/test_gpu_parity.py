@@ -194,9 +194,11 @@ def test_mover_object_and_no_position_update(ops, cpu):
 
 
 @pytest.mark.parametrize("periodic", [False, True])
-def test_mover_large_grid_path(ops, cpu, periodic):
-    """65537 grid points: the tables do not fit in shared memory (C4 of BASELINE.json)."""
-    n_cells = 65536
+@pytest.mark.parametrize("n_cells", [65536, 24576, 20000])
+def test_mover_large_grid_path(ops, cpu, periodic, n_cells):
+    """65537 grid points: the tables do not fit in shared memory (C4 of BASELINE.json).  24576 / 20000 cells:
+    too large for the whole-grid tables (~19k points) but not larger than the window of the windowed mover,
+    which then covers the grid completely (no global-memory path, no sorting needed)."""
     grid = wl.make_grid(n_cells)
     mask = np.zeros_like(grid)
     phi = wl.smooth_potential(grid, amplitude=1.0)
