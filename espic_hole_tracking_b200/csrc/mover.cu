@@ -483,7 +483,7 @@ static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
         int threads = kMoveThreads, per_sm = 0;
         if (const char* e = getenv("ESPIC_MOVE_THREADS")) {  // tuning knob
             const int t = atoi(e);
-            if (t == 256 || t == 512 || t == 1024) threads = t;
+            if (t >= 256 && t <= kMoveMaxThreads && t % 128 == 0) threads = t;
         }
         for (;;) {
             ESPIC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));

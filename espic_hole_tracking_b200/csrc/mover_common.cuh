@@ -22,8 +22,11 @@
 
 namespace espic {
 
-constexpr int kMoveThreads = 1024;  // one 32-warp CTA per SM (64 registers per thread): one tile to zero and flush per SM
-constexpr int kMoveMaxThreads = 1024;
+#ifndef ESPIC_MOVE_BOUNDS
+#define ESPIC_MOVE_BOUNDS 1024  // development switch: CTA width of k_move (768 -> 85 registers per thread, 24 warps per SM)
+#endif
+constexpr int kMoveThreads = ESPIC_MOVE_BOUNDS;  // one 32-warp CTA per SM (64 registers per thread): one tile to zero and flush per SM
+constexpr int kMoveMaxThreads = ESPIC_MOVE_BOUNDS;
 constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
 constexpr int kUnitSlots = 4 * kUnitQuads;    // 256 slots
 constexpr int kSmemBytesPerPoint = 12;

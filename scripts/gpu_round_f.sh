@@ -10,6 +10,12 @@ echo "== electron sort interval (segments default)" >> $L
 for k in 20 28 36; do echo -n "interval $k: " >> $L; PROBE_SORT_E=$k PROBE_STEPS=$((k*4)) timeout 300 python scripts/c4_production_probe.py 2>&1 | tail -1 | cut -c1-90 >> $L; done
 echo "== periodic 65536-cell bench" >> $L
 timeout 300 python bench.py --cells 65536 --steps 72 --no-cpu-baseline --no-host-arrays --no-configs3 2>&1 | tail -1 | cut -c1-300 >> $L
+echo "== k_move periodic CTA width variants" >> $L
+for v in m512 m768 m896 cur; do
+  if [ $v = cur ]; then unset ESPIC_LIB_PATH ESPIC_MOVE_THREADS; else export ESPIC_LIB_PATH=$PWD/variants/libespic_$v.so; export ESPIC_MOVE_THREADS=${v#m}; fi
+  echo -n "$v: " >> $L; timeout 300 python scripts/mover_micro_probe.py 2>&1 | tail -1 >> $L
+done
+unset ESPIC_LIB_PATH ESPIC_MOVE_THREADS
 cat $L
 PROBE_STEPS=20 timeout 900 ncu --set full --import-source on --clock-control none -k regex:k_move_win --launch-skip 212 --launch-count 2 -o gpurun_out/f_move_win python scripts/c4_production_probe.py > gpurun_out/f_ncu.log 2>&1
 echo "ncu exit $?"
