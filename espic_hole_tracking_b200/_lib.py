@@ -40,7 +40,7 @@ class StepArgs(C.Structure):
                 ("n_inject_ions", c_int), ("n_inject_electrons", c_int),
                 ("v_th_ions", c_float), ("v_d_ions", c_float), ("v_th_electrons", c_float),
                 ("v_d_electrons", c_float), ("inject_dt", c_float), ("step_index", c_int), ("inject_by_side", c_int), ("ion_tags", c_void_p),
-                ("electron_tags", c_void_p), ("fine_mesh", c_void_p), ("filter_scratch", c_void_p),
+                ("electron_tags", c_void_p), ("density_snapshot", c_void_p), ("fine_mesh", c_void_p), ("filter_scratch", c_void_p),
                 ("hole_position_out", c_void_p), ("n_fine", c_int), ("tracking_dz", c_double),
                 ("tracking_width", c_float)]
 

@@ -434,6 +434,13 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
                                 a->background_density, acc[0] ? &fix : nullptr);
     }
     if (rc) return rc;
+    if (a->density_snapshot) {  // the densities the solve used, before the pushes overwrite them
+        const float* src[2] = {a->exchange_parity >= 0 ? a->reduced_ion_density : a->ions.density,
+                               a->exchange_parity >= 0 ? a->reduced_electron_density : a->electrons.density};
+        for (int i = 0; i < 2; ++i)
+            ESPIC_CUDA(ctx, cudaMemcpyAsync(a->density_snapshot + (size_t)i * a->n_points, src[i],
+                                            (size_t)a->n_points * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     for (int i = 0; i < 2; ++i) {
         const espic_species* s = sp[i];
         rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,

@@ -16,15 +16,14 @@
 //   3. runs the slot update on its ranges, one quad (4 slots) per lane and instruction;
 //   4. flushes the plane into the global accumulators.
 //
-// Step 3 has two forms.  quad_win_fast is straight-line code for a warp all of whose live slots gather
-// from and deposit into the window: table index = cell - w_lo with ONE running maximum over the quad
-// as the in-window test (it also stands in for the index clamp and the bad-index test of the general
-// code: an index inside the window is inside the grid), dead or leaving slots steered to the window's
-// centre cell with zero weights instead of being branched around.  Behind one vote per quad, a warp with
-// a stray slot -- an electron that has outrun its segment, a particle injected since the last sort -- calls
-// quad_win_slow, the general per-lane code that serves such slots from global memory (kick table load,
-// 64-bit reductions).  ncu on the first version, which mapped, clamped and tested every slot on its own:
-// 109 instructions per particle.
+// Step 3 is straight-line code for every slot: table index = cell - w_lo, a slot that takes no part in
+// the gather or the deposit (dead, leaving, stray) steered to the window's centre cell with zero weights
+// instead of being branched around.  Stray slots -- an electron that has outrun its segment, a particle
+// injected since the last sort -- are patched per lane behind one vote each for the gather (kick from the
+// global table) and the deposit (64-bit global reductions); the warp keeps going, nothing is re-done.
+// ncu on the first version, which mapped, clamped and tested every slot on its own: 109 instructions per
+// particle; an all-or-nothing variant (a warp with one stray takes an out-of-line general path) lost more
+// than it gained: one stray in 128 slots is the rule late in a sort interval.
 //
 // After espic_sort_particles_coarse() a segment's particles sit within a few hundred cells of each
 // other and drift apart by |v| dt per step; the window leaves ~13700 cells of margin either side,
@@ -82,75 +81,22 @@ struct KickWindow {
     }
 };
 
-// General deposit of the slots of a quad named by `dep`: window cells through the shared-memory plane, the
-// others straight into the global accumulators.
-__device__ __forceinline__ void deposit_quad_win(const Geom& g, const float* x, const int* cell, unsigned dep,
-                                                 const WinMap& map, unsigned* s_lo, unsigned long long* acc) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (!((dep >> c) & 1u)) continue;
-        unsigned w0, w1;
-        node_weights_fixed(g, x[c], cell[c], w0, w1);
-        bool inside;
-        const int j = map(cell[c], inside);
-        if (inside) {
-            const unsigned old0 = atomicAdd(s_lo + j, w0);
-            const unsigned old1 = atomicAdd(s_lo + j + 1, w1);
-            // the word wrapped: its 2^32 goes straight to the global accumulator of that node
-            if (old0 > ~w0) atomicAdd(acc + map.node_of(j), 1ull << 32);
-            if (old1 > ~w1) atomicAdd(acc + map.node_of(j + 1), 1ull << 32);
-        } else {
-            atomicAdd(acc + cell[c], (unsigned long long)w0);
-            atomicAdd(acc + cell[c] + 1, (unsigned long long)w1);
-        }
-    }
-}
-
-// The general per-lane quad: any slot may gather or deposit outside the window (served from global memory),
-// every index is clamped and tested, anything the fast slot update does not cover goes through quad_generic.
-// Out of line: a few per cent of the warps of a sorted store come here, and its code must not sit in the
-// instruction stream of the others.
-// It loads the quad again itself (nothing has been stored yet): the caller's copy stays in registers.
+// One quad (see the header).  Every slot runs the straight-line code with a SAFE table index: a slot that takes
+// no part (dead on entry, leaving, stray) uses the window's centre cell jc with zero weights.  Strays -- table
+// index >= limit -- are patched per lane behind one vote each for the gather and the deposit: kick from the
+// global table, deposit by 64-bit global reductions; a stray whose CELL is not even inside the grid makes the
+// quad `rare` (redone by quad_generic, which clamps and reports as the reference's printf does).
+// xc: a position in the centre cell; limit: table indices below it are cells of the window.
 template <bool PERIODIC>
-__device__ __noinline__ unsigned quad_win_slow(const MoveArgs& a, const Geom& g, int q, int n_slots,
-                                               const KickWindow& kick, unsigned* s_lo) {
-    Quad p;
-    load_quad(a, q, p);
-    int cell[4];
-    bool rare = false;
-    unsigned dep = 0, rem = 0;
-    if (PERIODIC) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) push_fast_periodic(g, p.x[c], p.v[c], kick, a.dt, cell[c], rare);
-        dep = 0xFu;
-    } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            bool removed;
-            const bool d = push_fast_walls(g, p.x[c], p.v[c], kick, a.dt, cell[c], removed, rare);
-            dep |= d ? (1u << c) : 0u;
-            rem |= removed ? (1u << c) : 0u;
-        }
-    }
-    if (__any_sync(0xffffffffu, rare))
-        return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
-    store_quad(a, q, p);
-    deposit_quad_win(g, p.x, cell, dep, kick.map, s_lo, a.acc);
-    return rem;
-}
-
-// The straight-line quad (see the header).  xc: a position in the window's centre cell.
-template <bool PERIODIC>
-__device__ __forceinline__ unsigned quad_win_fast(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
-                                                  const KickWindow& kick, unsigned* s_lo, float xc, unsigned limit) {
-    // limit: table indices below it are cells of the window (kWinCells, or fewer on a grid smaller than the window)
+__device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
+                                             const KickWindow& kick, unsigned* s_lo, float xc, int jc, unsigned limit) {
     constexpr bool WRAP = PERIODIC;  // wall windows are clamped to the grid: index = cell - w_lo
     const WinMap& map = kick.map;
-    int j0[4];
-    unsigned worst = 0u;  // running maximum of the table indices of the quad; >= kWinCells: some slot is outside
+    const unsigned last = (unsigned)g.last_cell;
+    int j0[4], c0[4];
+    unsigned out0 = 0, alive = 0;
     bool rare = false;
     float xe[4];
-    unsigned alive = 0;
     // ---- entry: liveness, cell, table index (ref infMagSim_c.c:146-165)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -167,19 +113,33 @@ __device__ __forceinline__ unsigned quad_win_fast(const MoveArgs& a, const Geom&
             xe[c] = p.x[c];
             b0 = __fsub_rn(ok ? p.x[c] : xc, g.z_lo);
         }
-        j0[c] = map.index<WRAP>(__float2int_rz(quotient_dz<true>(g, b0)));
-        worst = max(worst, (unsigned)j0[c]);
+        c0[c] = __float2int_rz(quotient_dz<true>(g, b0));
+        const int j = map.index<WRAP>(c0[c]);
+        const bool out = (unsigned)j >= limit;
+        j0[c] = out ? jc : j;
+        out0 |= out ? (1u << c) : 0u;
     }
-    if (PERIODIC) worst = rare ? 0xffffffffu : worst;
-    if (!__all_sync(0xffffffffu, worst < limit)) return quad_win_slow<PERIODIC>(a, g, q, n_slots, kick, s_lo);
-    // ---- gather, push, boundaries, exit cell (ref :166-189, :211-217)
-    float xo[4], vo[4], xd[4];
+    // ---- gather (ref :166-168)
+    float kv[4];
+    if (!__any_sync(0xffffffffu, out0 != 0u)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kv[c] = kick.s_dv[j0[c]];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool out = (out0 >> c) & 1u;
+            const bool bad = out && (unsigned)c0[c] > last;  // not a cell of the grid at all
+            rare |= bad;
+            kv[c] = (out && !bad) ? __ldg(kick.dv_global + c0[c]) : kick.s_dv[j0[c]];
+        }
+    }
+    // ---- push, boundaries, exit cell (ref :166-189, :211-217)
+    float xd[4];
     int j1[4], c1[4];
-    unsigned dep = 0, rem = 0;
-    worst = 0u;
+    unsigned dep = 0, rem = 0, out1 = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float v1 = __fadd_rn(p.v[c], kick.s_dv[j0[c]]);
+        const float v1 = __fadd_rn(p.v[c], kv[c]);
         const float x1 = __fadd_rn(xe[c], __fmul_rn(v1, a.dt));
         if (PERIODIC) {
             const float a1 = __fsub_rn(x1, g.z_lo);
@@ -190,8 +150,8 @@ __device__ __forceinline__ unsigned quad_win_fast(const MoveArgs& a, const Geom&
             const float b2 = __fsub_rn(xd[c], g.z_lo);
             rare |= !(b2 < g.cell_span);
             c1[c] = __float2int_rz(quotient_dz<true>(g, b2));
-            xo[c] = xd[c];
-            vo[c] = v1;
+            p.x[c] = xd[c];
+            p.v[c] = v1;
         } else {
             const bool ok0 = (alive >> c) & 1u;
             const bool ok1 = (x1 > g.lo_edge) && (x1 < g.hi_edge);  // false for NaN: parked, as the reference parks it
@@ -199,33 +159,36 @@ __device__ __forceinline__ unsigned quad_win_fast(const MoveArgs& a, const Geom&
             const bool removed = ok0 ? !ok1 : (p.x[c] < g.live_thr);
             xd[c] = deposits ? x1 : xc;
             c1[c] = __float2int_rz(quotient_dz<true>(g, __fsub_rn(xd[c], g.z_lo)));
-            xo[c] = removed ? g.parked : (ok0 ? x1 : p.x[c]);
-            vo[c] = ok0 ? v1 : p.v[c];
+            p.x[c] = removed ? g.parked : (ok0 ? x1 : p.x[c]);
+            p.v[c] = ok0 ? v1 : p.v[c];
             dep |= deposits ? (1u << c) : 0u;
             rem |= removed ? (1u << c) : 0u;
         }
-        j1[c] = map.index<WRAP>(c1[c]);
-        worst = max(worst, (unsigned)j1[c]);
+        const int j = map.index<WRAP>(c1[c]);
+        const bool out = (unsigned)j >= limit;
+        j1[c] = out ? jc : j;
+        out1 |= out ? (1u << c) : 0u;
     }
-    if (PERIODIC) worst = rare ? 0xffffffffu : worst;
-    if (!__all_sync(0xffffffffu, worst < limit)) return quad_win_slow<PERIODIC>(a, g, q, n_slots, kick, s_lo);
+    if (PERIODIC) dep = 0xFu;
+    const bool strays = __any_sync(0xffffffffu, out1 != 0u);
+    if (strays) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        p.x[c] = xo[c];
-        p.v[c] = vo[c];
+        for (int c = 0; c < 4; ++c) rare |= ((out1 >> c) & 1u) && (unsigned)c1[c] > last;
     }
+    if (__any_sync(0xffffffffu, rare))
+        return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
     store_quad(a, q, p);
-    // ---- deposit (ref :219-225): eight atomics, one running maximum of the returned words as the carry test
+    // ---- deposit (ref :219-225): eight atomics, one running maximum of the returned words as the carry test;
+    //      slots that do not deposit here (dead, removed, stray) add zero to the centre cell
+    const unsigned here = dep & ~out1;
     unsigned old[8], top = 0u;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         unsigned w0, w1;
         node_weights_fixed(g, xd[c], c1[c], w0, w1);
-        if (!PERIODIC) {
-            const bool on = (dep >> c) & 1u;
-            w0 = on ? w0 : 0u;
-            w1 = on ? w1 : 0u;
-        }
+        const bool on = (here >> c) & 1u;
+        w0 = on ? w0 : 0u;
+        w1 = on ? w1 : 0u;
         old[2 * c] = atomicAdd(s_lo + j1[c], w0);
         old[2 * c + 1] = atomicAdd(s_lo + j1[c] + 1, w1);
         top = max(top, max(old[2 * c], old[2 * c + 1]));
@@ -235,9 +198,21 @@ __device__ __forceinline__ unsigned quad_win_fast(const MoveArgs& a, const Geom&
         for (int c = 0; c < 4; ++c) {
             unsigned w0, w1;
             node_weights_fixed(g, xd[c], c1[c], w0, w1);
-            const bool on = PERIODIC || ((dep >> c) & 1u);
+            const bool on = (here >> c) & 1u;
             if (on && old[2 * c] > ~w0) atomicAdd(a.acc + map.node_of(j1[c]), 1ull << 32);
             if (on && old[2 * c + 1] > ~w1) atomicAdd(a.acc + map.node_of(j1[c] + 1), 1ull << 32);
+        }
+    }
+    if (strays) {  // slots whose deposit cell lies outside the window: straight into the global accumulators
+        const unsigned far = dep & out1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if ((far >> c) & 1u) {
+                unsigned w0, w1;
+                node_weights_fixed(g, xd[c], c1[c], w0, w1);
+                atomicAdd(a.acc + c1[c], (unsigned long long)w0);
+                atomicAdd(a.acc + c1[c] + 1, (unsigned long long)w1);
+            }
         }
     }
     return rem;
@@ -326,9 +301,10 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
             const KickWindow kick{s_dv, a.dv_global, map};
             // a position inside the window's centre cell (table index kWinCells/2): where the fast path parks the
             // slots that take no part in the gather or the deposit
-            const int centre = map.node_of(min(kWinCells / 2, n_cells / 2));
+            const int centre = map.node_of(min(kWinCells / 2, n_cells / 2));  // table index jc below
             const float xc = __fmul_rn(0.5f, __fadd_rn(__ldg(a.grid + centre), __ldg(a.grid + centre + 1)));
             const unsigned limit = PERIODIC ? (unsigned)kWinCells : (unsigned)min(kWinCells, n_cells - map.w_lo);
+            const int jc = min(kWinCells / 2, n_cells / 2);
             const int range = r0 + warp;
             int removed = 0;
             const int u0 = split.first_unit(range), u1 = u0 + split.unit_count(range);
@@ -345,8 +321,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
                     Quad p0, p1;
                     load_quad(a, q0, p0);
                     load_quad(a, q1, p1);
-                    const unsigned rem0 = quad_win_fast<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, xc, limit);
-                    const unsigned rem1 = quad_win_fast<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, xc, limit);
+                    const unsigned rem0 = quad_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, xc, jc, limit);
+                    const unsigned rem1 = quad_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, xc, jc, limit);
                     if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
                         stage_removed(rem0, q0, lane, stage_ids, removed);
                         stage_removed(rem1, q1, lane, stage_ids, removed);

@@ -33,6 +33,7 @@ class Recorder:
         self.times, self.potentials, self.ion_densities, self.electron_densities = [], [], [], []
         self.charge_derivatives, self.histograms = [], {"ions": [], "electrons": [], "electrons_inject0": []}
         self._prev_charge = np.zeros(sim.n_points, np.float32)
+        sim.keep_solved_densities = True   # see Simulation.solved_densities
 
     def record(self) -> None:
         """Call after ``sim.step()``: stores the fields that step solved for (time t - dt)."""
@@ -42,8 +43,9 @@ class Recorder:
             return
         self.times.append(sim.t - sim.dt)
         self.potentials.append(sim.potential.cpu().numpy())
-        self.ion_densities.append(sim.ion_density.cpu().numpy())
-        self.electron_densities.append(sim.electron_density.cpu().numpy())
+        den_i, den_e = sim.solved_densities()   # reduced, end-fixed: what the reference appends (:906-910)
+        self.ion_densities.append(den_i.cpu().numpy())
+        self.electron_densities.append(den_e.cpu().numpy())
         charge = sim.charge_density.cpu().numpy()
         self.charge_derivatives.append((charge - self._prev_charge) / np.float32(sim.dt))   # :808-809
         self._prev_charge = charge

@@ -206,6 +206,11 @@ class Simulation:
         self.fused_deposit = self.exchange_mode in ("none", "p2p")
         self.acc = torch.zeros((2, (n_points + 64) & ~63), dtype=torch.int64, device=self.device)   # >= n_points + 1
         self._acc_pending = [False, False]
+        # what the reference driver stores per step (:906-910) are the reduced, end-fixed densities the solve used.
+        # With the fused deposit ion_density / electron_density hold exactly that after a step; without it
+        # (exchange="nccl") the pushes overwrite them, and a Recorder asks for a snapshot (keep_solved_densities)
+        self.keep_solved_densities = False
+        self._solved = None
         self.k = 0
         self.t = 0.0
         self.sort_intervals = {"ions": 0, "electrons": 0}   # set by initialize() (_plan_sorting)
@@ -400,6 +405,10 @@ class Simulation:
             else:
                 a.exchange_parity = -1
             a.ion_acc_pending, a.electron_acc_pending = int(self._acc_pending[0]), int(self._acc_pending[1])
+            if self.keep_solved_densities and not self.fused_deposit:
+                if self._solved is None:
+                    self._solved = torch.zeros((2, self.n_points), dtype=torch.float32, device=self.device)
+                a.density_snapshot = self._solved.data_ptr()
             a.a_b = a_b
             a.fix_ions = int(periodic or k <= c.time_steps_immobile_ions)
             a.fix_electrons = 1
@@ -463,6 +472,12 @@ class Simulation:
             if every and self.k % every == 0:
                 self.sort_particles((n,), key_shift=self.sort_key_shift, lookahead_steps=0.5 * every)
 
+    def solved_densities(self):
+        """(ion, electron) densities the last field solve used: reduced over the ranks, end nodes fixed."""
+        if self._solved is not None:
+            return self._solved[0], self._solved[1]
+        return self.ion_density, self.electron_density
+
     def flush_pending(self, k: int | None = None) -> None:
         """Converts a pending fused deposit into the float density rows step k (default: the next step to
         run) reads (espic_convert_density: the conversion the field solve would have made, bit for bit)."""
@@ -494,6 +509,7 @@ class Simulation:
         histograms are wanted).  Returns whether the hole position of this step has been tracked."""
         c = self.cfg
         self.flush_pending(k)   # the operators read and write the float density rows
+        self._solved = None     # this mode's Recorder reads the arrays themselves: nothing has been pushed yet when it does
         periodic = c.periodic_particles
         fix_ions = periodic or k <= c.time_steps_immobile_ions
         if self.xch is not None:

@@ -231,6 +231,10 @@ typedef struct {
                                           * lands among its neighbours in the store.  Physically invisible. */
     int *ion_tags;                       /* int[storage] injection histories; may be NULL when nothing is injected */
     int *electron_tags;
+    float *density_snapshot;             /* NULL, or float[2][n_points]: the reduced, end-fixed ion and electron
+                                          * densities the field solve used, copied right after the solve -- what the
+                                          * reference driver stores per step (ref :763-779, 906-910) -- for the step
+                                          * modes in which the pushes overwrite those arrays (species.acc == NULL) */
     /* hole tracking after the solve (ref :896-897): position_out == NULL switches it off */
     const float *fine_mesh;
     float *filter_scratch;               /* n_fine floats */
