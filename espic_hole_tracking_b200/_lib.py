@@ -55,6 +55,7 @@ SIGNATURES = {
     "espic_status": (c_int, [c_void_p, C.POINTER(c_int)]),
     "espic_device_info": (c_int, [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     "espic_launch_count": (C.c_longlong, [c_void_p]),
+    "espic_debug_cta_cycles": (c_int, [c_void_p, C.POINTER(C.c_longlong), c_int]),
     "espic_timing_enable": (c_int, [c_void_p, c_int]),
     "espic_timing_read": (c_int, [c_void_p, C.POINTER(c_double), C.POINTER(c_int), C.POINTER(c_double)]),
     "espic_move_particles": (c_int, [c_void_p, P, P, P, c_float, c_float, c_float, c_int, P, P, P, P,

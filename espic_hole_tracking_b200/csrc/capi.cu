@@ -157,6 +157,7 @@ void espic_destroy(espic_ctx* ctx) {
     free_scratch(ctx->sort_ws);
     free_scratch(ctx->host_stage);
     free_scratch(ctx->filter_ws);
+    free_scratch(ctx->debug_ws);
     for (int r = 0; r < ctx->xch.world; ++r)
         if (r != ctx->xch.rank && ctx->xch.peer[r]) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
     if (ctx->xch.local) cudaFree(ctx->xch.local);
@@ -205,6 +206,18 @@ int espic_mover_window_cells(espic_ctx* ctx, int n_points) {
 }
 
 long long espic_launch_count(espic_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// Development aid: with ESPIC_DEBUG_CTA=1 in the environment the windowed mover records, per CTA, the clock cycles
+// from entry to exit of its last launch; copies up to n of them to `out` (synchronises).  Returns the count.
+int espic_debug_cta_cycles(espic_ctx* ctx, long long* out, int n) {
+    DeviceGuard guard(ctx);
+    if (!ctx || !out || n < 1 || !ctx->debug_ws.ptr) return 0;
+    if (n > 1024) n = 1024;
+    if (cudaMemcpyAsync(out, ctx->debug_ws.ptr, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return 0;
+    return n;
+}
 
 int espic_timing_enable(espic_ctx* ctx, int on) {
     DeviceGuard guard(ctx);

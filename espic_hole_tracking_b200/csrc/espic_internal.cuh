@@ -168,6 +168,7 @@ struct espic_ctx {
     espic::Scratch sort_ws;             // radix-sort ping-pong buffers and histograms
     espic::Scratch host_stage;          // device staging for the host-pointer entry points
     espic::Scratch filter_ws;           // block centres + moments of the hole-tracking filter
+    espic::Scratch debug_ws;            // ESPIC_DEBUG_CTA: per-CTA cycle counts of the last windowed mover launch
     const float* filter_grid = nullptr; // grid whose end points are cached below
     int filter_n = 0;
     float filter_ends[2] = {0.f, 0.f};

@@ -571,6 +571,15 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.a_b = a_b;
     a.update_position = update_position;
     a.minimal = minimal;
+    {
+        static int debug_cta = -1;
+        if (debug_cta < 0) debug_cta = getenv("ESPIC_DEBUG_CTA") ? 1 : 0;
+        if (debug_cta) {
+            rc = ensure(ctx, ctx->debug_ws, 1024 * sizeof(long long), "debug");
+            if (rc) return rc;
+            a.cta_cycles = (long long*)ctx->debug_ws.ptr;
+        }
+    }
     a.vec_ok = ((reinterpret_cast<uintptr_t>(particles) & 15u) == 0 && (storage & 3) == 0) ? 1 : 0;
     if (minimal) a.vec_ok = 0;  // the stripped variant (never on the step path) runs the generic slot update only
     static int prefetch_env = -2;

@@ -69,6 +69,7 @@ struct MoveArgs {
     int* empty_slots;
     int largest_allowed_slot;
     int slot_offset;
+    long long* cta_cycles;  // development aid (ESPIC_DEBUG_CTA=1): per CTA, clock cycles from entry to exit
     int minimal;  // move_particles_c_minimal (ref infMagSim_c.c:231-341): no mask, and a slot that is out of
                   // bounds on entry is left alone even when it does not carry the parked marker (ref :333)
 };

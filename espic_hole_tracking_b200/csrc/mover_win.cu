@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     __shared__ int s_score[kWinBuckets];
     __shared__ int s_seg, s_w_lo;
 
+    const long long t_entry = a.cta_cycles ? clock64() : 0ll;
     const int n_points = a.n_points, n_cells = n_points - 1;
     const Geom g = make_geom(a.grid, n_points);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
         }
         __syncthreads();
     }
+    if (a.cta_cycles && tid == 0) a.cta_cycles[blockIdx.x] = clock64() - t_entry;
 }
 
 // Cells of the window for a grid whose whole-grid tables do not fit (the caller has checked that).  Grids of
