@@ -17,7 +17,7 @@
 //   4. flushes the plane into the global accumulators.
 //
 // Step 3 is straight-line code for every slot: table index = cell - w_lo, a slot that takes no part in
-// the gather or the deposit (dead, leaving, stray) steered to the window's centre cell with zero weights
+// the gather or the deposit (dead, leaving, stray) given a dummy word pair of its lane with zero weights
 // instead of being branched around.  Stray slots -- an electron that has outrun its segment, a particle
 // injected since the last sort -- are patched per lane behind one vote each for the gather (kick from the
 // global table) and the deposit (64-bit global reductions); the warp keeps going, nothing is re-done.
@@ -82,14 +82,16 @@ struct KickWindow {
 };
 
 // One quad (see the header).  Every slot runs the straight-line code with a SAFE table index: a slot that takes
-// no part (dead on entry, leaving, stray) uses the window's centre cell jc with zero weights.  Strays -- table
-// index >= limit -- are patched per lane behind one vote each for the gather and the deposit: kick from the
-// global table, deposit by 64-bit global reductions; a stray whose CELL is not even inside the grid makes the
-// quad `rare` (redone by quad_generic, which clamps and reports as the reference's printf does).
-// xc: a position in the centre cell; limit: table indices below it are cells of the window.
+// no part (dead on entry, leaving, stray) has a table index outside the window by construction -- its "cell" is
+// that of a parked or out-of-domain position -- and is given the lane's own dummy word pair jd instead, with zero
+// weights (one shared dummy address would serialise: a third of the slots of a wall segment leave every step).
+// Live strays -- table index >= limit -- are patched per lane behind one vote each for the gather and the deposit:
+// kick from the global table, deposit by 64-bit global reductions; a live stray whose CELL is not even inside the
+// grid makes the quad `rare` (redone by quad_generic, which clamps and reports as the reference's printf does).
+// limit: table indices below it are cells of the window.
 template <bool PERIODIC>
 __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
-                                             const KickWindow& kick, unsigned* s_lo, float xc, int jc, unsigned limit) {
+                                             const KickWindow& kick, unsigned* s_lo, int jd, unsigned limit) {
     constexpr bool WRAP = PERIODIC;  // wall windows are clamped to the grid: index = cell - w_lo
     const WinMap& map = kick.map;
     const unsigned last = (unsigned)g.last_cell;
@@ -101,23 +103,24 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float b0;
+        bool ok = true;
         if (PERIODIC) {  // a live slot inside the domain; everything else (dead slots included) is `rare`
             const float a0 = __fsub_rn(p.x[c], g.z_lo);
             xe[c] = __fadd_rn(a0, g.z_lo);
             b0 = __fsub_rn(xe[c], g.z_lo);
             rare |= !(a0 >= 0.f);
             rare |= !(b0 < g.cell_span);
-        } else {  // dead slots are common (removed particles wait for re-injection): steered to the centre cell
-            const bool ok = (p.x[c] > g.lo_edge) && (p.x[c] < g.hi_edge);
+        } else {  // dead slots are common (removed particles wait for re-injection)
+            ok = (p.x[c] > g.lo_edge) && (p.x[c] < g.hi_edge);
             alive |= ok ? (1u << c) : 0u;
             xe[c] = p.x[c];
-            b0 = __fsub_rn(ok ? p.x[c] : xc, g.z_lo);
+            b0 = __fsub_rn(p.x[c], g.z_lo);
         }
         c0[c] = __float2int_rz(quotient_dz<true>(g, b0));
         const int j = map.index<WRAP>(c0[c]);
         const bool out = (unsigned)j >= limit;
-        j0[c] = out ? jc : j;
-        out0 |= out ? (1u << c) : 0u;
+        j0[c] = out ? jd : j;
+        out0 |= (out && ok) ? (1u << c) : 0u;
     }
     // ---- gather (ref :166-168)
     float kv[4];
@@ -128,7 +131,7 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const bool out = (out0 >> c) & 1u;
-            const bool bad = out && (unsigned)c0[c] > last;  // not a cell of the grid at all
+            const bool bad = out && (unsigned)c0[c] > last;  // a live slot whose cell is not a cell of the grid
             rare |= bad;
             kv[c] = (out && !bad) ? __ldg(kick.dv_global + c0[c]) : kick.s_dv[j0[c]];
         }
@@ -141,6 +144,7 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
     for (int c = 0; c < 4; ++c) {
         const float v1 = __fadd_rn(p.v[c], kv[c]);
         const float x1 = __fadd_rn(xe[c], __fmul_rn(v1, a.dt));
+        bool deposits = true;
         if (PERIODIC) {
             const float a1 = __fsub_rn(x1, g.z_lo);
             rare |= !(a1 > g.fold_lo);
@@ -155,10 +159,10 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
         } else {
             const bool ok0 = (alive >> c) & 1u;
             const bool ok1 = (x1 > g.lo_edge) && (x1 < g.hi_edge);  // false for NaN: parked, as the reference parks it
-            const bool deposits = ok0 && ok1;
+            deposits = ok0 && ok1;
             const bool removed = ok0 ? !ok1 : (p.x[c] < g.live_thr);
-            xd[c] = deposits ? x1 : xc;
-            c1[c] = __float2int_rz(quotient_dz<true>(g, __fsub_rn(xd[c], g.z_lo)));
+            xd[c] = x1;
+            c1[c] = __float2int_rz(quotient_dz<true>(g, __fsub_rn(x1, g.z_lo)));
             p.x[c] = removed ? g.parked : (ok0 ? x1 : p.x[c]);
             p.v[c] = ok0 ? v1 : p.v[c];
             dep |= deposits ? (1u << c) : 0u;
@@ -166,8 +170,8 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
         }
         const int j = map.index<WRAP>(c1[c]);
         const bool out = (unsigned)j >= limit;
-        j1[c] = out ? jc : j;
-        out1 |= out ? (1u << c) : 0u;
+        j1[c] = out ? jd : j;
+        out1 |= (out && deposits) ? (1u << c) : 0u;
     }
     if (PERIODIC) dep = 0xFu;
     const bool strays = __any_sync(0xffffffffu, out1 != 0u);
@@ -179,7 +183,7 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
         return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
     store_quad(a, q, p);
     // ---- deposit (ref :219-225): eight atomics, one running maximum of the returned words as the carry test;
-    //      slots that do not deposit here (dead, removed, stray) add zero to the centre cell
+    //      slots that do not deposit here (dead, removed, stray) add zero to the lane's dummy words
     const unsigned here = dep & ~out1;
     unsigned old[8], top = 0u;
 #pragma unroll
@@ -204,10 +208,9 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
         }
     }
     if (strays) {  // slots whose deposit cell lies outside the window: straight into the global accumulators
-        const unsigned far = dep & out1;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            if ((far >> c) & 1u) {
+            if ((out1 >> c) & 1u) {
                 unsigned w0, w1;
                 node_weights_fixed(g, xd[c], c1[c], w0, w1);
                 atomicAdd(a.acc + c1[c], (unsigned long long)w0);
@@ -245,8 +248,11 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
         if (tid == 0) s_seg = atomicAdd(a.seg_counter, 1);
         if (tid < kWinBuckets) s_bucket[tid] = 0;
         __syncthreads();
-        const int seg = s_seg;
-        if (seg >= a.n_segments) break;
+        // segments are handed out from both ends of the store inwards: the two wall segments -- where a third of the
+        // slots is removed and re-injected every step, several times the work of an interior segment -- start first
+        const int ticket = s_seg;
+        if (ticket >= a.n_segments) break;
+        const int seg = (ticket & 1) ? a.n_segments - 1 - (ticket >> 1) : (ticket >> 1);
         const int r0 = seg * warps_per_cta;
         const int seg_u0 = split.first_unit(r0), seg_u1 = split.first_unit(r0 + warps_per_cta);
 
@@ -300,12 +306,9 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
         // 3. this warp's range
         {
             const KickWindow kick{s_dv, a.dv_global, map};
-            // a position inside the window's centre cell (table index kWinCells/2): where the fast path parks the
-            // slots that take no part in the gather or the deposit
-            const int centre = map.node_of(min(kWinCells / 2, n_cells / 2));  // table index jc below
-            const float xc = __fmul_rn(0.5f, __fadd_rn(__ldg(a.grid + centre), __ldg(a.grid + centre + 1)));
             const unsigned limit = PERIODIC ? (unsigned)kWinCells : (unsigned)min(kWinCells, n_cells - map.w_lo);
-            const int jc = min(kWinCells / 2, n_cells / 2);
+            // the lane's own dummy word pair in the middle of the table, for slots that take no part (zero weights)
+            const int jd = min(kWinCells / 2, n_cells / 2) + 2 * lane;
             const int range = r0 + warp;
             int removed = 0;
             const int u0 = split.first_unit(range), u1 = u0 + split.unit_count(range);
@@ -322,8 +325,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
                     Quad p0, p1;
                     load_quad(a, q0, p0);
                     load_quad(a, q1, p1);
-                    const unsigned rem0 = quad_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, xc, jc, limit);
-                    const unsigned rem1 = quad_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, xc, jc, limit);
+                    const unsigned rem0 = quad_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, jd, limit);
+                    const unsigned rem1 = quad_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, jd, limit);
                     if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
                         stage_removed(rem0, q0, lane, stage_ids, removed);
                         stage_removed(rem1, q1, lane, stage_ids, removed);

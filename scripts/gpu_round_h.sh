@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_loop.py -m gpu -q -x ) > gpurun_out/h_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/h_pytest.log
+tail -3 gpurun_out/h_pytest.log
+L=gpurun_out/h_probe.log
+echo "== per-CTA cycles, segments 1 / 4" > $L
+PROBE_STEPS=34 python scripts/cta_cycles_probe.py 2>&1 | tail -4 >> $L
+ESPIC_WINDOW_SEGMENTS=4 PROBE_STEPS=34 python scripts/cta_cycles_probe.py 2>&1 | tail -4 >> $L
+echo "== production-like 65536-cell run: segments per CTA" >> $L
+for s in 1 2 4 8; do echo -n "segments $s: " >> $L; ESPIC_WINDOW_SEGMENTS=$s PROBE_STEPS=56 timeout 300 python scripts/c4_production_probe.py 2>&1 | tail -1 | cut -c1-90 >> $L; done
+echo "== periodic 65536-cell bench" >> $L
+timeout 300 python bench.py --cells 65536 --steps 72 --no-cpu-baseline --no-host-arrays --no-configs3 2>&1 | tail -1 | cut -c1-300 >> $L
+cat $L
