@@ -212,7 +212,7 @@ long long espic_launch_count(espic_ctx* ctx) { return ctx ? ctx->launches : -1; 
 int espic_debug_cta_cycles(espic_ctx* ctx, long long* out, int n) {
     DeviceGuard guard(ctx);
     if (!ctx || !out || n < 1 || !ctx->debug_ws.ptr) return 0;
-    if (n > 1024) n = 1024;
+    if (n > 2048) n = 2048;
     if (cudaMemcpyAsync(out, ctx->debug_ws.ptr, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess)
         return 0;

@@ -575,7 +575,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
         static int debug_cta = -1;
         if (debug_cta < 0) debug_cta = getenv("ESPIC_DEBUG_CTA") ? 1 : 0;
         if (debug_cta) {
-            rc = ensure(ctx, ctx->debug_ws, 1024 * sizeof(long long), "debug");
+            rc = ensure(ctx, ctx->debug_ws, 2048 * sizeof(long long), "debug");
             if (rc) return rc;
             a.cta_cycles = (long long*)ctx->debug_ws.ptr;
         }
