@@ -35,10 +35,6 @@
 
 #include "mover_common.cuh"
 
-#ifndef ESPIC_DEBUG_WIN
-#define ESPIC_DEBUG_WIN 0   // development build (scripts/build_variants.sh dbg "-DESPIC_DEBUG_WIN=1" + ESPIC_DEBUG_CTA=1): per-CTA and
-#endif                      // per-segment cycle counts and stray counters through espic_debug_cta_cycles
-
 namespace espic {
 
 constexpr int kWinCells = 27648;
@@ -95,8 +91,7 @@ struct KickWindow {
 // limit: table indices below it are cells of the window.
 template <bool PERIODIC>
 __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Quad& p, int q, int n_slots,
-                                             const KickWindow& kick, unsigned* s_lo, int jd, unsigned limit,
-                                             int* dbg = nullptr) {
+                                             const KickWindow& kick, unsigned* s_lo, int jd, unsigned limit) {
     constexpr bool WRAP = PERIODIC;  // wall windows are clamped to the grid: index = cell - w_lo
     const WinMap& map = kick.map;
     const unsigned last = (unsigned)g.last_cell;
@@ -133,7 +128,6 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
 #pragma unroll
         for (int c = 0; c < 4; ++c) kv[c] = kick.s_dv[j0[c]];
     } else {
-        if (dbg && (threadIdx.x & 31) == 0) atomicAdd(dbg + 1, 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const bool out = (out0 >> c) & 1u;
@@ -185,11 +179,8 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
 #pragma unroll
         for (int c = 0; c < 4; ++c) rare |= ((out1 >> c) & 1u) && (unsigned)c1[c] > last;
     }
-    if (__any_sync(0xffffffffu, rare)) {
-        if (dbg && (threadIdx.x & 31) == 0) atomicAdd(dbg, 1);
+    if (__any_sync(0xffffffffu, rare))
         return quad_generic<PERIODIC, false>(a, q, n_slots, a.dv_global, false, nullptr, nullptr);
-    }
-    if (dbg && strays && (threadIdx.x & 31) == 0) atomicAdd(dbg + 2, 1);
     store_quad(a, q, p);
     // ---- deposit (ref :219-225): eight atomics, one running maximum of the returned words as the carry test;
     //      slots that do not deposit here (dead, removed, stray) add zero to the lane's dummy words
@@ -238,16 +229,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     __shared__ int s_bucket[kWinBuckets];
     __shared__ int s_score[kWinBuckets];
     __shared__ int s_seg, s_w_lo;
-#if ESPIC_DEBUG_WIN
-    __shared__ int s_dbg[4];
-    if (threadIdx.x < 4) s_dbg[threadIdx.x] = 0;
-#else
-    int* const s_dbg = nullptr;
-#endif
 
-#if ESPIC_DEBUG_WIN
     const long long t_entry = a.cta_cycles ? clock64() : 0ll;
-#endif
     const int n_points = a.n_points, n_cells = n_points - 1;
     const Geom g = make_geom(a.grid, n_points);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,108 +244,64 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     const int bucket_cells = (n_cells + kWinBuckets - 1) / kWinBuckets;
     const int window_buckets = kWinCells / bucket_cells;
 
-    constexpr int kTableIters = (kWinNodes + kWinThreads - 1) / kWinThreads;  // 28
-    const float inv_bucket_cells = 1.0f / (float)bucket_cells;
-    if (tid == 0) s_seg = atomicAdd(a.seg_counter, 1);
     for (;;) {
+        if (tid == 0) s_seg = atomicAdd(a.seg_counter, 1);
         if (tid < kWinBuckets) s_bucket[tid] = 0;
         __syncthreads();
         // segments are handed out from both ends of the store inwards: the two wall segments -- where a third of the
         // slots is removed and re-injected every step, several times the work of an interior segment -- start first
         const int ticket = s_seg;
         if (ticket >= a.n_segments) break;
-        // the next ticket is fetched now (thread 0 keeps it in a register until the end of this segment): the
-        // round trip of the global atomic overlaps with the segment's work
-        int next_ticket = 0;
-        if (tid == 0) next_ticket = atomicAdd(a.seg_counter, 1);
         const int seg = (ticket & 1) ? a.n_segments - 1 - (ticket >> 1) : (ticket >> 1);
-#if ESPIC_DEBUG_WIN
-        long long t_ph[5];
-        if (a.cta_cycles) t_ph[0] = clock64();
-#endif
         const int r0 = seg * warps_per_cta;
         const int seg_u0 = split.first_unit(r0), seg_u1 = split.first_unit(r0 + warps_per_cta);
 
-        // 1. where are this segment's particles?  1024 samples -> 64 buckets -> the best window start, found by one
-        //    warp (two barriers in all; the first version took 9.5 us per segment here: a 64-bit division per
-        //    sample, 1024 atomics on one or two shared words, a serial scan of the scores)
-        const int seg_slots = (seg_u1 - seg_u0) * kUnitSlots;
+        // 1. where are this segment's particles?
+        const long long seg_slots = (long long)(seg_u1 - seg_u0) * kUnitSlots;
         if (seg_slots == 0 && seg != a.n_segments - 1) {  // uniform: nothing here (a store much smaller than the grid)
             if (lane == 0) a.counts[r0 + warp] = 0;
-            if (tid == 0) s_seg = next_ticket;
             __syncthreads();
             continue;
         }
-        {
-            int bucket = -1;
-            if (seg_slots > 0) {
-                const float x = __ldg(a.px + (size_t)seg_u0 * kUnitSlots + (size_t)tid * (size_t)(seg_slots >> 10));
-                const bool live = PERIODIC ? (x < g.live_thr) : (x > g.lo_edge && x < g.hi_edge);
-                if (live) {
-                    const float xf = PERIODIC ? fold_periodic(g, x) : x;
-                    const float cf = fminf(fmaxf((xf - g.z_lo) * g.rcp_dz, 0.f), (float)g.last_cell);  // a heuristic: no exact cell needed
-                    bucket = min((int)(cf * inv_bucket_cells), kWinBuckets - 1);
-                }
+        if (seg_slots > 0) {
+            const float x = __ldg(a.px + (size_t)seg_u0 * kUnitSlots + (size_t)((tid * seg_slots) / blockDim.x));
+            const bool live = PERIODIC ? (x < g.live_thr) : (x > g.lo_edge && x < g.hi_edge);
+            if (live) {
+                bool bad = false;
+                const int c = cell_of<PERIODIC, false>(g, PERIODIC ? fold_periodic(g, x) : x, bad);
+                atomicAdd(&s_bucket[c / bucket_cells], 1);
             }
-            // a sorted segment's samples fall into one or two buckets: one atomic per group of equal lanes
-            const unsigned same = __match_any_sync(0xffffffffu, bucket);
-            if (bucket >= 0 && (same & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_bucket[bucket], __popc(same));
         }
         __syncthreads();
-        if (warp == 0) {
-            int best_score = -1, best_b = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int b0 = lane + 32 * h;
-                int score = 0;
-#pragma unroll 4
-                for (int i = 0; i < window_buckets; ++i) {
-                    const int b = b0 + i;  // periodic: circular; walls: buckets past the end hold nothing
-                    const int cnt = PERIODIC ? s_bucket[b & (kWinBuckets - 1)] : (b < kWinBuckets ? s_bucket[b] : 0);
-                    score += cnt * min(i + 1, window_buckets - i);
-                }
-                if (score > best_score) { best_score = score; best_b = b0; }
+        if (tid < kWinBuckets) {
+            int score = 0;
+            for (int i = 0; i < window_buckets; ++i) {
+                const int b = tid + i;  // periodic: circular; walls: buckets past the end hold nothing
+                const int cnt = PERIODIC ? s_bucket[b & (kWinBuckets - 1)] : (b < kWinBuckets ? s_bucket[b] : 0);
+                score += cnt * min(i + 1, window_buckets - i);
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {  // largest score, lowest start among equals (as the serial scan chose)
-                const int os = __shfl_xor_sync(0xffffffffu, best_score, d), ob = __shfl_xor_sync(0xffffffffu, best_b, d);
-                if (os > best_score || (os == best_score && ob < best_b)) { best_score = os; best_b = ob; }
-            }
-            if (lane == 0) {
-                int w_lo = best_b * bucket_cells;
-                if (n_cells <= kWinCells) w_lo = 0;                              // a window as large as the grid starts at cell 0
-                else if (!PERIODIC) w_lo = min(w_lo, n_cells - kWinCells);       // wall windows never reach past the last cell
-                s_w_lo = w_lo;
-            }
+            s_score[tid] = score;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = 0;
+            for (int b = 1; b < kWinBuckets; ++b)
+                if (s_score[b] > s_score[best]) best = b;
+            int w_lo = best * bucket_cells;
+            if (n_cells <= kWinCells) w_lo = 0;                              // a window as large as the grid starts at cell 0
+            else if (!PERIODIC) w_lo = min(w_lo, n_cells - kWinCells);       // wall windows never reach past the last cell
+            s_w_lo = w_lo;
         }
         __syncthreads();
         const WinMap map{s_w_lo, n_cells};
-#if ESPIC_DEBUG_WIN
-        if (a.cta_cycles) t_ph[1] = clock64();
-#endif
 
-        // 2. the window's tables: all loads of a thread in flight at once
-        {
-            float kv[kTableIters];
-#pragma unroll
-            for (int u = 0; u < kTableIters; ++u) {
-                const int j = tid + u * kWinThreads;
-                const int node = map.node_of(j);
-                kv[u] = (j < kWinNodes && (unsigned)node < (unsigned)n_cells) ? __ldg(a.dv_global + node) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < kTableIters; ++u) {
-                const int j = tid + u * kWinThreads;
-                if (j < kWinNodes) {
-                    s_dv[j] = kv[u];
-                    s_lo[j] = 0u;
-                }
-            }
+        // 2. the window's tables
+        for (int j = tid; j < kWinNodes; j += blockDim.x) {
+            const int node = map.node_of(j);
+            s_dv[j] = (node >= 0 && node < n_cells) ? __ldg(a.dv_global + node) : 0.f;
+            s_lo[j] = 0u;
         }
         __syncthreads();
-#if ESPIC_DEBUG_WIN
-        if (a.cta_cycles) t_ph[2] = clock64();
-#endif
 
         // 3. this warp's range
         {
@@ -386,8 +325,8 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
                     Quad p0, p1;
                     load_quad(a, q0, p0);
                     load_quad(a, q1, p1);
-                    const unsigned rem0 = quad_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, jd, limit, ESPIC_DEBUG_WIN && a.cta_cycles ? s_dbg : nullptr);
-                    const unsigned rem1 = quad_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, jd, limit, ESPIC_DEBUG_WIN && a.cta_cycles ? s_dbg : nullptr);
+                    const unsigned rem0 = quad_win<PERIODIC>(a, g, p0, q0, n_slots, kick, s_lo, jd, limit);
+                    const unsigned rem1 = quad_win<PERIODIC>(a, g, p1, q1, n_slots, kick, s_lo, jd, limit);
                     if (!PERIODIC || __any_sync(0xffffffffu, (rem0 | rem1) != 0u)) {
                         stage_removed(rem0, q0, lane, stage_ids, removed);
                         stage_removed(rem1, q1, lane, stage_ids, removed);
@@ -422,47 +361,16 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
                 }
             }
         }
-#if ESPIC_DEBUG_WIN
-        const long long t_mine = a.cta_cycles ? clock64() : 0ll;
         __syncthreads();
-        if (a.cta_cycles) t_ph[3] = clock64();
-#else
-        __syncthreads();
-#endif
 
         // 4. flush
-        {
-            unsigned lo[kTableIters];
-#pragma unroll
-            for (int u = 0; u < kTableIters; ++u) {
-                const int j = tid + u * kWinThreads;
-                lo[u] = j < kWinNodes ? s_lo[j] : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < kTableIters; ++u)
-                if (lo[u]) atomicAdd(a.acc + map.node_of(tid + u * kWinThreads), (unsigned long long)lo[u]);
+        for (int j = tid; j < kWinNodes; j += blockDim.x) {
+            const unsigned lo = s_lo[j];
+            if (lo) atomicAdd(a.acc + map.node_of(j), (unsigned long long)lo);
         }
-        if (tid == 0) s_seg = next_ticket;
         __syncthreads();
-#if ESPIC_DEBUG_WIN
-        if (a.cta_cycles && tid == 0 && seg < 160) {  // development aid: where a segment's time goes
-            long long* d = a.cta_cycles + 160 + 8 * seg;
-            const long long t_end = clock64();
-            d[0] = t_end - t_ph[0];      // whole segment
-            d[1] = t_ph[1] - t_ph[0];    // window search
-            d[2] = t_ph[2] - t_ph[1];    // table build
-            d[3] = t_ph[3] - t_ph[2];    // ranges, until the slowest warp is done
-            d[4] = t_end - t_ph[3];      // flush
-            d[5] = t_mine - t_ph[2];     // warp 0's own range
-            d[6] = map.w_lo;
-            d[7] = ((long long)s_dbg[0] << 40) | ((long long)s_dbg[1] << 20) | (long long)s_dbg[2];  // rare / stray gathers / stray deposits (warp level)
-            s_dbg[0] = s_dbg[1] = s_dbg[2] = 0;
-        }
-#endif
     }
-#if ESPIC_DEBUG_WIN
     if (a.cta_cycles && tid == 0) a.cta_cycles[blockIdx.x] = clock64() - t_entry;
-#endif
 }
 
 // Cells of the window for a grid whose whole-grid tables do not fit (the caller has checked that).  Grids of
@@ -474,10 +382,13 @@ int launch_move_window(espic_ctx* ctx, MoveArgs& a, int periodic) {
     const size_t smem = (size_t)kWinNodes * 8;
     static int segs_per_cta = 0;  // process-wide tuning knob (an environment variable), not device state
     if (!segs_per_cta) {
-        // measured (production-like 65536-cell step, ms): 1 -> 1.193, 2 -> 1.236, 3 -> 1.257, 4 -> 1.280, 6 -> 1.346:
-        // every segment costs a window search, a table build, a flush and a barrier at which the CTA waits for
-        // its slowest warp; one segment per CTA makes the split static, which the equal-sized ranges tolerate
-        segs_per_cta = 1;
+        // measured (production-like 65536-cell step, ms): 1 -> 1.261, 2 -> 1.253, 4 -> 1.272, 8 -> 1.366: every segment
+        // costs a window search, a table build, a flush and a barrier at which the CTA waits for its slowest warp
+        // (~5 us); with one segment per CTA the split is static and the two wall segments set the pace.  Tried and
+        // dropped (A/B builds, same run): table build / flush with all 28 loads of a thread in flight (the arrays go
+        // to local memory at 64 registers: 1.38 vs 1.29 at 4 segments), a one-warp window search with aggregated
+        // histogram atomics (no change), fetching the next ticket ahead (no change)
+        segs_per_cta = 2;
         if (const char* e = getenv("ESPIC_WINDOW_SEGMENTS")) {  // segments per CTA
             const int s = atoi(e);
             if (s >= 1 && s <= 64) segs_per_cta = s;
