@@ -459,7 +459,8 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
         rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,
                          s->charge_to_mass, a->background_density, -1, s->largest_index, s->particles, s->density,
                          s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic_particles, s->largest_allowed_slot,
-                         a->n_points, s->particle_storage_length, 0, 0, 1, acc[i], pushed[i]);
+                         a->n_points, s->particle_storage_length, 0, 0, 1, acc[i], pushed[i],
+                         (a->inject_by_side && !a->periodic_particles) ? 1 : 0);
         if (rc) return rc;
     }
     if (a->hole_position_out) {

@@ -262,7 +262,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage, int minimal = 0,
                 int slot_offset = 0, int finish_density = 1, unsigned long long* acc_fused = nullptr,
-                int* pushed = nullptr);
+                int* pushed = nullptr, int stack_interleave = 0);
 int launch_tridiagonal(espic_ctx* ctx, double* a, double* b, double* c, double* d, double* x, int n);
 int move_window_cells(espic_ctx* ctx, int n_points);  // 0: whole-grid tables fit in shared memory
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);

@@ -298,17 +298,22 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
 // Slot assignment.  The reference pops one stack entry per injected particle, in order: particle l takes entry
 // top-l (by_side == 0: bit-identical slots).  On a store kept sorted by position (large grids, csrc/sort.cu)
 // which of the free slots a new particle takes is physically irrelevant but decides whether it lands in a
-// segment of the store whose shared-memory window covers its wall: the mover pushes the slots it frees in
-// ascending slot order, i.e. left-wall leavers below right-wall leavers, so with by_side != 0 the particles that
-// enter at the left wall take the entries of the consumed range [top-n+1, top] from the bottom up and those that
-// enter at the right wall take them from the top down -- the same entries, each used once, deterministically
-// (ranks from a scan, no atomics).  Half of all injected electrons would otherwise sit 65536 cells away from
-// their segment until the next sort and be served from global memory.
+// segment of the store whose shared-memory window covers its wall.  With by_side != 0 the mover's k_scatter has
+// put the slots it freed this step on the stack alternately from the two ends of their ascending order, outermost
+// on top (highest slot, lowest slot, second highest, ...): particles that enter at the right wall take the
+// entries at even distance from the top, those that enter at the left wall the entries at odd distance -- the
+// slots next to their own wall -- and when more particles left than enter, what stays on the stack are the
+// innermost freed slots of both wall regions.  The same top n entries the reference would pop, each used once,
+// deterministically (ranks from a scan, no atomics).  Without this half of all injected electrons sat 65536
+// cells away from their segment until the next sort and were served from global memory; with a one-sided
+// assignment (left from the bottom of the popped range, right from the top) a shortfall of left-wall slots
+// -- (removed - injected)/2 per step while the population falls -- still put left-wall entrants into
+// right-wall slots, and the two segments that collected them ran 6x longer than the others.
 __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
     __shared__ unsigned s_wall[2 * kWallNodes];
     __shared__ int s_last;
-    __shared__ int s_scan[8];
-    __shared__ int s_base_left;
+    __shared__ int s_scan[8], s_scan2[8];
+    __shared__ int s_base_left, s_total_left;
     const Geom g = make_geom(a.grid, a.n_points);
     const int top0 = *a.top;
     const int n_bad = a.ws[0];
@@ -322,23 +327,45 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
         const int n_rounds = (a.n_inject + 255) / 256;
         const int per_cta = (n_rounds + (int)gridDim.x - 1) / (int)gridDim.x;
         const int r0 = min((int)blockIdx.x * per_cta, n_rounds), r1 = min(r0 + per_cta, n_rounds);
-        int base_left = 0;
-        if (a.by_side && r0 < r1) {  // particles entering at the left wall in front of this CTA's first round
-            int part = 0;
-            for (int c = threadIdx.x; c < 2 * r0; c += blockDim.x) part += a.left_count[c];  // two sampler chunks per round
+        int base_left = 0, total_left = 0;
+        if (a.by_side && r0 < r1) {
+            // particles entering at the left wall in front of this CTA's first round, and in all (two sampler chunks per round)
+            int part = 0, all = 0;
+            for (int c = threadIdx.x; c < 2 * n_rounds; c += blockDim.x) {
+                const int v = (c * kSampleThreads < a.n_inject) ? a.left_count[c] : 0;
+                all += v;
+                part += c < 2 * r0 ? v : 0;
+            }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-            if ((threadIdx.x & 31) == 0) s_scan[threadIdx.x >> 5] = part;
+            for (int d = 16; d > 0; d >>= 1) {
+                part += __shfl_xor_sync(0xffffffffu, part, d);
+                all += __shfl_xor_sync(0xffffffffu, all, d);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                s_scan[threadIdx.x >> 5] = part;
+                s_scan2[threadIdx.x >> 5] = all;
+            }
             __syncthreads();
             if (threadIdx.x == 0) {
-                int t = 0;
-                for (int w = 0; w < 8; ++w) t += s_scan[w];
+                int t = 0, u = 0;
+                for (int w = 0; w < 8; ++w) {
+                    t += s_scan[w];
+                    u += s_scan2[w];
+                }
                 s_base_left = t;
+                s_total_left = u;
             }
             __syncthreads();
             base_left = s_base_left;
+            total_left = s_total_left;
             __syncthreads();
         }
+        // by side: the mover's k_scatter left the freed slots on the stack alternately from the two ends of their
+        // ascending order, outermost on top (mover.cu, interleave): entrants at the right wall take the entries at even
+        // distance from the top, entrants at the left wall those at odd distance, as long as both sides have
+        // entrants left (m of each); the surplus of the larger side continues below.  Exactly the top n_inject
+        // entries are consumed, each once.
+        const int m_pairs = min(total_left, a.n_inject - total_left);
         for (int r = r0; r < r1; ++r) {
             const int l = r * 256 + (int)threadIdx.x;
             const bool have = l < a.n_inject;
@@ -357,8 +384,9 @@ __global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
                     round_left += s_scan[ww];
                 }
                 const int rank_left = base_left + before + __popc(lanes & ((1u << lane) - 1u));
-                const int rank_right = l - rank_left;  // particles in front of l that enter at the right wall
-                sp = left ? top0 - a.n_inject + 1 + rank_left : top0 - rank_right;
+                const int rank = left ? rank_left : l - rank_left;  // rank among the entrants of its own wall
+                const int t = rank < m_pairs ? 2 * rank + (left ? 1 : 0) : m_pairs + rank;  // distance from the top
+                sp = top0 - t;
                 base_left += round_left;
                 __syncthreads();
             }

@@ -406,14 +406,22 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging
                                                  const int* __restrict__ hdr, int* __restrict__ empty_slots,
                                                  int largest_allowed_slot, const int* largest_index_dev,
                                                  int largest_index, int mover_warps, int* strided_counts,
-                                                 int slot_offset) {
+                                                 int slot_offset, int interleave) {
     const int total = hdr[1];
     if (total == 0) return;
     const int old_top = hdr[0], n_chunks = hdr[2];
     const int n_slots = (largest_index_dev ? *largest_index_dev : largest_index) + 1;
     const Split split(n_slots, mover_warps);
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < total; d += stride) {
+        // Which staged id goes to stack position old_top+1+d.  The reference's order is ascending slot order
+        // (i = d).  interleave (stores kept sorted by position, together with the by-side injection of
+        // inject.cu): the ids are taken alternately from the two ends of the ascending list, outermost on top --
+        // top: highest slot, below it: lowest slot, then second highest, second lowest ... -- so that the next
+        // injection, which pops from the top, gets the slots next to either wall first and what is left over
+        // (more particles left than entered) are the innermost slots of both wall regions, at the bottom.
+        const int t = total - 1 - d;  // distance from the new top
+        const int i = !interleave ? d : ((t & 1) ? (t >> 1) : total - 1 - (t >> 1));
         // last range c with offsets[c] <= i (ranges without removals share their successor's offset)
         int lo = 0, hi = n_chunks - 1;
         while (lo < hi) {
@@ -425,7 +433,7 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging
         const int* src = strided_counts
                              ? staging + (size_t)c * kUnitSlots
                              : staging + (size_t)(c < mover_warps ? split.first_unit(c) : split.n_units) * kUnitSlots;
-        const int dst = old_top + 1 + i;
+        const int dst = old_top + 1 + d;
         if (dst >= 0 && dst <= largest_allowed_slot) empty_slots[dst] = src[i - __ldg(offsets + c)] + slot_offset;
     }
     // per-unit counts are only ever written when non-zero: leave them zeroed for the next launch
@@ -515,7 +523,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage, int minimal, int slot_offset,
-                int finish_density, unsigned long long* acc_fused, int* pushed) {
+                int finish_density, unsigned long long* acc_fused, int* pushed, int stack_interleave) {
     // acc_fused (the step path, espic_pic_step): the deposit is ADDED to these caller-owned fixed-point
     // accumulators and left there -- the next field solve converts it -- and `density` is not touched.
     // slot_offset / finish_density: the call covers slots [slot_offset, slot_offset + largest_index] of the
@@ -671,7 +679,8 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     ESPIC_CUDA(ctx, cudaGetLastError());
     k_scatter<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(a.staging, offsets, f.scatter_hdr, empty_slots,
                                                       largest_allowed_slot, largest_index_dev, largest_index,
-                                                      mover_warps, a.strided ? a.counts : nullptr, slot_offset);
+                                                      mover_warps, a.strided ? a.counts : nullptr, slot_offset,
+                                                      stack_interleave);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "mover epilogue launch");
 }

@@ -227,11 +227,13 @@ typedef struct {
     float inject_dt;                     /* the driver's dt (partial-step placement), independent of a frozen species */
     int step_index;                      /* k: written into the injection tags */
     int inject_by_side;                  /* 0: particle l takes stack entry top-l, the reference's pop order (ref
-                                          * infMagSim_cython.py:254-257, 282-283).  1 (stores kept sorted by position):
-                                          * the same n entries, but particles entering at the left wall take them
-                                          * from the bottom up and those entering at the right wall from the top down
-                                          * (the mover pushes freed slots in ascending slot order), so a new particle
-                                          * lands among its neighbours in the store.  Physically invisible. */
+                                          * infMagSim_cython.py:254-257, 282-283).  1 (stores kept sorted by position,
+                                          * wall-bounded runs): the movers of this step push the slots they free
+                                          * alternately from the two ends of their ascending order, outermost on top,
+                                          * and the injection gives entrants at the right / left wall the entries at
+                                          * even / odd distance from the top -- the same top n entries, each used once,
+                                          * so a new particle lands among its neighbours in the store.  Slot numbers
+                                          * only: physically invisible. */
     int *ion_tags;                       /* int[storage] injection histories; may be NULL when nothing is injected */
     int *electron_tags;
     float *density_snapshot;             /* NULL, or float[2][n_points]: the reduced, end-fixed ion and electron
