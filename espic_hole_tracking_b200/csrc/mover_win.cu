@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
         const int ticket = s_seg;
         if (ticket >= a.n_segments) break;
         const int seg = (ticket & 1) ? a.n_segments - 1 - (ticket >> 1) : (ticket >> 1);
+        const long long t_seg = a.cta_cycles ? clock64() : 0ll;
         const int r0 = seg * warps_per_cta;
         const int seg_u0 = split.first_unit(r0), seg_u1 = split.first_unit(r0 + warps_per_cta);
 
@@ -369,8 +370,10 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
             if (lo) atomicAdd(a.acc + map.node_of(j), (unsigned long long)lo);
         }
         __syncthreads();
+        // development aid (ESPIC_DEBUG_CTA=1): cycles per segment, ions in [512, 1024), electrons in [0, 512)
+        if (a.cta_cycles && tid == 0 && seg < 512) a.cta_cycles[(a.qm > 0.f ? 512 : 0) + seg] = clock64() - t_seg;
     }
-    if (a.cta_cycles && tid == 0) a.cta_cycles[blockIdx.x] = clock64() - t_entry;
+    if (a.cta_cycles && tid == 0) a.cta_cycles[1024 + blockIdx.x] = clock64() - t_entry;
 }
 
 // Cells of the window for a grid whose whole-grid tables do not fit (the caller has checked that).  Grids of

@@ -11,15 +11,13 @@ buf = (C.c_longlong * 2048)()
 def cycles():
     k = sim.ctx._lib.espic_debug_cta_cycles(sim.ctx.handle, buf, 2048)
     return np.array(buf[:k], dtype=np.int64)
+nseg = 148 * int(os.environ.get("ESPIC_WINDOW_SEGMENTS", "2"))
 for k in range(int(os.environ.get("PROBE_STEPS", "60"))):
     sim.step()
     if k in (5, 20, 27, 33, 47, 55):
-        # the last windowed launch of a step is the electron mover; run the ions alone once more to see them
         raw = cycles()
-        e = raw[:148]
-        seg = raw[160:160 + 8 * 148].reshape(148, 8)
-        slow = np.argsort(-seg[:, 0])[:4]
-        for sidx in list(slow) + [60]:
-            print(f"   segment {sidx}: total {seg[sidx,0]} search {seg[sidx,1]} build {seg[sidx,2]} ranges {seg[sidx,3]} (warp0 {seg[sidx,5]}) flush {seg[sidx,4]} w_lo {seg[sidx,6]} rare {seg[sidx,7] >> 40} stray-gather {(seg[sidx,7] >> 20) & 0xfffff} stray-deposit {seg[sidx,7] & 0xfffff} warp-quads {2 * 676000 // 128}")
-        order = np.argsort(-e)
-        print(f"step {k} electrons: min {e.min()} median {int(np.median(e))} max {e.max()}  slowest CTAs {order[:6].tolist()} -> {e[order[:6]].tolist()}", flush=True)
+        for name, off in (("electrons", 0), ("ions", 512)):
+            e = raw[off:off + min(nseg, 512)]
+            order = np.argsort(-e)
+            print(f"step {k} {name}: per-segment cycles min {e.min()} median {int(np.median(e))} max {e.max()} sum/148 {int(e.sum() / 148)}  "
+                  f"slowest segments {order[:8].tolist()} -> {e[order[:8]].tolist()}", flush=True)
