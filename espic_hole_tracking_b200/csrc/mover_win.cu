@@ -40,7 +40,10 @@ namespace espic {
 constexpr int kWinCells = 27648;
 constexpr int kWinNodes = kWinCells + 2;  // both nodes of every cell, plus one when the window wraps past the seam
 constexpr int kWinBuckets = 64;
-constexpr int kWinThreads = 1024;
+#ifndef ESPIC_WIN_BOUNDS
+#define ESPIC_WIN_BOUNDS 1024   // CTA width of k_move_win (build switch for A/B runs)
+#endif
+constexpr int kWinThreads = ESPIC_WIN_BOUNDS;
 
 // cell -> index into the window tables.  Cells at or above w_lo map to cell - w_lo; cells that
 // wrapped (below w_lo) map one further so that node n_cells (right end) and node 0 (left end)
