@@ -41,7 +41,8 @@ constexpr int kWinCells = 27648;
 constexpr int kWinNodes = kWinCells + 2;  // both nodes of every cell, plus one when the window wraps past the seam
 constexpr int kWinBuckets = 64;
 #ifndef ESPIC_WIN_BOUNDS
-#define ESPIC_WIN_BOUNDS 1024   // CTA width of k_move_win (build switch for A/B runs)
+#define ESPIC_WIN_BOUNDS 896    // CTA width of k_move_win: 28 warps at 72 registers (production-like 65536-cell step, ms:
+                                // 768 -> 1.142, 896 -> 1.138, 1024 -> 1.146)
 #endif
 constexpr int kWinThreads = ESPIC_WIN_BOUNDS;
 
