@@ -377,13 +377,13 @@ def configs3_leg(n, device, peak, peak_src):
 
     from espic_hole_tracking_b200.simulation import SimConfig, Simulation
     cells = 65536
-    cfg = SimConfig(n_steps=400, n_particles=n, n_cells=cells, periodic_particles=False, extra_storage_factor=1.1,
+    cfg = SimConfig(n_steps=600, n_particles=n, n_cells=cells, periodic_particles=False, extra_storage_factor=1.1,
                     track_hole=True, initial_transient_steps=0, create_electron_dimple=True)
     sim = Simulation(cfg, device=device)
     sim.init_synthetic()
     sim.initialize()
     k_e = max(int(sim.sort_intervals["electrons"]), 1)
-    warm = 8
+    warm = 100   # past the first, most violent part of the dimple's start-up transient
     steps = max(2 * k_e, 40)
     # start the timed region right after an electron sort so that it holds whole intervals
     while (sim.k + warm) % k_e != 0:

@@ -757,8 +757,6 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
         team_sync(tm);  // the cluster barrier releases / acquires the global writes above
     }
 
-    if (tm.T == 0 && a.fix.pushed[0] && (__ldcg(a.fix.pushed[0]) | __ldcg(a.fix.pushed[1]))) fix_stack_order(a.fix);
-
     // ---- fused driver prologue: end-node fix + charge density (ref infMagSim_script.py:763-779, 807)
     const RowConsts k = row_consts(a);
     const bool cacheable = (a.transparency == 1.f) && !a.boltzmann;
@@ -885,6 +883,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
             if (j < n) a.potential[j] = (float)r;
         }
     }
+    // stacks whose newest entries the periodic movers pushed in arrival order (practically never): put them in the
+    // reference's ascending order; checked last, off the critical path of the solve
+    if (tm.T == 0 && a.fix.pushed[0] && (__ldcg(a.fix.pushed[0]) | __ldcg(a.fix.pushed[1]))) fix_stack_order(a.fix);
     if (timed_out) {  // exchange timeout: every barrier above was still taken; the result is withdrawn
         for (int i = 0; i < m; ++i) {
             const int j = tm.T * m + i;
