@@ -440,11 +440,20 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
                                          a->potential, a->object_potential, a->object_transparency, 0,
                                          a->periodic_potential, a->n_points, acc[0] ? &fix : nullptr);
     } else {
+        unsigned long long* pend[2] = {a->ion_acc_pending ? acc[0] : nullptr, a->electron_acc_pending ? acc[1] : nullptr};
+        if (a->n_points > 8192) {
+            // beyond 8192 points the solve walks several rows per thread on 8 CTAs; converting 2 x n_points
+            // accumulators there costs more (65537 points: 37 -> 59 us) than two wide launches in front of it
+            for (int i = 0; i < 2; ++i)
+                if (pend[i]) {
+                    if ((rc = launch_convert_density(ctx, pend[i], sp[i]->density, a->n_points, a->background_density))) return rc;
+                    pend[i] = nullptr;
+                }
+        }
         rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
                                 a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,
                                 a->object_potential, a->object_transparency, 0, a->periodic_potential, a->n_points,
-                                a->ion_acc_pending ? acc[0] : nullptr, a->electron_acc_pending ? acc[1] : nullptr,
-                                a->background_density, acc[0] ? &fix : nullptr);
+                                pend[0], pend[1], a->background_density, acc[0] ? &fix : nullptr);
     }
     if (rc) return rc;
     if (a->density_snapshot) {  // the densities the solve used, before the pushes overwrite them
@@ -612,7 +621,9 @@ static int g_n_pinned = 0;
 // replaced by a larger one with headroom, never extended piecemeal -- a copy must not straddle
 // registered and unregistered pages.
 static void pin_host_range(const void* ptr, size_t bytes, size_t capacity) {
-    if (!ptr || bytes < (8u << 20)) return;  // small arrays are not worth a registration
+    size_t min_bytes = 8u << 20;  // small arrays are not worth a registration
+    if (const char* e = getenv("ESPIC_PIN_MIN_BYTES")) min_bytes = (size_t)atoll(e);  // test knob
+    if (!ptr || bytes < min_bytes) return;
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("ESPIC_PIN_HOST");
@@ -637,6 +648,12 @@ static void pin_host_range(const void* ptr, size_t bytes, size_t capacity) {
     } else {
         cudaGetLastError();  // leave it pageable
     }
+}
+
+static bool is_pinned(const void* ptr, size_t bytes) {
+    for (int i = 0; i < g_n_pinned; ++i)
+        if (g_pinned[i].ptr == ptr && g_pinned[i].bytes >= bytes) return true;
+    return false;
 }
 
 static void unpin_all() {
@@ -729,6 +746,23 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
         }
     }
     bounds.push_back(used);
+    // Zero-copy mode (ESPIC_HOST_MODE=zerocopy; the default is the chunked pipeline): the mover reads and writes the
+    // caller's page-locked rows directly over PCIe -- loads and stores of all resident warps keep both directions
+    // of the link busy with no fill/drain bubble and no staging copy.  Needs both rows registered (they are, unless
+    // registration failed or the store is small) and a device that can use host pointers of registered memory.
+    bool zero_copy = false;
+    {
+        const char* mode = getenv("ESPIC_HOST_MODE");
+        int can = 0;
+        if (mode && !strcmp(mode, "zerocopy") && used >= 1024 && !minimal &&
+            cudaDeviceGetAttribute(&can, cudaDevAttrCanUseHostPointerForRegisteredMem, ctx->device) == cudaSuccess && can)
+            zero_copy = is_pinned(particles, used * sizeof(float)) && is_pinned(particles + S, used * sizeof(float));
+    }
+    if (zero_copy) {
+        bounds.clear();
+        bounds.push_back(0);
+        bounds.push_back(used);
+    }
     const size_t n_chunks = bounds.size() - 1;
     const bool pipelined = n_chunks > 1;
     cudaStream_t s_up = ctx->stream, s_run = ctx->stream, s_down = ctx->stream;
@@ -769,7 +803,7 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
     for (size_t c = 0; c < n_chunks; ++c) {
         const size_t off = bounds[c];
         const size_t len = bounds[c + 1] - bounds[c];
-        if (len) {
+        if (len && !zero_copy) {
             COPY(d_part + off, particles + off, len, float, cudaMemcpyHostToDevice, s_up);
             COPY(d_part + S + off, particles + S + off, len, float, cudaMemcpyHostToDevice, s_up);
         }
@@ -778,7 +812,7 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
             cudaStreamWaitEvent(s_run, ctx->pipe_ev[2 * c], 0);
         }
         rc = launch_move(ctx, d_grid, d_mask, d_phi, dt, charge_to_mass, background_density, (int)len - 1, nullptr,
-                         d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles,
+                         zero_copy ? particles : d_part, d_den, d_stack, d_top, a_b, update_position, periodic_particles,
                          largest_allowed_slot, n_points, particle_storage_length, minimal, (int)off,
                          c + 1 == n_chunks ? 1 : 0);
         if (rc) {
@@ -789,7 +823,7 @@ static void move_host_arrays(const char* who, float* grid, float* object_mask, f
             cudaEventRecord(ctx->pipe_ev[2 * c + 1], s_run);
             cudaStreamWaitEvent(s_down, ctx->pipe_ev[2 * c + 1], 0);
         }
-        if (len) {
+        if (len && !zero_copy) {
             COPY(particles + off, d_part + off, len, float, cudaMemcpyDeviceToHost, s_down);
             COPY(particles + S + off, d_part + S + off, len, float, cudaMemcpyDeviceToHost, s_down);
         }

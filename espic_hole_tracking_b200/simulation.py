@@ -203,10 +203,7 @@ class Simulation:
         # caller-owned planes of fixed-point accumulators; the next field solve (or, multi-GPU, the publication
         # of the exchange slot) converts it.  No conversion pass and no epilogue launch on the step path.
         # Not with exchange="nccl": torch's all-reduce needs the float rows.
-        # Not on grids beyond 8192 points either: there the solve walks several rows per thread on 8 CTAs and the
-        # conversion of 2 x n_points accumulators costs it more (65537 points: 37 -> 59 us) than the multi-CTA
-        # conversion in the movers' epilogue kernels, which wall-bounded large-grid steps launch anyway.
-        self.fused_deposit = self.exchange_mode in ("none", "p2p") and n_points <= 8192
+        self.fused_deposit = self.exchange_mode in ("none", "p2p")
         self.acc = torch.zeros((2, (n_points + 64) & ~63), dtype=torch.int64, device=self.device)   # >= n_points + 1
         self._acc_pending = [False, False]
         # what the reference driver stores per step (:906-910) are the reduced, end-fixed densities the solve used.

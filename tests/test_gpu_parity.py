@@ -615,16 +615,20 @@ def test_hole_tracking_argmax_at_baseline_grids(ops, cpu, n_points, kind):
         assert abs(exact[i_gpu] - exact[i_ref]) <= noise_ref, (exact[i_gpu], exact[i_ref], noise_ref)
 
 
-@pytest.mark.parametrize("chunk_slots", [0, 4096])
+@pytest.mark.parametrize("chunk_slots", [0, 4096, -1])
 def test_host_pointer_dropins(ops, cpu, chunk_slots, monkeypatch):
     """The reference-named symbols with HOST arrays (what a relinked Cython extension calls).  With
     ESPIC_HOST_CHUNK=4096 the 20 000-slot store crosses the device in 5 pipelined chunks (upload / push /
-    download on three streams), each with removals: particle state, stack order and top must not change."""
+    download on three streams), each with removals: particle state, stack order and top must not change.
+    chunk_slots = -1: the zero-copy mode (the kernel works on the caller's page-locked rows over PCIe)."""
     import ctypes as C
     from espic_hole_tracking_b200._lib import lib
     L = lib()
-    if chunk_slots:
+    if chunk_slots > 0:
         monkeypatch.setenv("ESPIC_HOST_CHUNK", str(chunk_slots))
+    if chunk_slots < 0:
+        monkeypatch.setenv("ESPIC_HOST_MODE", "zerocopy")
+        monkeypatch.setenv("ESPIC_PIN_MIN_BYTES", "1024")
     n_cells = 512
     grid = wl.make_grid(n_cells)
     mask = np.zeros_like(grid)
@@ -645,8 +649,9 @@ def test_host_pointer_dropins(ops, cpu, chunk_slots, monkeypatch):
     np.testing.assert_allclose(d_h, d_ref, rtol=0, atol=2e-6 * d_ref.max())
     removed = c.empty_slots[sp.current_empty_slot[0] + 1:top.value + 1]
     assert len(removed) > 50 and np.all(np.diff(removed) > 0)          # ascending slot order, as the reference pushes
-    if chunk_slots:
+    if chunk_slots > 0:
         assert len(np.unique(removed // chunk_slots)) >= 3            # removals in at least three chunks
+    L.espic_host_release()
     charge = (d_ref - d_ref.mean()).astype(np.float32)
     p_ref, p_h = np.zeros_like(grid), np.zeros_like(grid)
     cpu.poisson_solve(grid, mask, charge, 0.125, p_ref)
