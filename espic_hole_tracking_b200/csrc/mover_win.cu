@@ -25,6 +25,13 @@
 // particle; an all-or-nothing variant (a warp with one stray takes an out-of-line general path) lost more
 // than it gained: one stray in 128 slots is the rule late in a sort interval.
 //
+// Tried and dropped (A/B builds on the production-like 65536-cell run, 1e8 + 1e8, ms per step against 1.13):
+// kick table left in global memory (L1/L2 gathers) with the whole shared memory as a 55296-cell deposit plane
+// -- no stray for 58 steps, but 1.80 (28-step sort interval) to 1.89 (58): the gather sits in the dependency
+// chain of every slot; a no-wrap instantiation of the mapping next to the general one (1.43: the duplicated
+// loop costs more in instruction fetch than it saves); an all-or-nothing slow path per warp (one stray in 128
+// slots is the rule late in a sort interval); 1024-thread CTAs at 64 registers (1.15).
+//
 // After espic_sort_particles_coarse() a segment's particles sit within a few hundred cells of each
 // other and drift apart by |v| dt per step; the window leaves ~13700 cells of margin either side,
 // so nearly all slots stay on the shared-memory path for many steps.  Because the deposit accumulates
