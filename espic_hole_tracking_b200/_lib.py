@@ -45,6 +45,13 @@ class StepArgs(C.Structure):
                 ("tracking_width", c_float)]
 
 
+class RunArgs(C.Structure):
+    """espic_run_args of include/espic_b200.h."""
+    _fields_ = [("n_steps", c_int), ("first_step", c_int), ("n_inject_ions", c_void_p),
+                ("n_inject_electrons", c_void_p), ("hole_positions", c_void_p), ("track_from", c_int),
+                ("track_until", c_int), ("use_graph", c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/espic_b200.h one to one
 SIGNATURES = {
     "espic_abi_version": (c_int, []),
@@ -80,6 +87,7 @@ SIGNATURES = {
     "espic_field_solve_exchange": (c_int, [c_void_p, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, c_float, P,
                                            c_float, c_float, c_int, c_int, c_int]),
     "espic_pic_step": (c_int, [c_void_p, C.POINTER(StepArgs)]),
+    "espic_pic_run": (c_int, [c_void_p, C.POINTER(StepArgs), C.POINTER(RunArgs)]),
     "espic_inject_particles": (c_int, [c_void_p, c_int, P, c_int, c_float, c_float, P, P, c_float, c_int,
                                        P, P, c_int, P, P, P, P]),
     "espic_seed": (c_int, [c_void_p, C.c_ulong]),

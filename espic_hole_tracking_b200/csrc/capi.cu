@@ -38,6 +38,7 @@ int ensure(espic_ctx* ctx, Scratch& s, size_t bytes, const char* what) {
         s.bytes = 0;
     }
     size_t want = bytes + bytes / 8 + 256;
+    ctx->scratch_epoch++;
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
@@ -64,6 +65,7 @@ int ensure_acc(espic_ctx* ctx, int n_points) {
         ctx->acc_len = 0;
     }
     const int len = n_points + 64;
+    ctx->scratch_epoch++;
     cudaError_t e = cudaMalloc((void**)&ctx->acc, (size_t)len * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -158,6 +160,9 @@ void espic_destroy(espic_ctx* ctx) {
     free_scratch(ctx->host_stage);
     free_scratch(ctx->filter_ws);
     free_scratch(ctx->debug_ws);
+    for (auto& g : ctx->step_graph)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
     for (int r = 0; r < ctx->xch.world; ++r)
         if (r != ctx->xch.rank && ctx->xch.peer[r]) cudaIpcCloseMemHandle(ctx->xch.peer[r]);
     if (ctx->xch.local) cudaFree(ctx->xch.local);
@@ -405,9 +410,8 @@ int espic_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float
                                        periodic_potential, n_points);
 }
 
-int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
-    DeviceGuard guard(ctx);
-    if (!ctx || !a) return ESPIC_E_ARG;
+// One timestep on ctx->stream.  track_cursor: device int indexing hole_position_out (step graphs), or null.
+static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cursor) {
     if (!a->grid || !a->object_mask || !a->potential || !a->charge) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null grid pointer");
     const espic_species* sp[2] = {&a->ions, &a->electrons};
     for (int i = 0; i < 2; ++i)
@@ -475,7 +479,7 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
     if (a->hole_position_out) {
         if (!a->fine_mesh || !a->filter_scratch) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: tracking buffers missing");
         rc = launch_hole_position(ctx, a->n_points, a->grid, a->potential, a->tracking_dz, a->tracking_width,
-                                  a->n_fine, a->fine_mesh, a->filter_scratch, a->hole_position_out);
+                                  a->n_fine, a->fine_mesh, a->filter_scratch, a->hole_position_out, track_cursor);
         if (rc) return rc;
     }
     const int n_inj[2] = {a->n_inject_ions, a->n_inject_electrons};
@@ -498,6 +502,112 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
                            a->step_index, tags[i], s->particles, s->particle_storage_length, s->empty_slots,
                            s->current_empty_slot, s->largest_index, s->density, true, acc[i], a->inject_by_side);
         if (rc) return rc;
+    }
+    return ESPIC_OK;
+}
+
+int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
+    DeviceGuard guard(ctx);
+    if (!ctx || !a) return ESPIC_E_ARG;
+    return pic_step_impl(ctx, a, nullptr);
+}
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+static void drop_step_graph(espic_ctx::StepGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+}
+
+// Captures one step with the given arguments on the side stream (nothing executes) and instantiates it.
+static int capture_step(espic_ctx* ctx, const espic_step_args* a, int which) {
+    espic_ctx::StepGraph& g = ctx->step_graph[which];
+    drop_step_graph(g);
+    if (!ctx->capture_stream)
+        ESPIC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t user = ctx->stream;
+    const long long before = ctx->launches;
+    const unsigned long long epoch = ctx->scratch_epoch;
+    ESPIC_CUDA(ctx, cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal));
+    ctx->stream = ctx->capture_stream;
+    int rc = pic_step_impl(ctx, a, which ? ctx->status + 12 : nullptr);
+    ctx->stream = user;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->capture_stream, &graph);
+    const int n_launch = (int)(ctx->launches - before);
+    ctx->launches = before;   // nothing ran
+    if (rc || e != cudaSuccess || !graph || ctx->scratch_epoch != epoch) {
+        // a buffer grew while capturing (the graph may hold the old pointer) or the step refused its arguments
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc ? rc : fail(ctx, ESPIC_E_CUDA, "espic_pic_run: capturing the step failed (%s)",
+                              e != cudaSuccess ? cudaGetErrorString(e) : "scratch reallocated");
+    }
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        g.exec = nullptr;
+        return check_cuda(ctx, e, "cudaGraphInstantiate");
+    }
+    memcpy(&g.key, a, sizeof *a);
+    g.epoch = epoch;
+    g.launches = n_launch;
+    return ESPIC_OK;
+}
+
+int espic_pic_run(espic_ctx* ctx, const espic_step_args* first, const espic_run_args* r) {
+    DeviceGuard guard(ctx);
+    if (!ctx || !first || !r) return ESPIC_E_ARG;
+    if (r->n_steps < 0) return fail(ctx, ESPIC_E_ARG, "espic_pic_run: negative step count");
+    if (first->exchange_parity >= 0)
+        return fail(ctx, ESPIC_E_ARG, "espic_pic_run: single-rank stepping only (the density exchange publishes between steps)");
+    const bool fused = first->ions.acc != nullptr;
+    int warmed[2] = {0, 0};
+    bool graphs = r->use_graph != 0 && !ctx->timing_on;
+    for (int i = 0; i < r->n_steps; ++i) {
+        const int k = r->first_step + i;
+        espic_step_args a;
+        memcpy(&a, first, sizeof a);
+        a.step_index = k;
+        a.n_inject_ions = r->n_inject_ions ? r->n_inject_ions[i] : 0;
+        a.n_inject_electrons = r->n_inject_electrons ? r->n_inject_electrons[i] : 0;
+        if (i > 0 && fused) a.ion_acc_pending = a.electron_acc_pending = 1;   // every step leaves its deposit pending
+        const bool track = r->hole_positions && k >= r->track_from && k < r->track_until;
+        a.hole_position_out = track ? r->hole_positions + k : nullptr;
+        const bool graphable = graphs && a.n_inject_ions <= 0 && a.n_inject_electrons <= 0;
+        int rc;
+        if (!graphable) {
+            if ((rc = pic_step_impl(ctx, &a, nullptr))) return rc;
+            continue;
+        }
+        // the replayed graph indexes the history through the device cursor; nothing else varies from step to step
+        a.step_index = 0;
+        a.hole_position_out = track ? r->hole_positions : nullptr;
+        espic_ctx::StepGraph& g = ctx->step_graph[track ? 1 : 0];
+        if (!g.exec || g.epoch != ctx->scratch_epoch || memcmp(&g.key, &a, sizeof a) != 0) {
+            espic_step_args plain;
+            memcpy(&plain, &a, sizeof a);
+            plain.step_index = k;
+            plain.hole_position_out = track ? r->hole_positions + k : nullptr;
+            if (!warmed[track]) {
+                // first an ordinary step: it sizes the scratch buffers and the per-kernel launch configuration
+                if ((rc = pic_step_impl(ctx, &plain, nullptr))) return rc;
+                warmed[track] = 1;
+                continue;
+            }
+            if (capture_step(ctx, &a, track ? 1 : 0)) {   // not capturable here: carry on launch by launch
+                graphs = false;
+                if ((rc = pic_step_impl(ctx, &plain, nullptr))) return rc;
+                continue;
+            }
+        }
+        if (track && ctx->track_cursor_host != k) {
+            k_set_int<<<1, 1, 0, ctx->stream>>>(ctx->status + 12, k);
+            ctx->launches++;
+        }
+        ESPIC_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->launches += g.launches;
+        if (track) ctx->track_cursor_host = k + 1;
     }
     return ESPIC_OK;
 }

@@ -120,7 +120,8 @@ constexpr int kFilterThreads = 256;
 // takes fine[argmax(Res)] (ref infMagSim_script.py:750-753).
 __global__ void __launch_bounds__(kFilterThreads) k_filter_eval(int n_blocks, FilterMoments mo, double inv_L, int n_fine,
                                                                 const float* __restrict__ fine, float* res,
-                                                                float* __restrict__ pos_out, unsigned* ticket) {
+                                                                float* __restrict__ pos_out, unsigned* ticket,
+                                                                int* cursor) {
     __shared__ double s_red[kFilterFine][kFilterThreads / 32];
     __shared__ int s_last;
     for (int i0 = blockIdx.x * kFilterFine; i0 < n_fine; i0 += gridDim.x * kFilterFine) {
@@ -164,8 +165,14 @@ __global__ void __launch_bounds__(kFilterThreads) k_filter_eval(int n_blocks, Fi
         __syncthreads();
         if (s_last) {
             __threadfence();
-            argmax_position(n_fine, res, fine, pos_out);
-            if (threadIdx.x == 0) *ticket = 0u;
+            // replayed step graphs (espic_pic_run) cannot carry a per-step pointer: they index pos_out by a
+            // device cursor, advanced here
+            const int at = cursor ? *cursor : 0;
+            argmax_position(n_fine, res, fine, pos_out + at);
+            if (threadIdx.x == 0) {
+                *ticket = 0u;
+                if (cursor) *cursor = at + 1;
+            }
         }
     }
 }
@@ -210,7 +217,7 @@ static int filter_group(const float* grid_ends, int n_points, float L) {
 
 template <bool GRADIENT>
 static int run_filter(espic_ctx* ctx, int n_points, const float* grid, const float* data, float div_mid, float div_end,
-                      float L, int n_fine, const float* fine, float* res, float* pos_out) {
+                      float L, int n_fine, const float* fine, float* res, float* pos_out, int* cursor = nullptr) {
     // the end points of the grid decide the block size; they never change in a run, so they are fetched once
     // per (grid pointer, n_points) and cached in the context
     if (ctx->filter_grid != grid || ctx->filter_n != n_points) {
@@ -237,7 +244,7 @@ static int run_filter(espic_ctx* ctx, int n_points, const float* grid, const flo
                                                           ctx->status);
     const int chunks = (n_fine + kFilterFine - 1) / kFilterFine;
     k_filter_eval<<<chunks < 2 * ctx->sm_count ? chunks : 2 * ctx->sm_count, kFilterThreads, 0, ctx->stream>>>(
-        n_blocks, mo, inv_L, n_fine, fine, res, pos_out, (unsigned*)(ctx->status + 9));
+        n_blocks, mo, inv_L, n_fine, fine, res, pos_out, (unsigned*)(ctx->status + 9), cursor);
     ctx->launches += 2;
     return check_cuda(ctx, cudaGetLastError(), "field filter launch");
 }
@@ -249,10 +256,10 @@ int launch_field_filter(espic_ctx* ctx, int n_points, const float* grid, const f
 }
 
 int launch_hole_position(espic_ctx* ctx, int n_points, const float* grid, const float* potential, double dz,
-                         float L, int n_fine, const float* fine, float* scratch_res, float* pos_out) {
+                         float L, int n_fine, const float* fine, float* scratch_res, float* pos_out, int* cursor) {
     if (n_points < 2 || n_fine < 1) return fail(ctx, ESPIC_E_ARG, "hole_position needs n_points>=2, n_fine>=1");
     return run_filter<true>(ctx, n_points, grid, potential, (float)(2. * dz), (float)dz, L, n_fine, fine, scratch_res,
-                            pos_out);
+                            pos_out, cursor);
 }
 
 int launch_histogram(espic_ctx* ctx, const float* xs, const float* ys, int n_data, const int* tags,

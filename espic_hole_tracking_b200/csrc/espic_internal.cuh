@@ -205,6 +205,18 @@ struct espic_ctx {
     size_t hist_smem_set = 0;
     double exchange_timeout_s = 30.;  // espic_exchange_set_timeout
 
+    // espic_pic_run: one step captured as a CUDA graph and replayed (slot 0: without hole tracking,
+    // slot 1: with); valid while the step arguments and the context's scratch buffers stay what they were
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        espic_step_args key;
+        unsigned long long epoch = 0;
+        int launches = 0;              // kernels per replay (for espic_launch_count)
+    } step_graph[2];
+    cudaStream_t capture_stream = nullptr;
+    unsigned long long scratch_epoch = 0;   // bumped whenever a scratch buffer is (re)allocated
+    int track_cursor_host = -1;             // host mirror of the device cursor (status word 12)
+
     // per-launch timing of the mover kernel
     int timing_on = 0;
     cudaEvent_t* ev = nullptr;
@@ -302,7 +314,7 @@ int launch_field_filter(espic_ctx* ctx, int n_points, const float* grid, const f
                         int n_fine, const float* fine, float* res);
 int launch_hole_position(espic_ctx* ctx, int n_points, const float* grid, const float* potential,
                          double dz, float L, int n_fine, const float* fine, float* scratch_res,
-                         float* pos_out);
+                         float* pos_out, int* cursor = nullptr);
 int launch_histogram(espic_ctx* ctx, const float* xs, const float* ys, int n_data, const int* tags,
                      int tag_value, float x_min, float step_x, float y_min, float step_y,
                      int nx, int ny, int* hist);

@@ -587,11 +587,81 @@ class Simulation:
         """n_steps timesteps.  The device status word is read every ``check_every`` steps and at the end
         (one host synchronisation each): a fatal bit -- an exchange timeout, i.e. a rank that solved
         on stale peer densities and withdrew its potential -- raises instead of producing fields."""
-        for i in range(n_steps):
-            self.step()
-            if check_every and (i + 1) % check_every == 0:
+        i = 0
+        while i < n_steps:
+            room = n_steps - i
+            if check_every:
+                room = min(room, check_every - i % check_every)
+            m = self._native_steps(room)
+            if m > 0:
+                self._run_native(m)
+            else:
+                self.step()
+                m = 1
+            i += m
+            if check_every and i % check_every == 0:
                 self.check_status()
         self.check_status()
+
+    # Small runs (BASELINE configs[0]/[4]: 1e5..1e6 particles) take ~30 us of GPU work per step: an interpreter
+    # between the launches would be most of the wall clock.  run() therefore hands whole stretches of steps
+    # to espic_pic_run (one host call; steps without injection replayed from a CUDA graph) whenever the step
+    # needs nothing from the host in between.
+    native_run = True
+    use_step_graph = True
+
+    def _native_steps(self, limit: int) -> int:
+        """How many of the next ``limit`` steps espic_pic_run can take in one call (0: step() must)."""
+        c, k = self.cfg, self.k
+        if (not self.native_run or not self.fused_deposit or self.xch is not None or self.world > 1
+                or not self.ctrl.is_static or c.moving_box_simulation or c.phase_space_histograms):
+            return 0
+        if not c.periodic_particles and not isinstance(self.sampler, DeviceUniformSampler):
+            return 0
+        if k > c.time_steps_immobile_ions:     # frozen ions: the host resets their density row every step (:934)
+            return 0
+        n = min(limit, c.time_steps_immobile_ions - k + 1)
+        if k < c.time_steps_immobile_electrons:
+            n = min(n, c.time_steps_immobile_electrons - k)
+        for every in self.sort_intervals.values():
+            if every:
+                n = min(n, every - k % every)
+        return n
+
+    def _run_native(self, n: int) -> None:
+        """Steps k .. k+n-1 exactly as step() takes them, from one host call."""
+        from ._lib import RunArgs
+        c, k = self.cfg, self.k
+        a = self._step_args()
+        a.exchange_parity = -1
+        a.ion_acc_pending, a.electron_acc_pending = int(self._acc_pending[0]), int(self._acc_pending[1])
+        a.a_b, a.fix_ions, a.fix_electrons = 0.0, 1, 1
+        a.ions.dt = self.dt
+        a.electrons.dt = 0. if k < c.time_steps_immobile_electrons else self.dt
+        r = RunArgs()
+        r.n_steps, r.first_step, r.use_graph = n, k, int(self.use_step_graph)
+        keep = None
+        if not c.periodic_particles:
+            counts = np.array([self.injection_counts(k + i) for i in range(n)], dtype=np.int32).reshape(n, 2)
+            keep = (np.ascontiguousarray(counts[:, 0]), np.ascontiguousarray(counts[:, 1]))
+            r.n_inject_ions, r.n_inject_electrons = keep[0].ctypes.data, keep[1].ctypes.data
+            v_inj = float(self.ctrl.box[0, 0])
+            a.v_d_ions, a.v_d_electrons = v_inj - c.v_d_i, v_inj
+            a.inject_dt = self.dt
+            a.inject_by_side = int(bool(self.sort_intervals["electrons"] or self.sort_intervals["ions"]))
+        if c.track_hole:
+            r.hole_positions = self.hole_relative_positions.data_ptr()
+            r.track_from, r.track_until = c.initial_transient_steps + 1, self.hole_relative_positions.shape[0]
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.ctx.check(self.ctx._lib.espic_pic_run(self.ctx.handle, a, r), "espic_pic_run")
+        del keep
+        self._acc_pending = [True, True]
+        for _ in range(n):
+            self.t += self.dt
+        self.k += n
+        for name, every in self.sort_intervals.items():
+            if every and self.k % every == 0:
+                self.sort_particles((name,), key_shift=self.sort_key_shift, lookahead_steps=0.5 * every)
 
     FATAL_STATUS = 64   # ESPIC_ST_EXCHANGE_TIMEOUT (include/espic_b200.h)
 

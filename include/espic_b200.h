@@ -251,6 +251,28 @@ typedef struct {
 
 int espic_pic_step(espic_ctx *ctx, const espic_step_args *args);
 
+/* n_steps timesteps of the reference's main loop (ref infMagSim_script.py:756-1027) from one host call, for
+ * runs whose step is too short to hide an interpreter between the launches (BASELINE configs[0] and [4]:
+ * 1e5..1e6 particles, where the reference itself spends ~1e5 steps).  Step i is espic_pic_step with *first,
+ * except: step_index = first_step + i; the injection counts come from the two host arrays (NULL = none);
+ * hole_position_out = hole_positions + step_index while track_from <= step_index < track_until (NULL
+ * otherwise, ref :896-897); from the second step on both accumulator planes count as pending.  Stream
+ * ordered, nothing synchronises.  Single rank only (exchange_parity must be < 0).
+ * use_graph != 0: steps without injection are captured once as a CUDA graph and replayed -- one graph launch
+ * instead of the step's 3..5 kernel launches; the first such step of a call runs ungraphed to size the
+ * scratch buffers.  The graph is kept in the context and reused by later calls with the same arguments. */
+typedef struct espic_run_args {
+    int n_steps;
+    int first_step;
+    const int *n_inject_ions;       /* host, n_steps entries, or NULL */
+    const int *n_inject_electrons;  /* host, n_steps entries, or NULL */
+    float *hole_positions;          /* device, indexed by step_index, or NULL */
+    int track_from, track_until;
+    int use_graph;
+} espic_run_args;
+
+int espic_pic_run(espic_ctx *ctx, const espic_step_args *first, const espic_run_args *run);
+
 /* ---- multi-GPU density exchange fused into the field solve (replaces comm.Allreduce of the two
  * density grids, ref infMagSim_script.py:763, 773) ------------------------------------------------
  * One process per GPU of one box.  Each rank owns a small symmetric buffer in its own HBM

@@ -69,9 +69,9 @@ def run_gpu_hole_history(n, steps, record_every=100, n_cells=512, seed=384, devi
     rec = {k: [] for k in ("step", "max_phi", "hole", "ke_i", "ke_e", "fe", "n_i", "n_e")}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for k in range(steps):
-        sim.step()
-        if k % record_every == record_every - 1:
+    for k in range(record_every - 1, steps, record_every):
+        sim.run(record_every)     # espic_pic_run: the whole stretch from one host call
+        if True:
             e = sim.energies()
             act = sim.n_active()
             rec["step"].append(k)

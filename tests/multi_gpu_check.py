@@ -57,11 +57,13 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
         one.initialize()
     worst_phi = worst_den = den0 = worst_sum = 0.0
     good = True
+    identical = True
     for k in range(steps):
         sim.step()   # solves step k's field from the all-rank sum of step k's densities, then pushes
         gathered = [torch.empty_like(sim.potential) for _ in range(world)]
         dist.all_gather(gathered, sim.potential)
-        good &= all(torch.equal(gathered[0], g) for g in gathered)   # replicated solve: identical bits on every rank
+        identical &= all(torch.equal(gathered[0], g) for g in gathered)   # replicated solve: identical bits on every rank
+        good &= identical
         if rank == 0:
             one.field_step()
             phi = sim.potential.cpu().numpy().astype(np.float64)
@@ -95,7 +97,8 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
         # itself ~1e-6 off the exact sum at these counts); the solve amplifies that by ~(L/lambda_D)^2/8 ~ 300
         # in the net-charge mode of the Robin system (same bound as tests/test_distributed_cpu.py)
         good &= den0 <= 5e-6 and worst_den <= 12.0 and worst_sum <= 2e-5 and worst_phi <= 3e-3
-        good &= [int(counts[0]), int(counts[1])] == [act["ions"], act["electrons"]]
+        # free-running: a particle within an ulp of a wall may leave a step earlier on one side
+        good &= abs(int(counts[0]) - act["ions"]) <= 3 and abs(int(counts[1]) - act["electrons"]) <= 3
         # rank 0's own shard against the oracle's first n slots: same trajectories up to the field difference
         x_gpu = sim.ions.particles[0, :n].cpu().numpy()
         x_cpu = one.ions.particles[0, :n]
@@ -107,7 +110,7 @@ def check_vs_oracle(n_cells, periodic, n=200_000, steps=10):
               f"(tol 3e-3), density at step 0: max error / peak = {den0:.2e} (tol 5e-6), later steps (free-running): interior total off "
               f"by {worst_sum:.1e} (tol 2e-5), largest node difference {worst_den:.2f} particle weights; live (all ranks) {counts.tolist()} "
               f"vs oracle {[act['ions'], act['electrons']]}, max ion |dx| = {dx:.2e}, status {st}, "
-              f"ranks bit-identical: {bool(good)}", flush=True)
+              f"ranks bit-identical: {bool(identical)}", flush=True)
     good &= st == 0
     return bool(good)
 
