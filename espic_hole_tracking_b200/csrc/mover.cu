@@ -143,9 +143,32 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
             // Units travel global -> shared with cp.async one unit ahead of the arithmetic (no
             // registers held across the wait), 2 stages of 2 KB per warp behind the grid tables:
             // [stage][x of quad 0 | v of quad 0 | x of quad 1 | v of quad 1][32 lanes x 16 B].
-            float4* ring = reinterpret_cast<float4*>(smem_raw + a.tile_bytes) + (size_t)(tid >> 5) * 256;
+            float4* ring = reinterpret_cast<float4*>(smem_raw + a.tile_bytes) + (size_t)(tid >> 5) * (kRingBytesPerWarp / 16);
             const float4* gx = reinterpret_cast<const float4*>(a.px);
             const float4* gv = reinterpret_cast<const float4*>(a.pv);
+#if ESPIC_VAR_TMA
+            // A/B: the unit travels as two 1 KB bulk copies (x, v) issued by lane 0 and completed on a per-warp,
+            // per-stage mbarrier; ring stage = [x of the unit | v of the unit]
+            const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem_raw + a.tile_bytes + (size_t)(blockDim.x >> 5) * kRingBytesPerWarp) +
+                                  (unsigned)(tid >> 5) * (8u * kTmaStages);
+            const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+            if (lane == 0) {
+#pragma unroll
+                for (int st = 0; st < kTmaStages; ++st) mbar_init(bar0 + 8u * st, 1u);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+            auto issue = [&](int u, int stage) {
+                __syncwarp();   // every lane has finished reading this stage
+                if (lane == 0) {
+                    const unsigned bar = bar0 + 8u * stage, dst = ring_s + 2048u * stage;
+                    mbar_expect_tx(bar, 2048u);
+                    bulk_load(dst, a.px + (size_t)u * kUnitSlots, 1024u, bar);
+                    bulk_load(dst + 1024u, a.pv + (size_t)u * kUnitSlots, 1024u, bar);
+                }
+            };
+            unsigned parity = 0u;
+#else
             auto issue = [&](int u, int stage) {
                 float4* dst = ring + stage * 128 + lane;
                 const int q = u * kUnitQuads + lane;
@@ -155,16 +178,36 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
                 cp_async16(dst + 96, gv + q + 32);
                 cp_async_commit();
             };
+#endif
             // strided: units dealt round-robin, so that at any moment the grid works on one contiguous
             // ~10 MB stretch of each row (DRAM page locality: 0.305 -> 0.295 ms per 1e8 particles)
             // instead of 4736 streams 340 KB apart
             const int du = STRIDED ? total_warps : 1;
             const int ub = STRIDED ? gw : u0, ue = STRIDED ? split.n_units : u1;
+#if ESPIC_VAR_TMA
+#pragma unroll
+            for (int st = 0; st < kTmaStages - 1; ++st)
+                if (ub + st * du < ue) issue(ub + st * du, st);
+#else
             if (ub < ue) issue(ub, 0);
+#endif
             int stage = 0;
 #pragma unroll 1
-            for (int u = ub; u < ue; u += du, stage ^= 1) {
+            for (int u = ub; u < ue; u += du, stage = (ESPIC_VAR_TMA ? (stage + 1 == kTmaStages ? 0 : stage + 1) : stage ^ 1)) {
                 const int q0 = u * kUnitQuads + lane, q1 = q0 + 32;
+#if ESPIC_VAR_TMA
+                mbar_wait(bar0 + 8u * stage, (parity >> stage) & 1u);
+                parity ^= 1u << stage;   // the stage's next fill completes the other phase
+                const float4* src = ring + stage * 128 + lane;
+                Quad p0, p1;
+                unpack_quad(src[0], src[64], p0);
+                unpack_quad(src[32], src[96], p1);
+                {   // refill the stage read in the previous iteration
+                    const int ahead = u + (kTmaStages - 1) * du;
+                    const int fill = stage == 0 ? kTmaStages - 1 : stage - 1;
+                    if (ahead < ue) issue(ahead, fill);
+                }
+#else
                 cp_async_wait_all();
                 const float4* src = ring + stage * 128 + lane;
                 Quad p0, p1;
@@ -172,7 +215,10 @@ __global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
 #if !ESPIC_VAR_UNPACK
                 unpack_quad(src[64], src[96], p1);
 #endif
+#endif
+#if !ESPIC_VAR_TMA
                 if (u + du < ue) issue(u + du, stage ^ 1);  // uniform; fills the OTHER stage
+#endif
                 if (lane < 16 && u + a.prefetch_units * du < split.n_units) {
                     const float* row = (lane & 8) ? a.pv : a.px;
                     const float* line = row + (size_t)(u + a.prefetch_units * du) * kUnitSlots + (lane & 7) * 32;
@@ -601,7 +647,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     ESPIC_CUDA(ctx, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const bool use_smem = tile <= (size_t)max_smem;
     // cp.async staging ring: 4 KB per warp of a 1024-thread CTA, when the tables leave room for it
-    const size_t ring = (size_t)(kMoveThreads / 32) * 4096;
+    const size_t ring = (size_t)(kMoveThreads / 32) * (kRingBytesPerWarp + 8 * kTmaStages * ESPIC_VAR_TMA);
     static int staging_env = -1;
     if (staging_env < 0) {
         const char* e = getenv("ESPIC_STAGING");  // tuning knob
@@ -609,14 +655,14 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     }
     // measured: staging gains 4 % in the periodic variant and loses 5 % in the wall variant (its
     // removal bookkeeping already strains the 64-register budget), so only the former uses it
-    a.staged = (use_smem && periodic && staging_env && tile + ring <= (size_t)max_smem && a.vec_ok) ? 1 : 0;
+    a.staged = (use_smem && (periodic || ESPIC_VAR_STAGE_WALLS) && staging_env && tile + ring <= (size_t)max_smem && a.vec_ok) ? 1 : 0;
     a.tile_bytes = (int)tile;
     static int strided_env = -1;
     if (strided_env < 0) {
         const char* e = getenv("ESPIC_STRIDED");  // tuning knob; 0 = contiguous ranges per warp
         strided_env = e ? atoi(e) : 1;
     }
-    a.strided = (a.staged && strided_env) ? 1 : 0;
+    a.strided = (a.staged && strided_env && periodic) ? 1 : 0;
     if (a.strided) a.counts = counts_strided;
     // windowed / global-table launches never take the round-robin kernel
     a.epilogue = (ESPIC_VAR_EPILOGUE && acc_fused && a.strided && periodic && use_smem) ? 1 : 0;

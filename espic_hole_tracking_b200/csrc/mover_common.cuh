@@ -11,6 +11,18 @@
 #define ESPIC_VAR_CARRY 0     // 1: one running maximum over the eight returned words; 0: one compare per word
                               // (measured on B200, 1e8 particles: 0.2937 vs 0.2920 ms per launch -- no gain in k_move)
 #endif
+#ifndef ESPIC_DEBUG_CYCLES
+#define ESPIC_DEBUG_CYCLES 0  // 1: the windowed mover records clock cycles per segment and per CTA (espic_debug_cta_cycles)
+#endif
+#ifndef ESPIC_VAR_TMA
+#define ESPIC_VAR_TMA 1       // 1: units reach the staging ring as 1 KB bulk copies (TMA) issued by one lane and completed
+#endif                        //    on an mbarrier; 0: four 16-byte cp.async per lane (0.2868 -> 0.2797 ms per 1e8 particles)
+#ifndef ESPIC_TMA_STAGES
+#define ESPIC_TMA_STAGES 2
+#endif
+#ifndef ESPIC_VAR_STAGE_WALLS
+#define ESPIC_VAR_STAGE_WALLS 0   // 1: the wall-bounded whole-grid kernel uses the staging ring too
+#endif
 #ifndef ESPIC_VAR_UNPACK
 #define ESPIC_VAR_UNPACK 0    // 1: the second quad is read from the ring after the first has been pushed (no spill in
                               // the loop, but the exposed LDS latency costs more: 0.3058 vs 0.2920 ms per launch)
@@ -27,6 +39,8 @@ namespace espic {
                                 // 4096 cells, ms per launch, periodic / walls): 512 -> 0.288 / 0.320, 640 -> 0.294 / 0.294,
                                 // 768 -> 0.295 / 0.285, 896 -> 0.287 / 0.279, 1024 (64 registers) -> 0.294 / 0.291
 #endif
+constexpr int kTmaStages = ESPIC_VAR_TMA ? ESPIC_TMA_STAGES : 2;
+constexpr int kRingBytesPerWarp = 2048 * kTmaStages;   // one 2 KB unit (x, v of 256 slots) per stage
 constexpr int kMoveThreads = ESPIC_MOVE_BOUNDS;  // one CTA per SM: one tile to zero and flush per SM
 constexpr int kMoveMaxThreads = ESPIC_MOVE_BOUNDS;
 constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
@@ -369,6 +383,30 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 1-D bulk copies (TMA) completed on an mbarrier: one lane moves a whole warp-unit.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ void store_quad(const MoveArgs& a, int q, const Quad& p) {
     __stcs(reinterpret_cast<float4*>(a.px) + q, make_float4(p.x[0], p.x[1], p.x[2], p.x[3]));

@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
     __shared__ int s_score[kWinBuckets];
     __shared__ int s_seg, s_w_lo;
 
+#if ESPIC_DEBUG_CYCLES
     const long long t_entry = a.cta_cycles ? clock64() : 0ll;
+#endif
     const int n_points = a.n_points, n_cells = n_points - 1;
     const Geom g = make_geom(a.grid, n_points);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -264,7 +266,9 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
         const int ticket = s_seg;
         if (ticket >= a.n_segments) break;
         const int seg = (ticket & 1) ? a.n_segments - 1 - (ticket >> 1) : (ticket >> 1);
+#if ESPIC_DEBUG_CYCLES
         const long long t_seg = a.cta_cycles ? clock64() : 0ll;
+#endif
         const int r0 = seg * warps_per_cta;
         const int seg_u0 = split.first_unit(r0), seg_u1 = split.first_unit(r0 + warps_per_cta);
 
@@ -381,10 +385,15 @@ __global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
             if (lo) atomicAdd(a.acc + map.node_of(j), (unsigned long long)lo);
         }
         __syncthreads();
-        // development aid (ESPIC_DEBUG_CTA=1): cycles per segment, ions in [512, 1024), electrons in [0, 512)
+#if ESPIC_DEBUG_CYCLES
+        // development aid (build with -DESPIC_DEBUG_CYCLES=1, run with ESPIC_DEBUG_CTA=1): cycles per segment, ions in
+        // [512, 1024), electrons in [0, 512); per CTA from 1024 on (scripts/cta_cycles_probe.py)
         if (a.cta_cycles && tid == 0 && seg < 512) a.cta_cycles[(a.qm > 0.f ? 512 : 0) + seg] = clock64() - t_seg;
+#endif
     }
+#if ESPIC_DEBUG_CYCLES
     if (a.cta_cycles && tid == 0) a.cta_cycles[1024 + blockIdx.x] = clock64() - t_entry;
+#endif
 }
 
 // Cells of the window for a grid whose whole-grid tables do not fit (the caller has checked that).  Grids of

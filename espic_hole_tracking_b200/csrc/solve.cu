@@ -168,27 +168,22 @@ struct SolveArgs {
 };
 
 // Practically never executed: the periodic movers of the previous step removed slots and pushed them in
-// arrival order.  One thread puts the new stretch of each stack into ascending slot order (what the
-// reference's slot-ordered loop produces, ref infMagSim_c.c:214-217) -- an insertion sort: the stretch
-// holds a handful of entries when it exists at all.
-__device__ __noinline__ void fix_stack_order(const StackFix& f) {
-    for (int s = 0; s < 2; ++s) {
-        if (!f.pushed[s]) continue;
-        const int n = *f.pushed[s];
-        if (n == 0) continue;
-        const int hi = min(*f.top[s], f.largest_allowed_slot[s]);
-        const int lo = max(*f.top[s] - n + 1, 0);
-        int* st = f.empty_slots[s];
-        for (int i = lo + 1; i <= hi; ++i) {
-            const int v = st[i];
-            int j = i - 1;
-            while (j >= lo && st[j] > v) {
-                st[j + 1] = st[j];
-                --j;
-            }
-            st[j + 1] = v;
+// arrival order.  The new stretch of each stack is put into ascending slot order (what the reference's
+// slot-ordered loop produces, ref infMagSim_c.c:214-217).  A handful of entries -- the normal case when the
+// stretch exists at all -- is an insertion sort by one thread (fix_stack_small).  A long stretch (a run that
+// blew up numerically can throw every particle out of a periodic box in one step) is sorted by the whole
+// team, fix_stack_team below: quadratic work by one thread would look like a hung GPU.
+constexpr int kFixSmall = 48;
+
+__device__ __noinline__ void fix_stack_small(int* st, int lo, int hi) {
+    for (int i = lo + 1; i <= hi; ++i) {
+        const int v = st[i];
+        int j = i - 1;
+        while (j >= lo && st[j] > v) {
+            st[j + 1] = st[j];
+            --j;
         }
-        *f.pushed[s] = 0;
+        st[j + 1] = v;
     }
 }
 
@@ -212,6 +207,60 @@ __device__ __forceinline__ void team_sync(const Team& tm) {
     if (tm.size > 1) cg::this_cluster().sync();
     else __syncthreads();
 }
+// Bitonic network with every compare-exchange ascending (the first sub-stage of a merge pairs i with its mirror
+// image in the block), so the stretch can be padded to a power of two virtually: a position past the end holds
+// +infinity and never moves.  Every team thread calls this with the same arguments; n log^2 n / Tn work each.
+__device__ __noinline__ void fix_stack_team(const Team& tm, int* st, int lo, int hi) {
+    const int n = hi - lo + 1;
+    int P = 1;
+    while (P < n) P <<= 1;
+    team_sync(tm);
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool mirror = j == (k >> 1);
+            for (int t = tm.T; t < (P >> 1); t += tm.Tn) {
+                // the t-th pair of this sub-stage: i has bit j clear
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = mirror ? (i ^ (k - 1)) : (i | j);
+                if (l < n) {
+                    const int a = __ldcg(st + lo + i), b = __ldcg(st + lo + l);
+                    if (a > b) {
+                        st[lo + i] = b;
+                        st[lo + l] = a;
+                    }
+                }
+            }
+            __threadfence();
+            team_sync(tm);
+        }
+    }
+}
+
+// All team threads, uniformly.  Returns after the stacks are in order and the counters are cleared.
+__device__ __noinline__ void fix_stack_order(const Team& tm, const StackFix& f) {
+    const int n0 = __ldcg(f.pushed[0]), n1 = __ldcg(f.pushed[1]);
+    if ((n0 | n1) == 0) return;
+    bool synced = false;
+    for (int s = 0; s < 2; ++s) {
+        const int n = s ? n1 : n0;
+        if (n == 0) continue;
+        const int top = __ldcg(f.top[s]);
+        const int hi = min(top, f.largest_allowed_slot[s]);
+        const int lo = max(top - n + 1, 0);
+        if (hi - lo + 1 <= kFixSmall) {
+            if (tm.T == 0) fix_stack_small(f.empty_slots[s], lo, hi);
+        } else {
+            fix_stack_team(tm, f.empty_slots[s], lo, hi);
+            synced = true;
+        }
+    }
+    if (synced) team_sync(tm);   // every thread has read the counters before they are cleared
+    if (tm.T == 0) {
+        *f.pushed[0] = 0;
+        *f.pushed[1] = 0;
+    }
+}
+
 template <class T>
 __device__ __forceinline__ T* remote(T* p, int rank) {
     return cg::this_cluster().map_shared_rank(p, rank);
@@ -885,7 +934,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
     }
     // stacks whose newest entries the periodic movers pushed in arrival order (practically never): put them in the
     // reference's ascending order; checked last, off the critical path of the solve
-    if (tm.T == 0 && a.fix.pushed[0] && (__ldcg(a.fix.pushed[0]) | __ldcg(a.fix.pushed[1]))) fix_stack_order(a.fix);
+    if (a.fix.pushed[0]) fix_stack_order(tm, a.fix);
     if (timed_out) {  // exchange timeout: every barrier above was still taken; the result is withdrawn
         for (int i = 0; i < m; ++i) {
             const int j = tm.T * m + i;

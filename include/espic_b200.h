@@ -80,8 +80,9 @@ int espic_device_info(espic_ctx *ctx, int *sm_count, int *mover_grid, int *mover
 int espic_mover_window_cells(espic_ctx *ctx, int n_points);
 /* Kernels launched on this context since creation (bench's gpu_launches). */
 long long espic_launch_count(espic_ctx *ctx);
-/* Development aid: with ESPIC_DEBUG_CTA=1 in the environment, per-CTA clock cycles of the last windowed
- * mover launch (up to n values copied to out; returns how many; synchronises). */
+/* Development aid: in a library built with -DESPIC_DEBUG_CYCLES=1 and with ESPIC_DEBUG_CTA=1 in the environment,
+ * per-segment and per-CTA clock cycles of the last windowed mover launch (up to n values copied to out; returns
+ * how many, 0 in a regular build; synchronises). */
 int espic_debug_cta_cycles(espic_ctx *ctx, long long *out, int n);
 /* Per-launch CUDA-event timing of the mover kernel: enable, run, then read the mean launch
  * duration in ms and the launch count (synchronises). */
