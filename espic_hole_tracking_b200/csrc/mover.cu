@@ -94,7 +94,7 @@ __device__ __noinline__ void removal_epilogue_strided(const MoveArgs& a, int n_s
 // complete unit, unaligned stores, start-up calls with update_position=0, an absorbing
 // object, exotic dz) goes quad by quad through quad_generic.
 template <bool PERIODIC, bool SMEM, bool STRIDED>
-__global__ void __launch_bounds__(kMoveMaxThreads, 1) k_move(const MoveArgs a) {
+__global__ void __launch_bounds__((move_threads<PERIODIC, SMEM>()), 1) k_move(const MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n_points = a.n_points;
     const int n_pad = (n_points + 3) & ~3;
@@ -534,14 +534,15 @@ static int launch_move_variant(espic_ctx* ctx, const MoveArgs& a, size_t smem) {
     if (cached_smem != smem) {
         if (smem > 48 * 1024)
             ESPIC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int threads = kMoveThreads, per_sm = 0;
+        constexpr int max_threads = move_threads<PERIODIC, SMEM>();
+        int threads = max_threads, per_sm = 0;
         if (const char* e = getenv("ESPIC_MOVE_THREADS")) {  // tuning knob
             const int t = atoi(e);
-            if (t >= 256 && t <= kMoveMaxThreads && t % 128 == 0) threads = t;
+            if (t >= 256 && t <= max_threads && t % 128 == 0) threads = t;
         }
         for (;;) {
             ESPIC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-            if (per_sm * threads >= 1024 || threads >= kMoveMaxThreads) break;
+            if (per_sm * threads >= 1024 || threads * 2 > max_threads) break;
             threads *= 2;
         }
         if (per_sm < 1) return fail(ctx, ESPIC_E_ARG, "mover kernel does not fit on an SM (smem %zu)", smem);
@@ -647,7 +648,7 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     ESPIC_CUDA(ctx, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const bool use_smem = tile <= (size_t)max_smem;
     // cp.async staging ring: 4 KB per warp of a 1024-thread CTA, when the tables leave room for it
-    const size_t ring = (size_t)(kMoveThreads / 32) * (kRingBytesPerWarp + 8 * kTmaStages * ESPIC_VAR_TMA);
+    const size_t ring = (size_t)((periodic ? kMoveThreadsStaged : kMoveThreads) / 32) * (kRingBytesPerWarp + 8 * kTmaStages * ESPIC_VAR_TMA);
     static int staging_env = -1;
     if (staging_env < 0) {
         const char* e = getenv("ESPIC_STAGING");  // tuning knob

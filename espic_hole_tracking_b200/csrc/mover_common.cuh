@@ -27,6 +27,9 @@
 #define ESPIC_VAR_UNPACK 0    // 1: the second quad is read from the ring after the first has been pushed (no spill in
                               // the loop, but the exposed LDS latency costs more: 0.3058 vs 0.2920 ms per launch)
 #endif
+#if ESPIC_VAR_TMA && ESPIC_VAR_UNPACK
+#error "ESPIC_VAR_UNPACK belongs to the cp.async ring (ESPIC_VAR_TMA=0)"
+#endif
 #ifndef ESPIC_VAR_EPILOGUE
 #define ESPIC_VAR_EPILOGUE 0  // 1: last-CTA removal epilogue compiled into the round-robin periodic kernel (the extra
                               // code at the end of the kernel perturbs the main loop: 0.3038 vs 0.2920 ms per launch)
@@ -41,8 +44,15 @@ namespace espic {
 #endif
 constexpr int kTmaStages = ESPIC_VAR_TMA ? ESPIC_TMA_STAGES : 2;
 constexpr int kRingBytesPerWarp = 2048 * kTmaStages;   // one 2 KB unit (x, v of 256 slots) per stage
+#ifndef ESPIC_MOVE_BOUNDS_STAGED
+#define ESPIC_MOVE_BOUNDS_STAGED 512   // CTA width of the periodic whole-grid kernels, whose units arrive through the bulk-copy ring:
+                                       // 16 warps at 108 registers, nothing spilled.  Measured (B200, 1e8 particles, 4096 cells, ms per
+                                       // launch): 256 x2 -> 0.282, 384 -> 0.294, 512 -> 0.261, 640 -> 0.268, 768 -> 0.266, 896 -> 0.272
+#endif
 constexpr int kMoveThreads = ESPIC_MOVE_BOUNDS;  // one CTA per SM: one tile to zero and flush per SM
-constexpr int kMoveMaxThreads = ESPIC_MOVE_BOUNDS;
+constexpr int kMoveThreadsStaged = ESPIC_MOVE_BOUNDS_STAGED;
+template <bool PERIODIC, bool SMEM>
+constexpr int move_threads() { return (PERIODIC && SMEM) ? kMoveThreadsStaged : kMoveThreads; }
 constexpr int kUnitQuads = 64;                // one unit = two warp instructions of 32 quads
 constexpr int kUnitSlots = 4 * kUnitQuads;    // 256 slots
 constexpr int kSmemBytesPerPoint = 12;

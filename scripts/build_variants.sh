@@ -12,6 +12,6 @@ while [ $# -ge 2 ]; do
   cp "$ROOT"/include/espic_b200.h "$tmp/include/"
   make -C "$tmp/pkg/csrc" -j8 NVCC="/usr/local/cuda/bin/nvcc $flags" > "$tmp/build.log" 2>&1 || { tail -20 "$tmp/build.log"; exit 1; }
   cp "$tmp/pkg/libespic_b200.so" "$ROOT/variants/libespic_$name.so"
-  grep -A2 "k_moveILb1ELb1ELb1E" "$tmp/pkg/csrc/mover.ptxas.log" | grep spill | sed "s/^/$name: /"
+  grep -A2 "k_moveILb1ELb1ELb1E" "$tmp/pkg/csrc/mover.ptxas.log" | grep "spill\|Used" | tr '\n' ' ' | sed "s/^/$name: /; s/ptxas info    ://; s/  */ /g"; echo
   rm -rf "$tmp"
 done
