@@ -30,7 +30,10 @@
 // -- no stray for 58 steps, but 1.80 (28-step sort interval) to 1.89 (58): the gather sits in the dependency
 // chain of every slot; a no-wrap instantiation of the mapping next to the general one (1.43: the duplicated
 // loop costs more in instruction fetch than it saves); an all-or-nothing slow path per warp (one stray in 128
-// slots is the rule late in a sort interval); 1024-thread CTAs at 64 registers (1.15).
+// slots is the rule late in a sort interval); 1024-thread CTAs at 64 registers (1.15); the bulk-copy (TMA) staging
+// ring of k_move<periodic> -- its 64 KB have to come out of the window (20480 cells, sort every 21 steps instead of
+// 28) and the CTA has to be 512 threads wide: 1.248 (periodic grid: mover 0.449 ms against 0.363); narrower CTAs on
+// register loads (768 -> 1.133, 640 -> 1.172, 512 -> 1.241); L2 prefetch 2 / 3 / 4 units ahead (1.132 / 1.145 / 1.161).
 //
 // After espic_sort_particles_coarse() a segment's particles sit within a few hundred cells of each
 // other and drift apart by |v| dt per step; the window leaves ~13700 cells of margin either side,
