@@ -309,7 +309,7 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
 // assignment (left from the bottom of the popped range, right from the top) a shortfall of left-wall slots
 // -- (removed - injected)/2 per step while the population falls -- still put left-wall entrants into
 // right-wall slots, and the two segments that collected them ran 6x longer than the others.
-__global__ void __launch_bounds__(256) k_inject_commit(const InjectArgs a) {
+__global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ InjectArgs a) {
     __shared__ unsigned s_wall[2 * kWallNodes];
     __shared__ int s_last;
     __shared__ int s_scan[8], s_scan2[8];

@@ -236,7 +236,7 @@ __device__ __forceinline__ unsigned quad_win(const MoveArgs& a, const Geom& g, Q
 }
 
 template <bool PERIODIC>
-__global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const MoveArgs a) {
+__global__ void __launch_bounds__(kWinThreads, 1) k_move_win(const __grid_constant__ MoveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_dv = reinterpret_cast<float*>(smem_raw);
     unsigned* s_lo = reinterpret_cast<unsigned*>(s_dv + kWinNodes);

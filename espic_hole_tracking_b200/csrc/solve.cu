@@ -731,7 +731,7 @@ __device__ __noinline__ void rhs_general(const SolveArgs& a, const RowConsts& k,
 // cold instruction cache every step (the movers in between evict it), and the general variant,
 // whose sweeps are unrolled for long runs, spent 40 % of its 23 us waiting for instructions.
 template <bool ONE_ROW>
-__global__ void __launch_bounds__(kSolveThreads) k_poisson(const SolveArgs a) {
+__global__ void __launch_bounds__(kSolveThreads) k_poisson(const __grid_constant__ SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];  // y plane when it fits (m <= kSolveSmemRows)
     __shared__ TeamShared sh;
     __shared__ __align__(16) double s_edge[2 * kSolveThreads];  // run-boundary values; reused as Aff[1024]
