@@ -488,6 +488,88 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ staging
             if (strided_counts[c]) strided_counts[c] = 0;
 }
 
+// k_finish + k_scatter in one launch, for the step path (fused deposit: nothing to convert) with contiguous ranges
+// (the wall-bounded whole-grid kernel and the windowed kernel): every CTA scans the per-range removal counts into
+// shared memory for itself -- a few thousand ints out of L2 -- and copies its share of the staged ids to the stack,
+// bisecting the shared-memory offsets; the last CTA to finish moves the stack top and resets the counters.  One
+// launch less per species and step.
+constexpr int kEpilogueMaxRanges = 12 * 1024 - 64;  // 48 KB of static shared memory
+
+__global__ void __launch_bounds__(256) k_removal_epilogue(const int* __restrict__ staging, const int* __restrict__ counts,
+                                                          int n_ranges, int* __restrict__ hdr, int* __restrict__ top,
+                                                          int* __restrict__ empty_slots, int largest_allowed_slot,
+                                                          const int* largest_index_dev, int largest_index, int mover_warps,
+                                                          int slot_offset, int interleave, int* flags_global, int* status,
+                                                          unsigned* ticket) {
+    __shared__ int s_off[kEpilogueMaxRanges];
+    __shared__ int s_warp[8];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int total = hdr[3];   // the movers' running total; every CTA reads it and the old top before the last one resets them
+    const int old_top = *top;
+    if (total != 0) {  // uniform
+        // counts -> shared memory with every load in flight at once (coalesced), then an in-place exclusive scan,
+        // each thread a contiguous run (an odd run length keeps the runs on different banks)
+#pragma unroll 8
+        for (int i = tid; i < n_ranges; i += 256) s_off[i] = __ldcg(counts + i);
+        __syncthreads();
+        const int per = ((n_ranges + 255) / 256) | 1;
+        const int i0 = min(tid * per, n_ranges), i1 = min(i0 + per, n_ranges);
+        int sum = 0;
+        for (int i = i0; i < i1; ++i) sum += s_off[i];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        int run = incl - sum;
+        for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
+        for (int i = i0; i < i1; ++i) {
+            const int c = s_off[i];
+            s_off[i] = run;
+            run += c;
+        }
+        __syncthreads();
+        const int n_slots = (largest_index_dev ? *largest_index_dev : largest_index) + 1;
+        const Split split(n_slots, mover_warps);
+        const int stride = gridDim.x * blockDim.x;
+        for (int d = blockIdx.x * blockDim.x + tid; d < total; d += stride) {
+            // which staged id goes to stack position old_top+1+d: see k_scatter
+            const int t = total - 1 - d;
+            const int i = !interleave ? d : ((t & 1) ? (t >> 1) : total - 1 - (t >> 1));
+            int lo = 0, hi = n_ranges - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_off[mid] <= i) lo = mid;
+                else hi = mid - 1;
+            }
+            const int* src = staging + (size_t)(lo < mover_warps ? split.first_unit(lo) : split.n_units) * kUnitSlots;
+            const int dst = old_top + 1 + d;
+            if (dst >= 0 && dst <= largest_allowed_slot) empty_slots[dst] = __ldcg(src + (i - s_off[lo])) + slot_offset;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && tid == 0) {
+        *top = old_top + total;
+        if (old_top + total > largest_allowed_slot) atomicOr(status, ESPIC_ST_STACK_OVERFLOW);
+        hdr[0] = old_top;
+        hdr[1] = total;
+        hdr[2] = n_ranges;
+        hdr[3] = 0;
+        if (flags_global) {
+            flags_global[0] = 0;
+            flags_global[1] = 0;
+        }
+        *ticket = 0u;
+    }
+}
+
 // Fixed-point accumulators -> float density (the conversion k_finish makes), accumulators cleared.
 __global__ void k_convert_density(unsigned long long* __restrict__ acc, float* __restrict__ density, int n,
                                   double inv_scale) {
@@ -721,6 +803,21 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     f.inv_scale = 1.0 / ((double)kWeightOne * (double)bg);
     f.flags_global = flags;
     f.convert = acc_fused ? 0 : finish_density;
+    static int fused_epilogue_env = -1;
+    if (fused_epilogue_env < 0) {
+        const char* e = getenv("ESPIC_FUSED_EPILOGUE");  // tuning knob; 0 = k_finish + k_scatter
+        fused_epilogue_env = e ? atoi(e) : 1;
+    }
+    if (fused_epilogue_env && acc_fused && !a.strided && f.n_ranges <= kEpilogueMaxRanges) {
+        int eg = 1 + max_slots / 16384;   // a small store needs a few CTAs, not a scan per SM
+        if (eg > 4 * ctx->sm_count) eg = 4 * ctx->sm_count;
+        k_removal_epilogue<<<eg, 256, 0, ctx->stream>>>(a.staging, a.counts, f.n_ranges, f.scatter_hdr, top, empty_slots,
+                                                        largest_allowed_slot, largest_index_dev, largest_index, mover_warps,
+                                                        slot_offset, stack_interleave, flags, ctx->status,
+                                                        (unsigned*)(ctx->status + 11));
+        ctx->launches++;
+        return check_cuda(ctx, cudaGetLastError(), "mover epilogue launch");
+    }
     k_finish<<<n_points <= 8192 ? 1 : (n_points + 4095) / 4096, 1024, 0, ctx->stream>>>(f);
     ctx->launches++;
     ESPIC_CUDA(ctx, cudaGetLastError());
