@@ -160,6 +160,7 @@ void espic_destroy(espic_ctx* ctx) {
     free_scratch(ctx->host_stage);
     free_scratch(ctx->filter_ws);
     free_scratch(ctx->debug_ws);
+    free_scratch(ctx->run_ctl);
     for (auto& g : ctx->step_graph)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
@@ -411,7 +412,7 @@ int espic_field_solve_exchange(espic_ctx* ctx, int parity, int step, const float
 }
 
 // One timestep on ctx->stream.  track_cursor: device int indexing hole_position_out (step graphs), or null.
-static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cursor) {
+static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cursor, int* inject_ctl = nullptr) {
     if (!a->grid || !a->object_mask || !a->potential || !a->charge) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: null grid pointer");
     const espic_species* sp[2] = {&a->ions, &a->electrons};
     for (int i = 0; i < 2; ++i)
@@ -485,8 +486,14 @@ static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cu
     const int n_inj[2] = {a->n_inject_ions, a->n_inject_electrons};
     const float v_th[2] = {a->v_th_ions, a->v_th_electrons}, v_d[2] = {a->v_d_ions, a->v_d_electrons};
     int* tags[2] = {a->ion_tags, a->electron_tags};
+    // inject_ctl (replayed step graphs): n_inject_* are the upper bounds of the stretch; the kernels take the step's
+    // own counts, the tag and the sampler's call counter from the control block, and the species injected last
+    // moves the block on to the next step
+    const int last_injecting = n_inj[1] > 0 ? 1 : 0;
     for (int i = 0; i < 2; ++i) {
         if (n_inj[i] <= 0) continue;
+        const InjectCtl ic{inject_ctl, i, kCtlMaxSteps, i == last_injecting ? 1 : 0};
+        const InjectCtl* icp = inject_ctl ? &ic : nullptr;
         if (!tags[i]) return fail(ctx, ESPIC_E_ARG, "espic_pic_step: injection needs the tag array");
         rc = ensure(ctx, ctx->rng_ws, (size_t)2 * ((n_inj[i] + 63) & ~63) * sizeof(float), "injection random inputs");
         if (rc) return rc;
@@ -495,12 +502,12 @@ static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cu
         // same draw order as the reference wrapper: fractions first, then velocities (ref infMagSim_cython.py:245-248);
         // both draws and the bad-index classification in one launch, placement + deposit + stack pop in a second
         if ((rc = rng_sample_for_injection(ctx, n_inj[i], v_th[i], v_d[i], vel, uni, a->grid, a->n_points, a->inject_dt,
-                                           a->background_density, a->a_b)))
+                                           a->background_density, a->a_b, icp)))
             return rc;
         const espic_species* s = sp[i];
         rc = launch_inject(ctx, n_inj[i], a->grid, a->n_points, a->inject_dt, a->background_density, vel, uni, a->a_b,
                            a->step_index, tags[i], s->particles, s->particle_storage_length, s->empty_slots,
-                           s->current_empty_slot, s->largest_index, s->density, true, acc[i], a->inject_by_side);
+                           s->current_empty_slot, s->largest_index, s->density, true, acc[i], a->inject_by_side, icp);
         if (rc) return rc;
     }
     return ESPIC_OK;
@@ -513,6 +520,11 @@ int espic_pic_step(espic_ctx* ctx, const espic_step_args* a) {
 }
 
 __global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_set_ctl(int* ctl, int k, int i, unsigned long long calls) {
+    ctl[0] = k;
+    ctl[1] = i;
+    *reinterpret_cast<unsigned long long*>(ctl + 2) = calls;
+}
 
 static void drop_step_graph(espic_ctx::StepGraph& g) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -520,7 +532,7 @@ static void drop_step_graph(espic_ctx::StepGraph& g) {
 }
 
 // Captures one step with the given arguments on the side stream (nothing executes) and instantiates it.
-static int capture_step(espic_ctx* ctx, const espic_step_args* a, int which) {
+static int capture_step(espic_ctx* ctx, const espic_step_args* a, int which, int* inject_ctl) {
     espic_ctx::StepGraph& g = ctx->step_graph[which];
     drop_step_graph(g);
     if (!ctx->capture_stream)
@@ -530,7 +542,7 @@ static int capture_step(espic_ctx* ctx, const espic_step_args* a, int which) {
     const unsigned long long epoch = ctx->scratch_epoch;
     ESPIC_CUDA(ctx, cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal));
     ctx->stream = ctx->capture_stream;
-    int rc = pic_step_impl(ctx, a, which ? ctx->status + 12 : nullptr);
+    int rc = pic_step_impl(ctx, a, which ? ctx->status + 12 : nullptr, inject_ctl);
     ctx->stream = user;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->capture_stream, &graph);
@@ -564,38 +576,71 @@ int espic_pic_run(espic_ctx* ctx, const espic_step_args* first, const espic_run_
     const bool fused = first->ions.acc != nullptr;
     int warmed[2] = {0, 0};
     bool graphs = r->use_graph != 0 && !ctx->timing_on;
+    // injecting stretches: the counts go to the device once, the launches are sized for the stretch's maxima
+    // (rounded up, so that the captured geometry survives from stretch to stretch)
+    int nmax[2] = {0, 0};
+    for (int i = 0; i < r->n_steps; ++i) {
+        if (r->n_inject_ions && r->n_inject_ions[i] > nmax[0]) nmax[0] = r->n_inject_ions[i];
+        if (r->n_inject_electrons && r->n_inject_electrons[i] > nmax[1]) nmax[1] = r->n_inject_electrons[i];
+    }
+    const bool injecting = nmax[0] > 0 || nmax[1] > 0;
+    int* ctl = nullptr;
+    bool ctl_set = false;
+    if (graphs && injecting) {
+        if (r->n_steps > kCtlMaxSteps) {
+            graphs = false;
+        } else {
+            for (int s = 0; s < 2; ++s)
+                if (nmax[s] > 0) nmax[s] = (nmax[s] + 1023) & ~1023;
+            const int big = nmax[0] > nmax[1] ? nmax[0] : nmax[1];
+            int rc = ensure(ctx, ctx->run_ctl, (size_t)(16 + 2 * kCtlMaxSteps) * sizeof(int), "step control block");
+            if (!rc) rc = ensure(ctx, ctx->rng_ws, (size_t)2 * ((big + 63) & ~63) * sizeof(float), "injection random inputs");
+            if (!rc) rc = ensure(ctx, ctx->inject_ws, 64 + ((size_t)big / 128 + 2) * sizeof(int), "inject workspace");
+            if (rc) return rc;
+            ctl = (int*)ctx->run_ctl.ptr;
+            const int* src[2] = {r->n_inject_ions, r->n_inject_electrons};
+            for (int s = 0; s < 2; ++s) {
+                if (src[s])
+                    ESPIC_CUDA(ctx, cudaMemcpyAsync(ctl + 16 + s * kCtlMaxSteps, src[s], (size_t)r->n_steps * sizeof(int),
+                                                    cudaMemcpyHostToDevice, ctx->stream));
+                else
+                    ESPIC_CUDA(ctx, cudaMemsetAsync(ctl + 16 + s * kCtlMaxSteps, 0, (size_t)r->n_steps * sizeof(int), ctx->stream));
+            }
+        }
+    }
     for (int i = 0; i < r->n_steps; ++i) {
         const int k = r->first_step + i;
+        const int n_i = r->n_inject_ions ? r->n_inject_ions[i] : 0, n_e = r->n_inject_electrons ? r->n_inject_electrons[i] : 0;
         espic_step_args a;
         memcpy(&a, first, sizeof a);
         a.step_index = k;
-        a.n_inject_ions = r->n_inject_ions ? r->n_inject_ions[i] : 0;
-        a.n_inject_electrons = r->n_inject_electrons ? r->n_inject_electrons[i] : 0;
+        a.n_inject_ions = n_i;
+        a.n_inject_electrons = n_e;
         if (i > 0 && fused) a.ion_acc_pending = a.electron_acc_pending = 1;   // every step leaves its deposit pending
         const bool track = r->hole_positions && k >= r->track_from && k < r->track_until;
         a.hole_position_out = track ? r->hole_positions + k : nullptr;
-        const bool graphable = graphs && a.n_inject_ions <= 0 && a.n_inject_electrons <= 0;
         int rc;
-        if (!graphable) {
+        if (!graphs) {
             if ((rc = pic_step_impl(ctx, &a, nullptr))) return rc;
             continue;
         }
-        // the replayed graph indexes the history through the device cursor; nothing else varies from step to step
+        // the replayed graph indexes the history through the device cursor and takes the injection's per-step values
+        // from the control block; nothing in its arguments varies from step to step
+        espic_step_args plain;
+        memcpy(&plain, &a, sizeof a);
         a.step_index = 0;
         a.hole_position_out = track ? r->hole_positions : nullptr;
+        a.n_inject_ions = nmax[0];
+        a.n_inject_electrons = nmax[1];
         espic_ctx::StepGraph& g = ctx->step_graph[track ? 1 : 0];
         if (!g.exec || g.epoch != ctx->scratch_epoch || memcmp(&g.key, &a, sizeof a) != 0) {
-            espic_step_args plain;
-            memcpy(&plain, &a, sizeof a);
-            plain.step_index = k;
-            plain.hole_position_out = track ? r->hole_positions + k : nullptr;
             if (!warmed[track]) {
                 // first an ordinary step: it sizes the scratch buffers and the per-kernel launch configuration
                 if ((rc = pic_step_impl(ctx, &plain, nullptr))) return rc;
                 warmed[track] = 1;
                 continue;
             }
-            if (capture_step(ctx, &a, track ? 1 : 0)) {   // not capturable here: carry on launch by launch
+            if (capture_step(ctx, &a, track ? 1 : 0, injecting ? ctl : nullptr)) {   // not capturable here: carry on launch by launch
                 graphs = false;
                 if ((rc = pic_step_impl(ctx, &plain, nullptr))) return rc;
                 continue;
@@ -605,9 +650,19 @@ int espic_pic_run(espic_ctx* ctx, const espic_step_args* first, const espic_run_
             k_set_int<<<1, 1, 0, ctx->stream>>>(ctx->status + 12, k);
             ctx->launches++;
         }
+        if (injecting && (!ctl_set || ctx->ctl_host_k != k)) {
+            if (!ctx->rng_seeded) rng_seed(ctx, 4357ul);
+            k_set_ctl<<<1, 1, 0, ctx->stream>>>(ctl, k, i, ctx->rng_consumed);
+            ctx->launches++;
+            ctl_set = true;
+        }
         ESPIC_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
         ctx->launches += g.launches;
         if (track) ctx->track_cursor_host = k + 1;
+        if (injecting) {
+            ctx->ctl_host_k = k + 1;
+            ctx->rng_consumed += (n_i > 0 ? 2ull : 0ull) + (n_e > 0 ? 2ull : 0ull);
+        }
     }
     return ESPIC_OK;
 }

@@ -214,6 +214,8 @@ struct espic_ctx {
         int launches = 0;              // kernels per replay (for espic_launch_count)
     } step_graph[2];
     cudaStream_t capture_stream = nullptr;
+    espic::Scratch run_ctl;                 // control block + injection counts of the stretch being replayed
+    int ctl_host_k = -1;                    // host mirror of the control block's step index
     unsigned long long scratch_epoch = 0;   // bumped whenever a scratch buffer is (re)allocated
     int track_cursor_host = -1;             // host mirror of the device cursor (status word 12)
 
@@ -300,12 +302,20 @@ int launch_field_solve_exchange(espic_ctx* ctx, int parity, int step, const floa
                                 int boltzmann, int periodic_potential, int n_points, const StackFix* fix = nullptr);
 int launch_prepare_charge(espic_ctx* ctx, float* ion, float* ele, float* charge, int n, int periodic,
                           int fix_i, int fix_e);
+// Device control block of a replayed step graph (espic_pic_run, see InjectArgs in inject.cu): the injection kernels
+// read the step index, the counts and the sampler's call counter from it; n_inject is then an upper bound.
+constexpr int kCtlMaxSteps = 4096;   // steps of one espic_pic_run call whose injection counts fit the control block
+struct InjectCtl {
+    int* ptr;
+    int species, stride, advance;
+};
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
                   int storage, int* empty_slots, int* top, int* largest, float* density, bool classified = false,
-                  unsigned long long* acc_fused = nullptr, int by_side = 0);
+                  unsigned long long* acc_fused = nullptr, int by_side = 0, const InjectCtl* ctl = nullptr);
 int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
-                             const float* grid, int n_points, float dt, float bg, float a_b);
+                             const float* grid, int n_points, float dt, float bg, float a_b,
+                             const InjectCtl* ctl = nullptr);
 int launch_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points, float bg);
 int rng_seed(espic_ctx* ctx, unsigned long seed);
 int rng_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out);

@@ -170,10 +170,38 @@ struct InjectArgs {
     // kSampleThreads consecutive particles) that enter at the left wall, written by k_sample_classify
     int* left_count;
     int by_side;
+    // Replayed step graphs (espic_pic_run): what changes from step to step is read from a device control block
+    // instead of the argument block -- ctl[0] = step index (the tag), ctl[1] = index of the step in the run's count
+    // arrays, ctl[2..3] = the sampler's call counter (64 bit), counts of species s at ctl[16 + s*ctl_stride + i].
+    // n_inject is then the upper bound the launch was sized for.  The commit kernel of the species injected
+    // last (ctl_advance) moves the block on to the next step.
+    int* ctl;
+    int ctl_species, ctl_stride, ctl_advance;
     int n_inject, n_points, k;
     float dt, a_b;
     double inv_scale;
 };
+
+struct InjectStep {
+    int n_inject, k;
+    unsigned long long call_uni, call_vel;
+};
+// The per-step values: from the argument block, or from the control block of a replayed graph.  A species with
+// nothing to inject in a step draws nothing (the stepwise path skips its two sampler calls), so the electrons'
+// calls come after the ions' only if there were ions.
+__device__ __forceinline__ InjectStep inject_step(const InjectArgs& a, unsigned long long call_uni, unsigned long long call_vel) {
+    InjectStep st{a.n_inject, a.k, call_uni, call_vel};
+    if (a.ctl) {
+        const int i = __ldcg(a.ctl + 1);
+        st.k = __ldcg(a.ctl);
+        st.n_inject = min(__ldcg(a.ctl + 16 + a.ctl_species * a.ctl_stride + i), a.n_inject);
+        unsigned long long base = __ldcg(reinterpret_cast<const unsigned long long*>(a.ctl + 2));
+        if (a.ctl_species > 0 && __ldcg(a.ctl + 16 + i) > 0) base += 2ull;
+        st.call_uni = base;
+        st.call_vel = base + 1ull;
+    }
+    return st;
+}
 
 struct Injected {
     float x, v;
@@ -214,11 +242,14 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample_classify(const Inject
     const Geom g = make_geom(a.grid, a.n_points);
     Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
     int bad = 0;
-    const int n_chunks = (a.n_inject + kSampleThreads - 1) / kSampleThreads;
+    const InjectStep st = inject_step(a, call_uni, call_vel);
+    call_uni = st.call_uni;
+    call_vel = st.call_vel;
+    const int n_chunks = (st.n_inject + kSampleThreads - 1) / kSampleThreads;
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {  // uniform trip count per CTA
         const int l = chunk * kSampleThreads + threadIdx.x;
         int left = 0;
-        if (l < a.n_inject) {
+        if (l < st.n_inject) {
             const float u = uniform_at(ph, l, call_uni);
             const float v = draw_velocity(ph, l, call_vel, k, a.status);
             uni_out[l] = u;
@@ -267,7 +298,7 @@ __device__ __forceinline__ void deposit_injected_tiled(const Geom& g, const Inje
 
 // Density of the injected particles added to the caller's float density, accumulators re-zeroed,
 // stack top updated: run by the last CTA of the commit kernel to finish (ref infMagSim_cython.py:281-285).
-__device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhere) {
+__device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhere, int n_inject) {
     const int n = a.n_points;
     // injected particles sit within |v| dt of a wall: unless a deposit went further in, only the
     // two wall regions can hold anything
@@ -283,7 +314,7 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
     if (threadIdx.x == 0) {
         const int top0 = *a.top;
         if (a.ws[0] == 0) {
-            const int n_ok = min(a.n_inject, top0 + 1);
+            const int n_ok = min(n_inject, top0 + 1);
             *a.top = top0 - (n_ok > 0 ? n_ok : 0);
         } else {
             *a.top = a.ws[1];
@@ -292,6 +323,13 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
         a.ws[1] = 0;
         a.ws[2] = 0;
         *a.ticket = 0u;
+        if (a.ctl && a.ctl_advance) {  // every CTA of this launch has read the block: on to the next step
+            const int i = a.ctl[1];
+            unsigned long long* calls = reinterpret_cast<unsigned long long*>(a.ctl + 2);
+            *calls += (a.ctl[16 + i] > 0 ? 2ull : 0ull) + (a.ctl[16 + a.ctl_stride + i] > 0 ? 2ull : 0ull);
+            a.ctl[0] += 1;
+            a.ctl[1] = i + 1;
+        }
     }
 }
 
@@ -317,6 +355,8 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
     const Geom g = make_geom(a.grid, a.n_points);
     const int top0 = *a.top;
     const int n_bad = a.ws[0];
+    const InjectStep st = inject_step(a, 0ull, 0ull);
+    const int n_inject = st.n_inject;
     if (n_bad == 0) {
         for (int j = threadIdx.x; j < 2 * kWallNodes; j += blockDim.x) s_wall[j] = 0u;
         __syncthreads();
@@ -324,7 +364,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
         bool interior = false;
         // contiguous runs of 256-particle rounds per CTA, so that the left-wall rank of a round is the rank
         // of the previous one plus its count
-        const int n_rounds = (a.n_inject + 255) / 256;
+        const int n_rounds = (n_inject + 255) / 256;
         const int per_cta = (n_rounds + (int)gridDim.x - 1) / (int)gridDim.x;
         const int r0 = min((int)blockIdx.x * per_cta, n_rounds), r1 = min(r0 + per_cta, n_rounds);
         int base_left = 0, total_left = 0;
@@ -332,7 +372,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
             // particles entering at the left wall in front of this CTA's first round, and in all (two sampler chunks per round)
             int part = 0, all = 0;
             for (int c = threadIdx.x; c < 2 * n_rounds; c += blockDim.x) {
-                const int v = (c * kSampleThreads < a.n_inject) ? a.left_count[c] : 0;
+                const int v = (c * kSampleThreads < n_inject) ? a.left_count[c] : 0;
                 all += v;
                 part += c < 2 * r0 ? v : 0;
             }
@@ -365,10 +405,10 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
         // distance from the top, entrants at the left wall those at odd distance, as long as both sides have
         // entrants left (m of each); the surplus of the larger side continues below.  Exactly the top n_inject
         // entries are consumed, each once.
-        const int m_pairs = min(total_left, a.n_inject - total_left);
+        const int m_pairs = min(total_left, n_inject - total_left);
         for (int r = r0; r < r1; ++r) {
             const int l = r * 256 + (int)threadIdx.x;
-            const bool have = l < a.n_inject;
+            const bool have = l < n_inject;
             const float vel = have ? a.vel[l] : 0.f;
             int sp = top0 - l;  // the reference's pop order
             if (a.by_side) {
@@ -397,7 +437,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
             }
             const int slot = a.empty_slots[sp];
             const Injected p = place_injected(g, vel, a.uni[l], a.dt, a.a_b);
-            a.hist[slot] = a.k;
+            a.hist[slot] = st.k;
             a.pv[slot] = p.v;
             a.px[slot] = p.x;
             my_max = max(my_max, slot);
@@ -419,14 +459,14 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
     } else if (blockIdx.x == 0 && threadIdx.x == 0) {
         // replay of the reference's sequential loop (only when a bad left_index occurred)
         int top = top0, last = *a.largest;
-        for (int l = 0; l < a.n_inject; ++l) {
+        for (int l = 0; l < n_inject; ++l) {
             if (top < 0) {
                 atomicOr(a.status, ESPIC_ST_STACK_EMPTY);
                 break;
             }
             const int slot = a.empty_slots[top];
             const Injected p = place_injected(g, a.vel[l], a.uni[l], a.dt, a.a_b);
-            a.hist[slot] = a.k;
+            a.hist[slot] = st.k;
             a.pv[slot] = p.v;
             a.px[slot] = p.x;
             last = max(last, slot);
@@ -451,7 +491,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
     if (s_last) {
         __threadfence();
         const bool everywhere = n_bad != 0 || a.n_points < 2 * kWallNodes || *(volatile int*)(a.ws + 2) != 0;
-        inject_finish(a, everywhere);
+        inject_finish(a, everywhere, n_inject);
     }
 }
 
@@ -481,9 +521,15 @@ static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const f
 int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points, float dt, float bg,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
                   int storage, int* empty_slots, int* top, int* largest, float* density, bool classified,
-                  unsigned long long* acc_fused, int by_side) {
+                  unsigned long long* acc_fused, int by_side, const InjectCtl* ctl) {
     if (n_inject <= 0) return 0;
     InjectArgs a{};
+    if (ctl) {
+        a.ctl = ctl->ptr;
+        a.ctl_species = ctl->species;
+        a.ctl_stride = ctl->stride;
+        a.ctl_advance = ctl->advance;
+    }
     int rc = fill_inject_args(ctx, a, n_inject, grid, n_points, dt, bg, a_b);
     if (rc) return rc;
     if (acc_fused) {  // step path: add to the caller's accumulators (converted by the next field solve)
@@ -520,13 +566,22 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
 // launch; follow with launch_inject(..., classified = true).  Same streams as rng_uniforms followed by
 // rng_draw_velocities (ref infMagSim_cython.py:245-248: fractions first).
 int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
-                             const float* grid, int n_points, float dt, float bg, float a_b) {
+                             const float* grid, int n_points, float dt, float bg, float a_b,
+                             const InjectCtl* ctl) {
     if (n_inject <= 0) return 0;
     InjectArgs a{};
     int rc = fill_inject_args(ctx, a, n_inject, grid, n_points, dt, bg, a_b);
     if (rc) return rc;
     const unsigned long long key = rng_key(ctx);
-    const unsigned long long call_uni = ctx->rng_consumed++, call_vel = ctx->rng_consumed++;
+    unsigned long long call_uni = 0ull, call_vel = 0ull;
+    if (ctl) {  // the kernel takes both from the control block; the caller keeps the host's counter in step
+        a.ctl = ctl->ptr;
+        a.ctl_species = ctl->species;
+        a.ctl_stride = ctl->stride;
+    } else {
+        call_uni = ctx->rng_consumed++;
+        call_vel = ctx->rng_consumed++;
+    }
     a.left_count = (int*)ctx->inject_ws.ptr + 16;
     int grid_dim = (n_inject + kSampleThreads - 1) / kSampleThreads;
     if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;

@@ -259,9 +259,13 @@ int espic_pic_step(espic_ctx *ctx, const espic_step_args *args);
  * hole_position_out = hole_positions + step_index while track_from <= step_index < track_until (NULL
  * otherwise, ref :896-897); from the second step on both accumulator planes count as pending.  Stream
  * ordered, nothing synchronises.  Single rank only (exchange_parity must be < 0).
- * use_graph != 0: steps without injection are captured once as a CUDA graph and replayed -- one graph launch
- * instead of the step's 3..5 kernel launches; the first such step of a call runs ungraphed to size the
- * scratch buffers.  The graph is kept in the context and reused by later calls with the same arguments. */
+ * use_graph != 0: the step is captured once as a CUDA graph and replayed -- one graph launch instead of the step's
+ * 3..11 kernel launches; the first step of a call that needs a new graph runs ungraphed to size the scratch
+ * buffers.  What varies from step to step stays out of the graph's arguments: the tracking result is indexed by a
+ * device cursor, and an injecting stretch (at most 4096 steps per call) has its counts copied to the device once, its
+ * launches sized for the stretch's maxima, and the step index, counts and sampler position read by the injection
+ * kernels from a device control block that the last of them advances.  Results are bit-identical to stepping.
+ * The graphs are kept in the context and reused by later calls with the same arguments. */
 typedef struct espic_run_args {
     int n_steps;
     int first_step;

@@ -15,7 +15,10 @@ for _ in range(100): sim.step()
 e0 = sim.energies(); a0 = sim.n_active()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); ev0.record()
-for _ in range(steps): sim.step()
+if os.environ.get("PROBE_RUN") == "1":
+    sim.run(steps, check_every=0)   # stretches of steps from one host call, replayed from step graphs
+else:
+    for _ in range(steps): sim.step()
 ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / steps
 e1 = sim.energies(); a1 = sim.n_active()

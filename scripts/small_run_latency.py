@@ -39,6 +39,4 @@ if __name__ == "__main__":
     for n, cells in ((100_000, 512), (1_000_000, 4096)):
         for periodic in (True, False):
             for mode in ("stepwise", "native", "graph"):
-                if mode == "graph" and not periodic:
-                    continue
                 case(n, cells, periodic, mode)
