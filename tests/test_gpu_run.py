@@ -1,5 +1,6 @@
-"""espic_pic_run (many steps from one host call, injection-free steps replayed from a CUDA graph) against the
-step-by-step path: the same kernels in the same order, so everything must agree bit for bit."""
+"""espic_pic_run (many steps from one host call, the step replayed from a CUDA graph -- wall-bounded steps with
+their injection counts, tag and sampler position in a device control block) against the step-by-step path: the
+same kernels in the same order, so everything must agree bit for bit."""
 import numpy as np
 import pytest
 
@@ -61,7 +62,8 @@ def test_native_run_periodic_matches_stepwise(graph, n_cells):
 
 def test_native_run_walls_injection_matches_stepwise():
     """Wall-bounded run: the injection counts of every step are drawn on the host in advance, in the order
-    the stepwise path draws them."""
+    the stepwise path draws them, and the replayed graph takes them -- and the tag and the sampler's position --
+    from the device control block."""
     cfg = dict(n_steps=300, n_particles=60_000, n_cells=512, periodic_particles=False, track_hole=True,
                initial_transient_steps=3)
     ref, nat = _pair(cfg, 280, dict(use_step_graph=True))
@@ -87,3 +89,20 @@ def test_graph_replay_launch_accounting():
     ref, nat = _pair(cfg, 200, dict(use_step_graph=True))
     _same(nat, ref)
     assert nat.native_launches == 3 * 200          # solve + two pushes per step, graph or not
+
+
+def test_native_run_stretch_longer_than_the_control_block():
+    """A single injecting stretch of more than 4096 steps does not fit the control block: espic_pic_run then
+    launches kernel by kernel (still one host call) -- same results."""
+    from espic_hole_tracking_b200.simulation import SimConfig, Simulation
+    cfg = dict(n_steps=4400, n_particles=20_000, n_cells=512, periodic_particles=False, track_hole=True,
+               initial_transient_steps=3)
+    sims = []
+    for native in (False, True):
+        sim = Simulation(SimConfig(**cfg))
+        sim.init_synthetic()
+        sim.initialize()
+        sim.native_run = native
+        sim.run(4300, check_every=0)
+        sims.append(sim)
+    _same(sims[1], sims[0])
