@@ -92,3 +92,30 @@ def test_operator_signatures_match_reference():
     sig = inspect.signature(ops.poisson_solve).parameters
     assert sig["object_potential"].default == -4. and sig["object_transparency"].default == 1.
     assert inspect.signature(ops.move_particles).parameters["a_b"].default is inspect.Parameter.empty
+
+
+def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
+    """espic_species / espic_step_args / espic_run_args as ctypes sees them against what a C compiler makes of
+    include/espic_b200.h: same size, every field at the same offset (a silent mismatch would hand the library
+    garbage pointers)."""
+    import shutil
+    import subprocess
+    from espic_hole_tracking_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    mirrors = {"espic_species": _lib.Species, "espic_step_args": _lib.StepArgs, "espic_run_args": _lib.RunArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
