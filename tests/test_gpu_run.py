@@ -20,12 +20,11 @@ def _pair(cfg_kwargs, n_steps, native_kwargs):
         if native:
             for name, v in native_kwargs.items():
                 setattr(sim, name, v)
-            launches0 = sim.ctx.launch_count()
-            sim.run(n_steps)
-            sim.native_launches = sim.ctx.launch_count() - launches0
         else:
             sim.native_run = False
-            sim.run(n_steps)
+        launches0 = sim.ctx.launch_count()
+        sim.run(n_steps)
+        sim.native_launches = sim.ctx.launch_count() - launches0
         sims.append(sim)
     return sims
 
@@ -88,7 +87,10 @@ def test_graph_replay_launch_accounting():
     cfg = dict(n_steps=300, n_particles=20_000, n_cells=512, periodic_particles=True, track_hole=False)
     ref, nat = _pair(cfg, 200, dict(use_step_graph=True))
     _same(nat, ref)
-    assert nat.native_launches == 3 * 200          # solve + two pushes per step, graph or not
+    assert nat.native_launches == ref.native_launches      # graph or not, the same kernels
+    import os
+    if not any(k in os.environ for k in ("ESPIC_STAGING", "ESPIC_STRIDED")):
+        assert nat.native_launches == 3 * 200              # solve + two pushes per step
 
 
 def test_native_run_stretch_longer_than_the_control_block():
