@@ -20,16 +20,20 @@
 // converts to the float density the reference's callers expect.
 //
 // Work split: the store is cut into units of 256 consecutive slots.  The wall variant gives every
-// warp of the persistent grid (148 CTAs x 32 warps) one contiguous, ascending range of units;
-// the periodic variant deals the units round-robin (warp w: units w, w+4736, ...), which keeps
-// the whole grid on one contiguous stretch of the store at any moment (DRAM page locality).
+// warp of the persistent grid (148 CTAs x 28 warps, register loads) one contiguous, ascending range of
+// units; the periodic variant (148 CTAs x 16 warps) deals the units round-robin (warp w: units w,
+// w+2368, ...), which keeps the whole grid on one contiguous stretch of the store at any moment (DRAM
+// page locality), and brings each unit into a per-warp shared-memory ring as two 1 KB bulk copies (TMA,
+// cp.async.bulk completing on an mbarrier) issued by one lane, one unit ahead of the arithmetic.
 //
 // Removal (walls, absorbing object; in periodic runs only a particle flung past 0.99*2*z_max)
 // must reproduce the reference's sequential stack pushes: slots appear on the stack in
 // ascending slot order.  A range -- a warp's range of units, or a single unit in the
 // round-robin split -- compacts its removed slot ids in order with ballots into the staging
 // region behind its first slot and records the count; k_finish scans the counts (skipped when
-// nothing was removed) and k_scatter copies the staged ids to their final stack positions.
+// nothing was removed) and k_scatter copies the staged ids to their final stack positions -- on the
+// step path (espic_pic_step, deposit left in the caller's accumulators) one launch does both,
+// k_removal_epilogue, and the periodic variant pushes its practically-never removals itself.
 //
 // Grids too large for the shared-memory tables (more than ~19k points) are moved by
 // k_move_win (mover_win.cu); start-up calls on such grids use this kernel with the kick table
