@@ -33,7 +33,8 @@
 // slots is the rule late in a sort interval); 1024-thread CTAs at 64 registers (1.15); the bulk-copy (TMA) staging
 // ring of k_move<periodic> -- its 64 KB have to come out of the window (20480 cells, sort every 21 steps instead of
 // 28) and the CTA has to be 512 threads wide: 1.248 (periodic grid: mover 0.449 ms against 0.363); narrower CTAs on
-// register loads (768 -> 1.133, 640 -> 1.172, 512 -> 1.241); L2 prefetch 2 / 3 / 4 units ahead (1.132 / 1.145 / 1.161).
+// register loads (768 -> 1.133, 640 -> 1.172, 512 -> 1.241); L2 prefetch 2 / 3 / 4 units ahead (1.132 / 1.145 / 1.161);
+// register loads issued one unit ahead (against 1.030: 896 threads 1.114, 768 -> 1.069, 640 -> 1.079 -- spills or too few warps).
 //
 // After espic_sort_particles_coarse() a segment's particles sit within a few hundred cells of each
 // other and drift apart by |v| dt per step; the window leaves ~13700 cells of margin either side,
