@@ -448,12 +448,11 @@ static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cu
         unsigned long long* pend[2] = {a->ion_acc_pending ? acc[0] : nullptr, a->electron_acc_pending ? acc[1] : nullptr};
         if (a->n_points > 8192) {
             // beyond 8192 points the solve walks several rows per thread on 8 CTAs; converting 2 x n_points
-            // accumulators there costs more (65537 points: 37 -> 59 us) than two wide launches in front of it
-            for (int i = 0; i < 2; ++i)
-                if (pend[i]) {
-                    if ((rc = launch_convert_density(ctx, pend[i], sp[i]->density, a->n_points, a->background_density))) return rc;
-                    pend[i] = nullptr;
-                }
+            // accumulators there costs more (65537 points: 37 -> 59 us) than one wide launch in front of it
+            if ((rc = launch_convert_density2(ctx, pend[0], sp[0]->density, pend[1], sp[1]->density, a->n_points,
+                                              a->background_density)))
+                return rc;
+            pend[0] = pend[1] = nullptr;
         }
         rc = launch_field_solve(ctx, a->grid, a->object_mask, a->ions.density, a->electrons.density, a->charge,
                                 a->periodic_particles, a->fix_ions, a->fix_electrons, a->debye_length, a->potential,

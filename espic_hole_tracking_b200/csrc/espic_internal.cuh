@@ -317,6 +317,8 @@ int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d
                              const float* grid, int n_points, float dt, float bg, float a_b,
                              const InjectCtl* ctl = nullptr);
 int launch_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points, float bg);
+int launch_convert_density2(espic_ctx* ctx, unsigned long long* acc0, float* den0, unsigned long long* acc1, float* den1,
+                            int n_points, float bg);
 int rng_seed(espic_ctx* ctx, unsigned long seed);
 int rng_draw_velocities(espic_ctx* ctx, int n, float v_th, float v_d, float* v_out);
 int rng_uniforms(espic_ctx* ctx, int n, float* out);

@@ -583,6 +583,30 @@ __global__ void k_convert_density(unsigned long long* __restrict__ acc, float* _
     }
 }
 
+// Both species' pending planes in one launch (either may be null).
+__global__ void k_convert_density2(unsigned long long* __restrict__ acc0, float* __restrict__ den0,
+                                   unsigned long long* __restrict__ acc1, float* __restrict__ den1, int n, double inv_scale) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        if (acc0) {
+            den0[j] = (float)((double)acc0[j] * inv_scale);
+            acc0[j] = 0ull;
+        }
+        if (acc1) {
+            den1[j] = (float)((double)acc1[j] * inv_scale);
+            acc1[j] = 0ull;
+        }
+    }
+}
+
+int launch_convert_density2(espic_ctx* ctx, unsigned long long* acc0, float* den0, unsigned long long* acc1, float* den1,
+                            int n_points, float bg) {
+    if (n_points < 1 || (!acc0 && !acc1)) return 0;
+    k_convert_density2<<<(n_points + 1023) / 1024, 1024, 0, ctx->stream>>>(acc0, den0, acc1, den1, n_points,
+                                                                          1.0 / ((double)kWeightOne * (double)bg));
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "k_convert_density2 launch");
+}
+
 int launch_convert_density(espic_ctx* ctx, unsigned long long* acc, float* density, int n_points, float bg) {
     if (n_points < 1) return 0;
     k_convert_density<<<(n_points + 1023) / 1024, 1024, 0, ctx->stream>>>(acc, density, n_points,
