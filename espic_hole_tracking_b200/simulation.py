@@ -310,9 +310,11 @@ class Simulation:
                 continue
             margin = 0.5 * window - (1 << self.sort_key_shift)
             drift = max(v_th, abs(self.v_b)) * self.dt / self.dz          # cells per step at one thermal speed
-            # measured optimum on the 65536-cell grid: 2.3 thermal speeds of margin with walls (injected particles pile
-            # up unsorted in the tail of the store meanwhile), 1.8 in a periodic box
-            reach = 1.8 if c.periodic_particles else 2.3
+            # measured optimum on the 65536-cell grid: 2.05 thermal speeds of margin with walls (injected particles pile
+            # up unsorted in the tail of the store meanwhile; electrons every 32 steps: 26 / 28 / 30 / 32 / 34 / 36 steps
+            # give 1.006 / 1.004 / 0.998 / 0.994 / 0.998 / 1.008 ms per step -- it was 2.3, every 28, while the mover
+            # was slower), 1.8 in a periodic box
+            reach = 1.8 if c.periodic_particles else 2.05
             auto[name] = int(min(1000, max(1, 2 * margin / (reach * drift))))
         self.sort_intervals = {
             "ions": auto["ions"] if c.sort_interval_ions is None else c.sort_interval_ions,

@@ -338,7 +338,7 @@ def test_large_grid_auto_sort_is_physically_invisible(pkg, periodic):
         sim.init_synthetic()
         sim.initialize()
         if not never:
-            assert sim.sort_intervals["electrons"] == (36 if periodic else 28) and sim.sort_key_shift == 8
+            assert sim.sort_intervals["electrons"] == (36 if periodic else 32) and sim.sort_key_shift == 8
         sim.run(25)
         assert sim.status_word() == 0
         runs.append((sim.ion_density.cpu().numpy().copy(), sim.electron_density.cpu().numpy().copy(),
