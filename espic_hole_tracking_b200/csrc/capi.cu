@@ -469,11 +469,14 @@ static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cu
     }
     for (int i = 0; i < 2; ++i) {
         const espic_species* s = sp[i];
+        // large grids: the ions' call builds both species' kick tables, the electrons' call finds its own ready
+        const espic_species* o = sp[1];
+        const DvPlan plan{i == 0 ? 1 : 2, o->potential ? o->potential : a->potential, o->charge_to_mass, a->a_b, o->dt};
         rc = launch_move(ctx, a->grid, a->object_mask, s->potential ? s->potential : a->potential, s->dt,
                          s->charge_to_mass, a->background_density, -1, s->largest_index, s->particles, s->density,
                          s->empty_slots, s->current_empty_slot, a->a_b, 1, a->periodic_particles, s->largest_allowed_slot,
                          a->n_points, s->particle_storage_length, 0, 0, 1, acc[i], pushed[i],
-                         (a->inject_by_side && !a->periodic_particles) ? 1 : 0);
+                         (a->inject_by_side && !a->periodic_particles) ? 1 : 0, &plan);
         if (rc) return rc;
     }
     if (a->hole_position_out) {

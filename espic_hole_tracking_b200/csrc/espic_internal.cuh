@@ -271,12 +271,20 @@ struct StackFix {
 };
 
 // launchers implemented in the other translation units
+// Large grids keep the per-cell kick table in global memory (k_build_dv).  A step pushes two species on the same
+// grid: the first call can build both tables in one launch (role 1, with the second species' parameters), the
+// second call then finds its table ready (role 2).  Each species has its own flag pair behind the tables.
+struct DvPlan {
+    int role;              // 0: build this call's table only
+    const float* phi_b;    // role 1: the second species' potential, charge-to-mass ratio, frame acceleration, dt
+    float qm_b, a_b_b, dt_b;
+};
 int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const float* phi, float dt,
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage, int minimal = 0,
                 int slot_offset = 0, int finish_density = 1, unsigned long long* acc_fused = nullptr,
-                int* pushed = nullptr, int stack_interleave = 0);
+                int* pushed = nullptr, int stack_interleave = 0, const DvPlan* dv_plan = nullptr);
 int launch_tridiagonal(espic_ctx* ctx, double* a, double* b, double* c, double* d, double* x, int n);
 int move_window_cells(espic_ctx* ctx, int n_points);  // 0: whole-grid tables fit in shared memory
 int launch_selftest_quotient(espic_ctx* ctx, const float* grid, int n_points, unsigned long long* counts_out);

@@ -359,6 +359,28 @@ __global__ void k_build_dv(const float* __restrict__ grid, const float* __restri
     if (__syncthreads_or(obj) && threadIdx.x == 0) atomicOr(flags, 1);
 }
 
+// The same for both species of a step in one launch: table / flag pair A for the species pushed first, B behind it.
+__global__ void k_build_dv2(const float* __restrict__ grid, const float* __restrict__ mask, int n_points,
+                            const float* __restrict__ phi_a, float qm_a, float a_b_a, float dt_a, float* __restrict__ dv_a,
+                            const float* __restrict__ phi_b, float qm_b, float a_b_b, float dt_b, float* __restrict__ dv_b,
+                            int* __restrict__ flags) {
+    const Geom g = make_geom(grid, n_points);
+    int obj = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_points; j += gridDim.x * blockDim.x) {
+        if (j < n_points - 1) {
+            const float ea = __fdiv_rn(-__fsub_rn(phi_a[j + 1], phi_a[j]), g.dz);
+            dv_a[j] = __fmul_rn(__fsub_rn(__fmul_rn(qm_a, ea), a_b_a), dt_a);
+            const float eb = __fdiv_rn(-__fsub_rn(phi_b[j + 1], phi_b[j]), g.dz);
+            dv_b[j] = __fmul_rn(__fsub_rn(__fmul_rn(qm_b, eb), a_b_b), dt_b);
+        }
+        obj |= (mask[j] > 0.f);
+    }
+    if (__syncthreads_or(obj) && threadIdx.x == 0) {
+        atomicOr(flags, 1);
+        atomicOr(flags + 2, 1);
+    }
+}
+
 struct FinishArgs {
     unsigned long long* acc;
     float* density;
@@ -680,7 +702,8 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
                 float qm, float bg, int largest_index, const int* largest_index_dev, float* particles,
                 float* density, int* empty_slots, int* top, float a_b, int update_position,
                 int periodic, int largest_allowed_slot, int n_points, int storage, int minimal, int slot_offset,
-                int finish_density, unsigned long long* acc_fused, int* pushed, int stack_interleave) {
+                int finish_density, unsigned long long* acc_fused, int* pushed, int stack_interleave,
+                const DvPlan* dv_plan) {
     // acc_fused (the step path, espic_pic_step): the deposit is ADDED to these caller-owned fixed-point
     // accumulators and left there -- the next field solve converts it -- and `density` is not touched.
     // slot_offset / finish_density: the call covers slots [slot_offset, slot_offset + largest_index] of the
@@ -785,12 +808,22 @@ int launch_move(espic_ctx* ctx, const float* grid, const float* mask, const floa
     a.prefetch_units = prefetch_env < 0 ? (a.staged ? 2 : 1) : (prefetch_env == 0 ? (1 << 28) : prefetch_env);
     int* flags = nullptr;
     if (!use_smem) {
-        rc = ensure(ctx, ctx->dv_table, (size_t)n_points * sizeof(float) + 64, "kick table");
+        // [16 ints: flag pair A, flag pair B (zeroed at allocation / by the epilogues)][table A][table B]
+        const size_t n_tab = ((size_t)n_points + 63) & ~(size_t)63;
+        rc = ensure(ctx, ctx->dv_table, (16 + 2 * n_tab) * sizeof(float), "kick tables");
         if (rc) return rc;
-        flags = (int*)ctx->dv_table.ptr;  // first 16 ints are flags (zeroed at allocation / by k_finish)
-        float* dvt = (float*)ctx->dv_table.ptr + 16;
-        k_build_dv<<<(n_points + 255) / 256, 256, 0, ctx->stream>>>(grid, mask, phi, n_points, qm, a_b, dt, dvt, flags);
-        ctx->launches++;
+        const int role = dv_plan ? dv_plan->role : 0;
+        flags = (int*)ctx->dv_table.ptr + (role == 2 ? 2 : 0);
+        float* dvt = (float*)ctx->dv_table.ptr + 16 + (role == 2 ? n_tab : 0);
+        if (role == 1) {
+            k_build_dv2<<<(n_points + 255) / 256, 256, 0, ctx->stream>>>(grid, mask, n_points, phi, qm, a_b, dt, dvt,
+                                                                         dv_plan->phi_b, dv_plan->qm_b, dv_plan->a_b_b,
+                                                                         dv_plan->dt_b, dvt + n_tab, flags);
+            ctx->launches++;
+        } else if (role == 0) {
+            k_build_dv<<<(n_points + 255) / 256, 256, 0, ctx->stream>>>(grid, mask, phi, n_points, qm, a_b, dt, dvt, flags);
+            ctx->launches++;
+        }
         a.dv_global = dvt;
         a.flags_global = flags;
     }

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+( timeout 1500 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -3
 for i in 1 2; do
 ( timeout 900 python bench.py --no-host-arrays --no-cpu-baseline ) 2>/dev/null | tail -1 | python -c "
 import json,sys
