@@ -628,6 +628,8 @@ class Simulation:
         for every in self.sort_intervals.values():
             if every:
                 n = min(n, every - k % every)
+        if not c.periodic_particles:
+            n = min(n, 4096)   # the device control block of an injecting stretch holds 4096 steps' counts
         return n
 
     def _run_native(self, n: int) -> None:

@@ -104,7 +104,11 @@ def test_native_run_stretch_longer_than_the_control_block():
         sim = Simulation(SimConfig(**cfg))
         sim.init_synthetic()
         sim.initialize()
-        sim.native_run = native
-        sim.run(4300, check_every=0)
+        if native:
+            sim._run_native(4300)          # one C call (run() itself would cut the stretch at 4096 steps)
+            sim.check_status()
+        else:
+            sim.native_run = False
+            sim.run(4300, check_every=0)
         sims.append(sim)
     _same(sims[1], sims[0])
