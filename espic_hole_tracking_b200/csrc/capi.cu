@@ -492,6 +492,19 @@ static int pic_step_impl(espic_ctx* ctx, const espic_step_args* a, int* track_cu
     // own counts, the tag and the sampler's call counter from the control block, and the species injected last
     // moves the block on to the next step
     const int last_injecting = n_inj[1] > 0 ? 1 : 0;
+    if (n_inj[0] > 0 && n_inj[1] > 0 && tags[0] && tags[1] && acc[0] && acc[1]) {   // fused deposit: a plane per species
+        const char* e = getenv("ESPIC_PAIRED_INJECT");   // tuning / test knob; 0 = one sample and one commit launch per species
+        if (!e || atoi(e) != 0) {
+            InjectPairSpecies ps[2];
+            for (int i = 0; i < 2; ++i) {
+                const espic_species* s = sp[i];
+                ps[i] = InjectPairSpecies{n_inj[i], v_th[i], v_d[i], tags[i], s->particles, s->particle_storage_length,
+                                          s->empty_slots, s->current_empty_slot, s->largest_index, s->density, acc[i]};
+            }
+            return launch_inject_pair(ctx, ps, a->grid, a->n_points, a->inject_dt, a->background_density, a->a_b,
+                                      a->step_index, a->inject_by_side, inject_ctl, kCtlMaxSteps);
+        }
+    }
     for (int i = 0; i < 2; ++i) {
         if (n_inj[i] <= 0) continue;
         const InjectCtl ic{inject_ctl, i, kCtlMaxSteps, i == last_injecting ? 1 : 0};
@@ -596,8 +609,9 @@ int espic_pic_run(espic_ctx* ctx, const espic_step_args* first, const espic_run_
                 if (nmax[s] > 0) nmax[s] = (nmax[s] + 1023) & ~1023;
             const int big = nmax[0] > nmax[1] ? nmax[0] : nmax[1];
             int rc = ensure(ctx, ctx->run_ctl, (size_t)(16 + 2 * kCtlMaxSteps) * sizeof(int), "step control block");
-            if (!rc) rc = ensure(ctx, ctx->rng_ws, (size_t)2 * ((big + 63) & ~63) * sizeof(float), "injection random inputs");
-            if (!rc) rc = ensure(ctx, ctx->inject_ws, 64 + ((size_t)big / 128 + 2) * sizeof(int), "inject workspace");
+            // sized for the paired launch (both species' random inputs and counters side by side)
+            if (!rc) rc = ensure(ctx, ctx->rng_ws, (size_t)4 * ((big + 63) & ~63) * sizeof(float), "injection random inputs");
+            if (!rc) rc = ensure(ctx, ctx->inject_ws, 2 * (48 + (size_t)big / 128) * sizeof(int), "inject workspace");
             if (rc) return rc;
             ctl = (int*)ctx->run_ctl.ptr;
             const int* src[2] = {r->n_inject_ions, r->n_inject_electrons};

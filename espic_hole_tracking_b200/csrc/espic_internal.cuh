@@ -321,6 +321,20 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
                   const float* vel, const float* uni, float a_b, int k, int* hist, float* particles,
                   int storage, int* empty_slots, int* top, int* largest, float* density, bool classified = false,
                   unsigned long long* acc_fused = nullptr, int by_side = 0, const InjectCtl* ctl = nullptr);
+struct InjectPairSpecies {
+    int n_inject;
+    float v_th, v_d;
+    int* hist;
+    float* particles;
+    int storage;
+    int* empty_slots;
+    int* top;
+    int* largest;
+    float* density;
+    unsigned long long* acc_fused;
+};
+int launch_inject_pair(espic_ctx* ctx, const InjectPairSpecies sp[2], const float* grid, int n_points, float dt, float bg,
+                       float a_b, int k, int by_side, int* ctl, int ctl_stride);
 int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d, float* vel, float* uni,
                              const float* grid, int n_points, float dt, float bg, float a_b,
                              const InjectCtl* ctl = nullptr);

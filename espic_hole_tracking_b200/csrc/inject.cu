@@ -235,10 +235,9 @@ __global__ void k_inject_classify(const InjectArgs a) {
 // velocities are written out for the commit kernel, the bad-index count goes to ws[0].
 constexpr int kSampleThreads = 128;
 
-__global__ void __launch_bounds__(kSampleThreads) k_sample_classify(const InjectArgs a, const SamplerConsts k,
-                                                                    float* __restrict__ uni_out, float* __restrict__ vel_out,
-                                                                    unsigned long long seed, unsigned long long call_uni,
-                                                                    unsigned long long call_vel) {
+__device__ __forceinline__ void sample_classify_body(const InjectArgs& a, const SamplerConsts& k, float* __restrict__ uni_out,
+                                                     float* __restrict__ vel_out, unsigned long long seed,
+                                                     unsigned long long call_uni, unsigned long long call_vel, int bid, int nb) {
     const Geom g = make_geom(a.grid, a.n_points);
     Philox ph{{(uint32_t)seed, (uint32_t)(seed >> 32)}};
     int bad = 0;
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample_classify(const Inject
     call_uni = st.call_uni;
     call_vel = st.call_vel;
     const int n_chunks = (st.n_inject + kSampleThreads - 1) / kSampleThreads;
-    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {  // uniform trip count per CTA
+    for (int chunk = bid; chunk < n_chunks; chunk += nb) {  // uniform trip count per CTA
         const int l = chunk * kSampleThreads + threadIdx.x;
         int left = 0;
         if (l < st.n_inject) {
@@ -262,6 +261,33 @@ __global__ void __launch_bounds__(kSampleThreads) k_sample_classify(const Inject
     }
     bad = __syncthreads_count(bad);
     if (threadIdx.x == 0 && bad) atomicAdd(a.ws, bad);
+}
+
+__global__ void __launch_bounds__(kSampleThreads) k_sample_classify(const InjectArgs a, const SamplerConsts k,
+                                                                    float* __restrict__ uni_out, float* __restrict__ vel_out,
+                                                                    unsigned long long seed, unsigned long long call_uni,
+                                                                    unsigned long long call_vel) {
+    sample_classify_body(a, k, uni_out, vel_out, seed, call_uni, call_vel, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Both species of a step in one launch: the first `blocks` CTAs of the grid work for job 0 (the ions), the rest for
+// job 1.  Each job has its own outputs, counters and sampler calls -- exactly what two launches would produce.
+struct SampleJob {
+    InjectArgs a;
+    SamplerConsts k;
+    float* uni;
+    float* vel;
+    unsigned long long call_uni, call_vel;
+    int blocks;
+};
+
+__global__ void __launch_bounds__(kSampleThreads) k_sample_classify2(const __grid_constant__ SampleJob j0,
+                                                                     const __grid_constant__ SampleJob j1,
+                                                                     unsigned long long seed) {
+    if ((int)blockIdx.x < j0.blocks)
+        sample_classify_body(j0.a, j0.k, j0.uni, j0.vel, seed, j0.call_uni, j0.call_vel, (int)blockIdx.x, j0.blocks);
+    else
+        sample_classify_body(j1.a, j1.k, j1.uni, j1.vel, seed, j1.call_uni, j1.call_vel, (int)blockIdx.x - j0.blocks, j1.blocks);
 }
 
 __device__ __forceinline__ void deposit_injected(const Geom& g, const Injected& p, unsigned long long* acc) {
@@ -347,7 +373,7 @@ __device__ __forceinline__ void inject_finish(const InjectArgs& a, bool everywhe
 // assignment (left from the bottom of the popped range, right from the top) a shortfall of left-wall slots
 // -- (removed - injected)/2 per step while the population falls -- still put left-wall entrants into
 // right-wall slots, and the two segments that collected them ran 6x longer than the others.
-__global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ InjectArgs a) {
+__device__ __forceinline__ void inject_commit_body(const InjectArgs& a, const int bid, const int nb) {
     __shared__ unsigned s_wall[2 * kWallNodes];
     __shared__ int s_last;
     __shared__ int s_scan[8], s_scan2[8];
@@ -365,8 +391,8 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
         // contiguous runs of 256-particle rounds per CTA, so that the left-wall rank of a round is the rank
         // of the previous one plus its count
         const int n_rounds = (n_inject + 255) / 256;
-        const int per_cta = (n_rounds + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int r0 = min((int)blockIdx.x * per_cta, n_rounds), r1 = min(r0 + per_cta, n_rounds);
+        const int per_cta = (n_rounds + nb - 1) / nb;
+        const int r0 = min(bid * per_cta, n_rounds), r1 = min(r0 + per_cta, n_rounds);
         int base_left = 0, total_left = 0;
         if (a.by_side && r0 < r1) {
             // particles entering at the left wall in front of this CTA's first round, and in all (two sampler chunks per round)
@@ -456,7 +482,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
                 atomicAdd(a.acc + node, (unsigned long long)v);
             }
         }
-    } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    } else if (bid == 0 && threadIdx.x == 0) {
         // replay of the reference's sequential loop (only when a bad left_index occurred)
         int top = top0, last = *a.largest;
         for (int l = 0; l < n_inject; ++l) {
@@ -486,7 +512,7 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
     // CTA has read it, the accumulators only once every CTA has flushed)
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u;
     __syncthreads();
     if (s_last) {
         __threadfence();
@@ -495,21 +521,50 @@ __global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ I
     }
 }
 
+__global__ void __launch_bounds__(256) k_inject_commit(const __grid_constant__ InjectArgs a) {
+    inject_commit_body(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Both species of a step in one launch (see k_sample_classify2): the first blocks0 CTAs commit job 0, the rest job 1,
+// each with its own store, counters and ticket.  In a replayed graph the last CTA of the whole grid to finish moves
+// the control block on to the next step (every CTA has read it by then).
+__global__ void __launch_bounds__(256) k_inject_commit2(const __grid_constant__ InjectArgs a0, const __grid_constant__ InjectArgs a1,
+                                                        int blocks0, unsigned* joint_ticket) {
+    const bool second = (int)blockIdx.x >= blocks0;
+    const InjectArgs& a = second ? a1 : a0;   // grid constants: their addresses can be taken
+    inject_commit_body(a, second ? (int)blockIdx.x - blocks0 : (int)blockIdx.x, second ? (int)gridDim.x - blocks0 : blocks0);
+    if (a0.ctl) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(joint_ticket, 1u) == gridDim.x - 1) {
+            int* ctl = a0.ctl;
+            const int i = ctl[1];
+            unsigned long long* calls = reinterpret_cast<unsigned long long*>(ctl + 2);
+            *calls += (ctl[16 + i] > 0 ? 2ull : 0ull) + (ctl[16 + a0.ctl_stride + i] > 0 ? 2ull : 0ull);
+            ctl[0] += 1;
+            ctl[1] = i + 1;
+            *joint_ticket = 0u;
+        }
+    }
+}
+
 static unsigned long long rng_key(espic_ctx* ctx);
 
+// Ints of workspace one injection call needs: [16 counters][one int per sampler chunk: entrants at the left wall].
+static size_t inject_ws_ints(int n_inject) { return (16 + (size_t)n_inject / kSampleThreads + 2 + 15) & ~(size_t)15; }
+
 static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const float* grid, int n_points, float dt,
-                            float bg, float a_b) {
+                            float bg, float a_b, size_t ws_offset_ints = 0, int ticket_slot = 8) {
     if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
     int rc = ensure_acc(ctx, n_points);
     if (rc) return rc;
-    // [16 ints of counters][one int per sampler chunk: particles entering at the left wall]
-    rc = ensure(ctx, ctx->inject_ws, 64 + ((size_t)n_inject / kSampleThreads + 2) * sizeof(int), "inject workspace");
+    rc = ensure(ctx, ctx->inject_ws, (ws_offset_ints + inject_ws_ints(n_inject)) * sizeof(int), "inject workspace");
     if (rc) return rc;
     a.grid = grid;
     a.acc = ctx->acc;
     a.status = ctx->status;
-    a.ws = (int*)ctx->inject_ws.ptr;
-    a.ticket = (unsigned*)(ctx->status + 8);
+    a.ws = (int*)ctx->inject_ws.ptr + ws_offset_ints;
+    a.ticket = (unsigned*)(ctx->status + ticket_slot);
     a.n_inject = n_inject;
     a.n_points = n_points;
     a.dt = dt;
@@ -548,7 +603,7 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
     a.k = k;
     // assignment by wall needs the per-chunk counts the device sampler leaves behind (rng_sample_for_injection)
     a.by_side = (by_side && classified) ? 1 : 0;
-    a.left_count = (int*)ctx->inject_ws.ptr + 16;
+    a.left_count = a.ws + 16;
     int grid_dim = (n_inject + 255) / 256;
     if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
     if (!classified) {
@@ -582,12 +637,85 @@ int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d
         call_uni = ctx->rng_consumed++;
         call_vel = ctx->rng_consumed++;
     }
-    a.left_count = (int*)ctx->inject_ws.ptr + 16;
+    a.left_count = a.ws + 16;
     int grid_dim = (n_inject + kSampleThreads - 1) / kSampleThreads;
     if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
     k_sample_classify<<<grid_dim, kSampleThreads, 0, ctx->stream>>>(a, sampler_consts(v_th, v_d), uni, vel, key, call_uni, call_vel);
     ctx->launches++;
     return check_cuda(ctx, cudaGetLastError(), "k_sample_classify launch");
+}
+
+// Sampling and commit of BOTH species of a step in two launches instead of four (espic_pic_step with the device
+// sampler, both counts positive): same values, same slots, same deposit as the per-species calls -- each species
+// keeps its own random inputs, counters and ticket; only the launches are shared.
+int launch_inject_pair(espic_ctx* ctx, const InjectPairSpecies sp[2], const float* grid, int n_points, float dt, float bg,
+                       float a_b, int k, int by_side, int* ctl, int ctl_stride) {
+    const unsigned long long key = rng_key(ctx);
+    // workspace: [species 0 block][species 1 block]; random inputs: [uni0 | vel0 | uni1 | vel1]
+    const size_t ws0 = inject_ws_ints(sp[0].n_inject);
+    size_t pad[2], off = 0;
+    for (int s = 0; s < 2; ++s) pad[s] = ((size_t)sp[s].n_inject + 63) & ~(size_t)63;
+    int rc = ensure(ctx, ctx->rng_ws, 2 * (pad[0] + pad[1]) * sizeof(float), "injection random inputs");
+    if (rc) return rc;
+    SampleJob job[2];
+    InjectArgs ca[2];
+    for (int s = 0; s < 2; ++s) {
+        InjectArgs a{};
+        rc = fill_inject_args(ctx, a, sp[s].n_inject, grid, n_points, dt, bg, a_b, s ? ws0 : 0, s ? 13 : 8);
+        if (rc) return rc;
+        a.left_count = a.ws + 16;
+        if (ctl) {
+            a.ctl = ctl;
+            a.ctl_species = s;
+            a.ctl_stride = ctl_stride;
+            a.ctl_advance = 0;   // the joint ticket of k_inject_commit2 advances the block
+        }
+        float* uni = (float*)ctx->rng_ws.ptr + off;
+        float* vel = uni + pad[s];
+        off += 2 * pad[s];
+        job[s].a = a;
+        job[s].k = sampler_consts(sp[s].v_th, sp[s].v_d);
+        job[s].uni = uni;
+        job[s].vel = vel;
+        job[s].call_uni = job[s].call_vel = 0ull;
+        if (!ctl) {  // same order as two calls: ions' fractions, ions' velocities, electrons' fractions, electrons' velocities
+            job[s].call_uni = ctx->rng_consumed++;
+            job[s].call_vel = ctx->rng_consumed++;
+        }
+        int blocks = (sp[s].n_inject + kSampleThreads - 1) / kSampleThreads;
+        if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+        job[s].blocks = blocks;
+        // commit arguments
+        a.vel = vel;
+        a.uni = uni;
+        a.px = sp[s].particles;
+        a.pv = sp[s].particles + sp[s].storage;
+        a.hist = sp[s].hist;
+        a.empty_slots = sp[s].empty_slots;
+        a.top = sp[s].top;
+        a.largest = sp[s].largest;
+        a.density = sp[s].acc_fused ? nullptr : sp[s].density;
+        if (sp[s].acc_fused) a.acc = sp[s].acc_fused;
+        a.k = k;
+        a.by_side = by_side ? 1 : 0;
+        ca[s] = a;
+    }
+    // the two species' workspace blocks are fixed only now (the second fill may have grown the buffer)
+    for (int s = 0; s < 2; ++s) {
+        int* ws = (int*)ctx->inject_ws.ptr + (s ? ws0 : 0);
+        job[s].a.ws = ca[s].ws = ws;
+        job[s].a.left_count = ca[s].left_count = ws + 16;
+    }
+    k_sample_classify2<<<job[0].blocks + job[1].blocks, kSampleThreads, 0, ctx->stream>>>(job[0], job[1], key);
+    ctx->launches++;
+    int cb[2];
+    for (int s = 0; s < 2; ++s) {
+        int g = (sp[s].n_inject + 255) / 256;
+        cb[s] = g < ctx->sm_count ? g : ctx->sm_count;
+    }
+    k_inject_commit2<<<cb[0] + cb[1], 256, 0, ctx->stream>>>(ca[0], ca[1], cb[0], (unsigned*)(ctx->status + 14));
+    ctx->launches++;
+    return check_cuda(ctx, cudaGetLastError(), "paired inject launch");
 }
 
 // ---- sampler front ends -----------------------------------------------------------------------

@@ -112,3 +112,27 @@ def test_native_run_stretch_longer_than_the_control_block():
             sim.run(4300, check_every=0)
         sims.append(sim)
     _same(sims[1], sims[0])
+
+
+def test_paired_injection_launches_equal_per_species_launches(monkeypatch):
+    """Both species of a wall-bounded step are sampled by one launch and committed by one launch
+    (k_sample_classify2 / k_inject_commit2); ESPIC_PAIRED_INJECT=0 gives the four per-species launches.  Same
+    sampler calls, same slots, same deposit: the whole state agrees bit for bit.  (The simulations share the
+    default context and its sampler, re-seeded by each constructor: one after the other, not interleaved.)"""
+    from espic_hole_tracking_b200.simulation import SimConfig, Simulation
+    cfg = SimConfig(n_steps=40, n_particles=80_000, n_cells=512, periodic_particles=False, track_hole=True,
+                    initial_transient_steps=3)
+    sims, launches = [], []
+    for paired in ("1", "0"):
+        monkeypatch.setenv("ESPIC_PAIRED_INJECT", paired)
+        sim = Simulation(cfg)
+        sim.init_synthetic()
+        sim.initialize()
+        sim.native_run = False
+        l0 = sim.ctx.launch_count()
+        sim.run(15)
+        launches.append(sim.ctx.launch_count() - l0)
+        sims.append(sim)
+    assert launches[1] - launches[0] == 2 * 15, launches
+    _same(sims[0], sims[1])
+    assert int(sims[0].electrons.tags.max()) == 14
