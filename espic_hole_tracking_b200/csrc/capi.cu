@@ -605,13 +605,21 @@ int espic_pic_run(espic_ctx* ctx, const espic_step_args* first, const espic_run_
         if (r->n_steps > kCtlMaxSteps) {
             graphs = false;
         } else {
-            for (int s = 0; s < 2; ++s)
-                if (nmax[s] > 0) nmax[s] = (nmax[s] + 1023) & ~1023;
+            for (int s = 0; s < 2; ++s) {
+                if (nmax[s] <= 0) continue;
+                nmax[s] = (nmax[s] + 1023) & ~1023;
+                // a graph captured for a slightly larger bound serves this stretch too: no recapture because the
+                // stretch's maximum happened to fall on the other side of a multiple of 1024
+                for (const auto& g : ctx->step_graph) {
+                    const int have = s ? g.key.n_inject_electrons : g.key.n_inject_ions;
+                    if (g.exec && have >= nmax[s] && have <= nmax[s] + nmax[s] / 4 + 4096) nmax[s] = have;
+                }
+            }
             const int big = nmax[0] > nmax[1] ? nmax[0] : nmax[1];
             int rc = ensure(ctx, ctx->run_ctl, (size_t)(16 + 2 * kCtlMaxSteps) * sizeof(int), "step control block");
             // sized for the paired launch (both species' random inputs and counters side by side)
             if (!rc) rc = ensure(ctx, ctx->rng_ws, (size_t)4 * ((big + 63) & ~63) * sizeof(float), "injection random inputs");
-            if (!rc) rc = ensure(ctx, ctx->inject_ws, 2 * (48 + (size_t)big / 128) * sizeof(int), "inject workspace");
+            if (!rc) rc = ensure(ctx, ctx->inject_ws, (32 + 2 * (32 + (size_t)big / 128)) * sizeof(int), "inject workspace");
             if (rc) return rc;
             ctl = (int*)ctx->run_ctl.ptr;
             const int* src[2] = {r->n_inject_ions, r->n_inject_electrons};

@@ -550,21 +550,25 @@ __global__ void __launch_bounds__(256) k_inject_commit2(const __grid_constant__ 
 
 static unsigned long long rng_key(espic_ctx* ctx);
 
-// Ints of workspace one injection call needs: [16 counters][one int per sampler chunk: entrants at the left wall].
-static size_t inject_ws_ints(int n_inject) { return (16 + (size_t)n_inject / kSampleThreads + 2 + 15) & ~(size_t)15; }
+// Injection workspace: [16 counters of job 0][16 counters of job 1][left-wall counts per sampler chunk, job 0][..., job 1].
+// The counter blocks sit at FIXED offsets: they are state that must be zero between calls (a stale bad-index count
+// sends the commit kernel down the reference's sequential replay), so no layout of any call may place its per-chunk
+// counts on top of them.
+static size_t chunk_ints(int n_inject) { return ((size_t)n_inject / kSampleThreads + 2 + 15) & ~(size_t)15; }
 
 static int fill_inject_args(espic_ctx* ctx, InjectArgs& a, int n_inject, const float* grid, int n_points, float dt,
-                            float bg, float a_b, size_t ws_offset_ints = 0, int ticket_slot = 8) {
+                            float bg, float a_b, int job = 0, size_t left_offset_ints = 0) {
     if (n_points < 2) return fail(ctx, ESPIC_E_ARG, "n_points must be >= 2");
     int rc = ensure_acc(ctx, n_points);
     if (rc) return rc;
-    rc = ensure(ctx, ctx->inject_ws, (ws_offset_ints + inject_ws_ints(n_inject)) * sizeof(int), "inject workspace");
+    rc = ensure(ctx, ctx->inject_ws, (32 + left_offset_ints + chunk_ints(n_inject)) * sizeof(int), "inject workspace");
     if (rc) return rc;
     a.grid = grid;
     a.acc = ctx->acc;
     a.status = ctx->status;
-    a.ws = (int*)ctx->inject_ws.ptr + ws_offset_ints;
-    a.ticket = (unsigned*)(ctx->status + ticket_slot);
+    a.ws = (int*)ctx->inject_ws.ptr + 16 * job;
+    a.left_count = (int*)ctx->inject_ws.ptr + 32 + left_offset_ints;
+    a.ticket = (unsigned*)(ctx->status + (job ? 13 : 8));
     a.n_inject = n_inject;
     a.n_points = n_points;
     a.dt = dt;
@@ -603,7 +607,6 @@ int launch_inject(espic_ctx* ctx, int n_inject, const float* grid, int n_points,
     a.k = k;
     // assignment by wall needs the per-chunk counts the device sampler leaves behind (rng_sample_for_injection)
     a.by_side = (by_side && classified) ? 1 : 0;
-    a.left_count = a.ws + 16;
     int grid_dim = (n_inject + 255) / 256;
     if (grid_dim > 4 * ctx->sm_count) grid_dim = 4 * ctx->sm_count;
     if (!classified) {
@@ -637,7 +640,6 @@ int rng_sample_for_injection(espic_ctx* ctx, int n_inject, float v_th, float v_d
         call_uni = ctx->rng_consumed++;
         call_vel = ctx->rng_consumed++;
     }
-    a.left_count = a.ws + 16;
     int grid_dim = (n_inject + kSampleThreads - 1) / kSampleThreads;
     if (grid_dim > 8 * ctx->sm_count) grid_dim = 8 * ctx->sm_count;
     k_sample_classify<<<grid_dim, kSampleThreads, 0, ctx->stream>>>(a, sampler_consts(v_th, v_d), uni, vel, key, call_uni, call_vel);
@@ -652,7 +654,7 @@ int launch_inject_pair(espic_ctx* ctx, const InjectPairSpecies sp[2], const floa
                        float a_b, int k, int by_side, int* ctl, int ctl_stride) {
     const unsigned long long key = rng_key(ctx);
     // workspace: [species 0 block][species 1 block]; random inputs: [uni0 | vel0 | uni1 | vel1]
-    const size_t ws0 = inject_ws_ints(sp[0].n_inject);
+    const size_t left1 = chunk_ints(sp[0].n_inject);   // job 1's per-chunk counts sit behind job 0's
     size_t pad[2], off = 0;
     for (int s = 0; s < 2; ++s) pad[s] = ((size_t)sp[s].n_inject + 63) & ~(size_t)63;
     int rc = ensure(ctx, ctx->rng_ws, 2 * (pad[0] + pad[1]) * sizeof(float), "injection random inputs");
@@ -661,9 +663,8 @@ int launch_inject_pair(espic_ctx* ctx, const InjectPairSpecies sp[2], const floa
     InjectArgs ca[2];
     for (int s = 0; s < 2; ++s) {
         InjectArgs a{};
-        rc = fill_inject_args(ctx, a, sp[s].n_inject, grid, n_points, dt, bg, a_b, s ? ws0 : 0, s ? 13 : 8);
+        rc = fill_inject_args(ctx, a, sp[s].n_inject, grid, n_points, dt, bg, a_b, s, s ? left1 : 0);
         if (rc) return rc;
-        a.left_count = a.ws + 16;
         if (ctl) {
             a.ctl = ctl;
             a.ctl_species = s;
@@ -702,9 +703,9 @@ int launch_inject_pair(espic_ctx* ctx, const InjectPairSpecies sp[2], const floa
     }
     // the two species' workspace blocks are fixed only now (the second fill may have grown the buffer)
     for (int s = 0; s < 2; ++s) {
-        int* ws = (int*)ctx->inject_ws.ptr + (s ? ws0 : 0);
-        job[s].a.ws = ca[s].ws = ws;
-        job[s].a.left_count = ca[s].left_count = ws + 16;
+        int* base = (int*)ctx->inject_ws.ptr;
+        job[s].a.ws = ca[s].ws = base + 16 * s;
+        job[s].a.left_count = ca[s].left_count = base + 32 + (s ? left1 : 0);
     }
     k_sample_classify2<<<job[0].blocks + job[1].blocks, kSampleThreads, 0, ctx->stream>>>(job[0], job[1], key);
     ctx->launches++;

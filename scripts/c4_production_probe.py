@@ -11,15 +11,20 @@ cfg = SimConfig(n_steps=steps + 200, n_particles=n, n_cells=65536, periodic_part
                 extra_storage_factor=1.1, sort_interval_electrons=int(sort_e) if sort_e else None)
 sim = Simulation(cfg); sim.init_synthetic(); sim.initialize()
 print("sort intervals", sim.sort_intervals, "key_shift", sim.sort_key_shift, flush=True)
-for _ in range(100): sim.step()
+if os.environ.get("PROBE_WARM_RUN") == "1":
+    sim.run(100, check_every=0)
+else:
+    for _ in range(100): sim.step()
 e0 = sim.energies(); a0 = sim.n_active()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+l_before = sim.ctx.launch_count()
 torch.cuda.synchronize(); ev0.record()
 if os.environ.get("PROBE_RUN") == "1":
     sim.run(steps, check_every=0)   # stretches of steps from one host call, replayed from step graphs
 else:
     for _ in range(steps): sim.step()
 ev1.record(); torch.cuda.synchronize()
+print("launches in the timed region", sim.ctx.launch_count() - l_before, flush=True)
 ms = ev0.elapsed_time(ev1) / steps
 e1 = sim.energies(); a1 = sim.n_active()
 tot = a1["ions"] + a1["electrons"]
